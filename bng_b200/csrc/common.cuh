@@ -1,0 +1,391 @@
+// bng_b200 — device-side building blocks shared by every kernel:
+// table descriptors, the open-addressing hash, packet access, statistics and
+// event staging.  sm_100a only; no host fallback exists for anything here.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef unsigned long long u64;
+typedef uint32_t u32;
+typedef uint16_t u16;
+typedef uint8_t u8;
+
+// ---------------------------------------------------------------------------
+// Packed statistics vector.  One u64 per counter of the reference's four
+// stats structs, in declaration order, so a map lookup is a plain copy:
+//   antispoof_stats  bpf/antispoof.c:58-65      [ST_AS, +6)
+//   qos_stats        bpf/qos_ratelimit.c:53-58  [ST_QOS, +4)
+//   nat_stats        bpf/nat44.c:176-190        [ST_NAT, +13)
+//   dhcp_stats       bpf/maps.h:171-184         [ST_DHCP, +10)
+// followed by dataplane-internal diagnostics.
+// ---------------------------------------------------------------------------
+enum {
+    ST_AS = 0,
+    ST_AS_ALLOWED = 0, ST_AS_DROPPED, ST_AS_LOGGED, ST_AS_V4_VIOL, ST_AS_V6_VIOL, ST_AS_UNKNOWN_MAC,
+    ST_QOS = 6,
+    ST_QOS_PASS_PKTS = 6, ST_QOS_DROP_PKTS, ST_QOS_PASS_BYTES, ST_QOS_DROP_BYTES,
+    ST_NAT = 10,
+    ST_NAT_SNAT = 10, ST_NAT_DNAT, ST_NAT_HAIRPIN, ST_NAT_DROPPED, ST_NAT_PASSED, ST_NAT_CREATED,
+    ST_NAT_EXPIRED, ST_NAT_EXHAUST, ST_NAT_EIM_HIT, ST_NAT_EIM_MISS, ST_NAT_ALG, ST_NAT_CT_LOOKUPS, ST_NAT_CT_HITS,
+    ST_DHCP = 23,
+    ST_DHCP_TOTAL = 23, ST_DHCP_HIT, ST_DHCP_MISS, ST_DHCP_ERROR, ST_DHCP_EXPIRED, ST_DHCP_O82_PRESENT,
+    ST_DHCP_O82_ABSENT, ST_DHCP_BCAST, ST_DHCP_UCAST, ST_DHCP_VLAN,
+    ST_LRU_OVERFLOW = 33,
+    ST_EV_LOST_SPOOF = 34,
+    ST_EV_LOST_NATLOG = 35,
+    ST_TABLE_FULL = 36,
+    ST_COUNT = 40,
+};
+
+// ---------------------------------------------------------------------------
+// Open-addressing hash table.  Every slot starts with a 64-bit key word that
+// doubles as the slot's state: K_EMPTY / K_TOMB / K_BUSY are reserved values
+// (no frame can produce them and host updates carrying them are refused).
+// Keys shorter than 8 bytes are zero-extended; longer keys continue in the
+// following words.  The value sits at `voff`, verbatim in the reference's
+// layout, so device code addresses the reference's fields by offset.
+// ---------------------------------------------------------------------------
+#define K_EMPTY 0xFFFFFFFFFFFFFFFFull
+#define K_TOMB 0xFFFFFFFFFFFFFFFEull
+#define K_BUSY 0xFFFFFFFFFFFFFFFDull
+
+struct Tbl {
+    u8 *slots;
+    u32 *count;      // live entries
+    u32 mask;        // capacity - 1 (capacity is a power of two)
+    u32 slot_bytes;  // multiple of 32
+    u32 voff;        // value offset inside the slot
+    u32 max_entries; // the reference map's max_entries
+    u32 key_size;
+    u32 value_size;
+};
+
+struct LpmTbl { // BPF_MAP_TYPE_LPM_TRIE with a 4-byte address: {prefixlen, addr bytes, value}
+    u32 *ents;  // 3 x u32 per entry: prefixlen, addr (memory order), value
+    u32 *count;
+    u32 max_entries;
+};
+
+struct EvRing { // staged event records: {payload, u32 frame index, u32 batch seq}
+    u8 *buf;
+    u32 *count;
+    u32 cap;
+    u32 rec_bytes; // payload + 8, a multiple of 16
+    u32 lost_stat;
+    u32 pad;
+};
+
+struct DevCtx {
+    Tbl bindings;   // subscriber_bindings      u64 mac   -> 24 B
+    Tbl qos_eg;     // qos_egress               u32 ip    -> 32 B token_bucket (at slot+16)
+    Tbl qos_in;     // qos_ingress
+    Tbl sub_nat;    // subscriber_nat           u32 ip    -> 64 B
+    Tbl sessions;   // nat_sessions             16 B      -> 80 B
+    Tbl reverse;    // nat_reverse              16 B      -> 16 B
+    Tbl eim;        // eim_table                8 B       -> 32 B
+    Tbl hairpin;    // hairpin_ips              u32       -> u8
+    Tbl alg;        // alg_ports                u32       -> 8 B
+    Tbl sub_pools;  // subscriber_pools         u64 mac   -> 25 B
+    Tbl vlan_pools; // vlan_subscriber_pools    4 B       -> 25 B
+    Tbl cid_subs;   // circuit_id_subscribers   32 B      -> 25 B
+    Tbl ip_pools;   // ip_pools                 u32       -> 28 B
+    Tbl cid_map;    // circuit_id_map           u64       -> u64 (never read by a program)
+    LpmTbl ranges_v4;  // allowed_ranges_v4
+    LpmTbl priv_ranges; // nat_private_ranges (never read by a program)
+    u8 *as_config;     // antispoof_config[1]   8 B
+    u8 *nat_config;    // nat_config_map[1]     16 B
+    u8 *server_config; // server_config[1]      16 B
+    u8 *nat_pool;      // nat_pool[256]         16 B each (never read by a program)
+    u64 *stats;        // ST_COUNT counters
+    EvRing spoof_ev;   // spoof_events, payload 56 B
+    EvRing natlog_ev;  // nat_log_rb,   payload 40 B
+    u32 batch_seq;
+    u32 pad;
+};
+
+// one batch, device view
+struct DevBatch {
+    u8 *pkts;
+    const u32 *off16;
+    u32 *len;
+    u8 *verdict;
+    u32 *priority;
+    u32 n;
+    u32 stride;
+    u64 now;
+};
+
+// ---------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ u64 mix64(u64 x) {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
+}
+
+__host__ __device__ __forceinline__ u64 splitmix64(u64 x) {
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+
+__device__ __forceinline__ u16 bswap16(u16 x) { return (u16)((x << 8) | (x >> 8)); }
+__device__ __forceinline__ u32 bswap32(u32 x) { return __byte_perm(x, 0, 0x0123); }
+
+template <int KW>
+__device__ __forceinline__ u64 tbl_hash(const u64 *k) {
+    u64 h = 0x9e3779b97f4a7c15ull;
+#pragma unroll
+    for (int i = 0; i < KW; i++) h = mix64(h ^ k[i]);
+    return h;
+}
+
+__device__ __forceinline__ u8 *tbl_slot(const Tbl &t, u32 i) { return t.slots + (size_t)i * t.slot_bytes; }
+
+__device__ __forceinline__ u64 ld_vol64(const u8 *p) { return *(volatile const u64 *)p; }
+
+// Find the slot holding key k (KW 64-bit words), or nullptr.  VOL selects
+// L1-bypassing loads of the state word, needed in kernels that insert
+// concurrently.
+template <int KW, bool VOL>
+__device__ __forceinline__ u8 *tbl_find(const Tbl &t, const u64 *k) {
+    if (k[0] >= K_BUSY) return nullptr;
+    u32 i = (u32)tbl_hash<KW>(k) & t.mask;
+    for (u32 probe = 0; probe <= t.mask; probe++) {
+        u8 *s = tbl_slot(t, i);
+        u64 w0 = VOL ? ld_vol64(s) : *(const u64 *)s;
+        if (VOL) {
+            while (w0 == K_BUSY) {
+                __nanosleep(32);
+                w0 = ld_vol64(s);
+            }
+        }
+        if (w0 == K_EMPTY) return nullptr;
+        if (w0 == k[0]) {
+            bool eq = true;
+#pragma unroll
+            for (int j = 1; j < KW; j++) eq = eq && (((const u64 *)s)[j] == k[j]);
+            if (eq) return s;
+        }
+        i = (i + 1) & t.mask;
+    }
+    return nullptr;
+}
+
+// Find-or-claim.  Returns the slot; *created says whether this call claimed
+// it.  A claimed slot is left in the K_BUSY state with key words 1.. written:
+// the caller fills the value and then calls tbl_publish().  Returns nullptr
+// when the table is full (max_entries reached or no free slot).
+template <int KW>
+__device__ __forceinline__ u8 *tbl_find_or_claim(const Tbl &t, const u64 *k, bool *created) {
+    *created = false;
+    if (k[0] >= K_BUSY) return nullptr;
+    u32 i = (u32)tbl_hash<KW>(k) & t.mask;
+    int tomb = -1;
+    for (u32 probe = 0; probe <= t.mask;) {
+        u8 *s = tbl_slot(t, i);
+        u64 w0 = ld_vol64(s);
+        while (w0 == K_BUSY) {
+            __nanosleep(32);
+            w0 = ld_vol64(s);
+        }
+        if (w0 == k[0]) {
+            bool eq = true;
+#pragma unroll
+            for (int j = 1; j < KW; j++) eq = eq && (((volatile const u64 *)s)[j] == k[j]);
+            if (eq) return s;
+        }
+        if (w0 == K_TOMB && tomb < 0) tomb = (int)i;
+        if (w0 == K_EMPTY) {
+            u32 target = tomb >= 0 ? (u32)tomb : i;
+            u64 expect = tomb >= 0 ? K_TOMB : K_EMPTY;
+            u8 *ts = tbl_slot(t, target);
+            if (atomicAdd(t.count, 1u) >= t.max_entries) {
+                atomicSub(t.count, 1u);
+                return nullptr;
+            }
+            u64 old = atomicCAS((u64 *)ts, expect, K_BUSY);
+            if (old == expect) {
+#pragma unroll
+                for (int j = 1; j < KW; j++) ((u64 *)ts)[j] = k[j];
+                *created = true;
+                return ts;
+            }
+            // lost the race for that slot: undo the reservation and look again
+            atomicSub(t.count, 1u);
+            if (tomb >= 0) {
+                tomb = -1;
+                i = (u32)tbl_hash<KW>(k) & t.mask;
+                probe = 0;
+            }
+            continue; // re-examine the same slot (it may now hold our key)
+        }
+        i = (i + 1) & t.mask;
+        probe++;
+    }
+    return nullptr;
+}
+
+__device__ __forceinline__ void tbl_publish(u8 *slot, u64 k0) {
+    __threadfence();
+    *(volatile u64 *)slot = k0;
+}
+
+template <int KW>
+__device__ __forceinline__ bool tbl_erase(const Tbl &t, const u64 *k) {
+    u8 *s = tbl_find<KW, true>(t, k);
+    if (!s) return false;
+    u64 old = atomicCAS((u64 *)s, k[0], K_TOMB);
+    if (old != k[0]) return false;
+    atomicSub(t.count, 1u);
+    return true;
+}
+
+// longest-prefix match over 4 address bytes in memory order (byte 0 first),
+// as BPF_MAP_TYPE_LPM_TRIE compares them.  `addr` is the little-endian load of
+// those bytes.  Returns true when any entry with prefixlen <= maxlen matches.
+__device__ __forceinline__ bool lpm_match(const LpmTbl &t, u32 addr, u32 maxlen) {
+    u32 n = *t.count;
+    u32 a = bswap32(addr); // byte 0 becomes the most significant
+    for (u32 i = 0; i < n; i++) {
+        u32 pl = t.ents[3 * i];
+        if (pl > maxlen) continue;
+        u32 e = bswap32(t.ents[3 * i + 1]);
+        u32 m = pl == 0 ? 0u : (0xFFFFFFFFu << (32 - pl));
+        if (((a ^ e) & m) == 0) return true;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------
+// per-block statistics: counters accumulate in shared memory and are flushed
+// with one global atomic per non-zero counter per block.
+// ---------------------------------------------------------------------------
+struct BlockStats {
+    u64 v[ST_COUNT];
+};
+
+__device__ __forceinline__ void bstats_init(BlockStats &s) {
+    for (int i = threadIdx.x; i < ST_COUNT; i += blockDim.x) s.v[i] = 0;
+    __syncthreads();
+}
+__device__ __forceinline__ void bstats_add(BlockStats &s, int idx, u64 v) { atomicAdd(&s.v[idx], v); }
+__device__ __forceinline__ void bstats_flush(BlockStats &s, u64 *g) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < ST_COUNT; i += blockDim.x)
+        if (s.v[i]) atomicAdd(&g[i], s.v[i]);
+}
+
+// Warp-aggregated increment of a shared counter: one shared atomic per warp.
+__device__ __forceinline__ void bstats_inc_pred(BlockStats &s, int idx, bool pred) {
+    unsigned m = __ballot_sync(__activemask(), pred);
+    if (pred) {
+        int leader = __ffs(m) - 1;
+        if ((threadIdx.x & 31) == leader) atomicAdd(&s.v[idx], (u64)__popc(m));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// event staging
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ u8 *ev_reserve(const DevCtx &c, const EvRing &r, u32 frame_idx) {
+    u32 pos = atomicAdd(r.count, 1u);
+    if (pos >= r.cap) {
+        atomicSub(r.count, 1u);
+        atomicAdd(&c.stats[r.lost_stat], 1ull);
+        return nullptr;
+    }
+    u8 *rec = r.buf + (size_t)pos * r.rec_bytes; // 16-byte aligned payload first, tag last
+    *(uint2 *)(rec + r.rec_bytes - 8) = make_uint2(frame_idx, c.batch_seq);
+    return rec;
+}
+
+// ---------------------------------------------------------------------------
+// frame access.  Frames start on 16-byte boundaries; all multi-byte fields
+// are read the way the eBPF programs read them: little-endian loads of wire
+// bytes.  Even offsets are 2-byte aligned, so u16 accesses are always legal.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ u8 *frame_ptr(const DevBatch &b, u32 i) {
+    return b.pkts + (b.off16 ? (size_t)b.off16[i] * 16 : (size_t)i * b.stride);
+}
+__device__ __forceinline__ u16 rd16(const u8 *p, u32 off) { return *(const u16 *)(p + off); }
+__device__ __forceinline__ u32 rd32(const u8 *p, u32 off) {
+    return (u32)rd16(p, off) | ((u32)rd16(p, off + 2) << 16);
+}
+__device__ __forceinline__ void wr16(u8 *p, u32 off, u16 v) { *(u16 *)(p + off) = v; }
+__device__ __forceinline__ void wr32(u8 *p, u32 off, u32 v) {
+    wr16(p, off, (u16)v);
+    wr16(p, off + 2, (u16)(v >> 16));
+}
+
+// The first 64 bytes of a frame held in registers (16 little-endian words).
+struct Hdr64 {
+    u32 w[16];
+    __device__ __forceinline__ u8 b8(u32 off) const { return (u8)(w[off >> 2] >> ((off & 3) * 8)); }
+    __device__ __forceinline__ u16 b16(u32 off) const { // off even
+        return (u16)(w[off >> 2] >> ((off & 2) * 8));
+    }
+    __device__ __forceinline__ u32 b32(u32 off) const { // off even
+        return (off & 2) ? (u32)(w[off >> 2] >> 16) | (w[(off >> 2) + 1] << 16) : w[off >> 2];
+    }
+    __device__ __forceinline__ void s16(u32 off, u16 v) {
+        u32 sh = (off & 2) * 8;
+        w[off >> 2] = (w[off >> 2] & ~(0xFFFFu << sh)) | ((u32)v << sh);
+    }
+    __device__ __forceinline__ void s32(u32 off, u32 v) {
+        s16(off, (u16)v);
+        s16(off + 2, (u16)(v >> 16));
+    }
+};
+
+// Loads the 16-byte chunks of the frame that contain bytes < min(len, 64).
+__device__ __forceinline__ void hdr_load(Hdr64 &h, const u8 *p, u32 len) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if ((u32)c * 16 < len) v = *(const uint4 *)(p + c * 16);
+        h.w[4 * c + 0] = v.x;
+        h.w[4 * c + 1] = v.y;
+        h.w[4 * c + 2] = v.z;
+        h.w[4 * c + 3] = v.w;
+    }
+}
+__device__ __forceinline__ void hdr_store_chunk(const Hdr64 &h, u8 *p, int c) {
+    *(uint4 *)(p + c * 16) = make_uint4(h.w[4 * c], h.w[4 * c + 1], h.w[4 * c + 2], h.w[4 * c + 3]);
+}
+
+// MAC bytes [off, off+6) as the reference's big-endian u64 key
+// (bpf/antispoof.c:122-129, bpf/dhcp_fastpath.c:175-182).
+__device__ __forceinline__ u64 mac_key(const Hdr64 &h, u32 off) {
+    u64 k = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) k = (k << 8) | h.b8(off + i);
+    return k;
+}
+
+// RFC 1624-style incremental checksum helpers, op-for-op as bpf/nat44.c:378-398.
+__device__ __forceinline__ u16 csum_fold32(u32 c) {
+    c = (c & 0xffff) + (c >> 16);
+    c = (c & 0xffff) + (c >> 16);
+    return (u16)~c;
+}
+__device__ __forceinline__ u16 csum_upd32(u16 csum, u32 old_val, u32 new_val) {
+    u32 sum = ~((u32)csum) & 0xffff;
+    sum += ~old_val & 0xffff;
+    sum += ~(old_val >> 16) & 0xffff;
+    sum += new_val & 0xffff;
+    sum += new_val >> 16;
+    return csum_fold32(sum);
+}
+__device__ __forceinline__ u16 csum_upd16(u16 csum, u16 old_val, u16 new_val) {
+    u32 sum = ~((u32)csum) & 0xffff;
+    sum += ~(u32)old_val & 0xffff;
+    sum += (u32)new_val & 0xffff;
+    return csum_fold32(sum);
+}

@@ -1,0 +1,791 @@
+// bng_b200 — C-ABI layer (include/bng_b200.h): context, map registry with the
+// reference's map names / key / value layouts, control-plane map commands,
+// batch program runs, event drain.  Everything that touches table or frame
+// contents is a CUDA kernel; this file only moves bytes and launches.
+#include <errno.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/bng_b200.h"
+#include "kernels.h"
+
+namespace {
+
+enum Kind { KIND_HASH, KIND_ARRAY, KIND_STATS, KIND_LPM, KIND_EVENT };
+
+// bpf_map_type values the reference declares
+enum { T_HASH = 1, T_ARRAY = 2, T_PERF = 4, T_PERCPU_ARRAY = 6, T_LRU = 9, T_LPM = 11, T_RINGBUF = 27 };
+
+struct MapReg {
+    const char *name;
+    u32 type, key_size, value_size, max_entries;
+    Kind kind;
+    Tbl *tbl;          // KIND_HASH: descriptor inside dev
+    u8 **arr;          // KIND_ARRAY: device base pointer
+    int stat_base;     // KIND_STATS
+    LpmTbl *lpm;       // KIND_LPM
+    EvRing *ring;      // KIND_EVENT
+    u32 ev_payload;    // KIND_EVENT
+    std::vector<u32> lpm_host; // KIND_LPM: authoritative host copy (3 x u32 per entry)
+    std::vector<u8> ev_pending; // KIND_EVENT: ordered, capacity-filtered payloads not yet drained
+};
+
+thread_local std::string g_open_err;
+
+} // namespace
+
+struct bng_ctx {
+    std::mutex mu;
+    int device = 0;
+    DevCtx dev{};
+    Launcher L{};
+    std::vector<MapReg> maps;
+    std::vector<void *> allocs;
+    std::string err;
+    // staging for control-plane commands
+    u8 *io_dev = nullptr;
+    u8 *io_host = nullptr; // pinned
+    size_t io_bytes = 0;
+    // staging for BNG_MEM_HOST batches
+    u8 *hb_pkts = nullptr;
+    u32 *hb_off = nullptr, *hb_len = nullptr, *hb_prio = nullptr;
+    u8 *hb_verdict = nullptr;
+    size_t hb_arena = 0;
+    u32 hb_n = 0;
+    u64 lost_base[2] = {0, 0};
+};
+
+namespace {
+
+int fail(bng_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c)
+        c->err = buf;
+    else
+        g_open_err = buf;
+    return code;
+}
+
+#define CU(c, call)                                                                        \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess) return fail(c, -EIO, "%s: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+u32 pow2_at_least(u64 v) {
+    u64 p = 1;
+    while (p < v) p <<= 1;
+    return (u32)p;
+}
+
+int dev_alloc(bng_ctx *c, void **p, size_t bytes, int fill) {
+    CU(c, cudaMalloc(p, bytes ? bytes : 16));
+    c->allocs.push_back(*p);
+    CU(c, cudaMemset(*p, fill, bytes ? bytes : 16));
+    return 0;
+}
+
+int make_table(bng_ctx *c, Tbl *t, u32 key_size, u32 value_size, u32 voff, u32 max_entries) {
+    u32 cap = pow2_at_least(std::max<u64>(64, (u64)max_entries * 2));
+    t->mask = cap - 1;
+    t->voff = voff;
+    t->key_size = key_size;
+    t->value_size = value_size;
+    t->max_entries = max_entries;
+    t->slot_bytes = (voff + value_size + 31u) & ~31u;
+    int r = dev_alloc(c, (void **)&t->slots, (size_t)cap * t->slot_bytes, 0xFF);
+    if (r) return r;
+    return dev_alloc(c, (void **)&t->count, 16, 0);
+}
+
+int ensure_scratch(bng_ctx *c, u32 n) {
+    Scratch &s = c->L.s;
+    if (n <= s.cap) return 0;
+    u32 cap = std::max<u32>(n, 1024);
+    void **ptrs[] = {(void **)&s.key_a, (void **)&s.key_b, (void **)&s.val_a, (void **)&s.val_b, (void **)&s.qslot};
+    for (void **pp : ptrs) {
+        if (*pp) cudaFree(*pp);
+        CU(c, cudaMalloc(pp, (size_t)cap * 4));
+    }
+    if (s.pflag) cudaFree(s.pflag);
+    CU(c, cudaMalloc((void **)&s.pflag, cap));
+    if (s.cub_tmp) cudaFree(s.cub_tmp);
+    s.cub_tmp_bytes = sort_temp_bytes(cap);
+    CU(c, cudaMalloc(&s.cub_tmp, s.cub_tmp_bytes ? s.cub_tmp_bytes : 16));
+    s.cap = cap;
+    return 0;
+}
+
+int ensure_io(bng_ctx *c, size_t bytes) {
+    if (bytes <= c->io_bytes) return 0;
+    size_t nb = std::max<size_t>(bytes, 1 << 20);
+    if (c->io_dev) cudaFree(c->io_dev);
+    if (c->io_host) cudaFreeHost(c->io_host);
+    c->io_dev = nullptr;
+    c->io_host = nullptr;
+    c->io_bytes = 0;
+    CU(c, cudaMalloc((void **)&c->io_dev, nb));
+    CU(c, cudaMallocHost((void **)&c->io_host, nb));
+    c->io_bytes = nb;
+    return 0;
+}
+
+MapReg *get_map(bng_ctx *c, int id) {
+    if (!c || id < 0 || id >= (int)c->maps.size()) return nullptr;
+    return &c->maps[id];
+}
+
+void add_hash(bng_ctx *c, const char *name, u32 type, u32 ks, u32 vs, u32 max, Tbl *t) {
+    MapReg m{};
+    m.name = name; m.type = type; m.key_size = ks; m.value_size = vs; m.max_entries = max;
+    m.kind = KIND_HASH; m.tbl = t;
+    c->maps.push_back(m);
+}
+void add_array(bng_ctx *c, const char *name, u32 vs, u32 max, u8 **base) {
+    MapReg m{};
+    m.name = name; m.type = T_ARRAY; m.key_size = 4; m.value_size = vs; m.max_entries = max;
+    m.kind = KIND_ARRAY; m.arr = base;
+    c->maps.push_back(m);
+}
+void add_stats(bng_ctx *c, const char *name, u32 type, u32 vs, int base) {
+    MapReg m{};
+    m.name = name; m.type = type; m.key_size = 4; m.value_size = vs; m.max_entries = 1;
+    m.kind = KIND_STATS; m.stat_base = base;
+    c->maps.push_back(m);
+}
+void add_lpm(bng_ctx *c, const char *name, u32 max, LpmTbl *l) {
+    MapReg m{};
+    m.name = name; m.type = T_LPM; m.key_size = 8; m.value_size = 1; m.max_entries = max;
+    m.kind = KIND_LPM; m.lpm = l;
+    c->maps.push_back(m);
+}
+void add_event(bng_ctx *c, const char *name, u32 type, u32 ks, u32 vs, u32 max, EvRing *r, u32 payload) {
+    MapReg m{};
+    m.name = name; m.type = type; m.key_size = ks; m.value_size = vs; m.max_entries = max;
+    m.kind = KIND_EVENT; m.ring = r; m.ev_payload = payload;
+    c->maps.push_back(m);
+}
+
+int make_ring(bng_ctx *c, EvRing *r, u32 payload, u32 cap, u32 lost_stat) {
+    r->rec_bytes = (payload + 8 + 15u) & ~15u;
+    r->cap = cap;
+    r->lost_stat = lost_stat;
+    int e = dev_alloc(c, (void **)&r->buf, (size_t)cap * r->rec_bytes, 0);
+    if (e) return e;
+    return dev_alloc(c, (void **)&r->count, 16, 0);
+}
+
+int make_lpm(bng_ctx *c, LpmTbl *l, u32 max) {
+    l->max_entries = max;
+    int e = dev_alloc(c, (void **)&l->ents, (size_t)max * 12, 0);
+    if (e) return e;
+    return dev_alloc(c, (void **)&l->count, 16, 0);
+}
+
+// ---- control-plane commands on hash maps ----
+int hash_cmd(bng_ctx *c, MapReg *m, int op, const void *keys, void *vals, u64 n, u32 flags, int *first_err) {
+    const Tbl &t = *m->tbl;
+    const u64 chunk_max = 1u << 18;
+    *first_err = 0;
+    for (u64 done = 0; done < n; done += chunk_max) {
+        u64 k = std::min(chunk_max, n - done);
+        size_t kb = k * t.key_size, vb = k * t.value_size, rb = k * 4;
+        size_t koff = 0, voff = (kb + 255) & ~(size_t)255, roff = (voff + vb + 255) & ~(size_t)255;
+        int r = ensure_io(c, roff + rb);
+        if (r) return r;
+        memcpy(c->io_host + koff, (const u8 *)keys + done * t.key_size, kb);
+        if (op == TOP_UPDATE) memcpy(c->io_host + voff, (const u8 *)vals + done * t.value_size, vb);
+        size_t up = op == TOP_UPDATE ? voff + vb : kb;
+        CU(c, cudaMemcpyAsync(c->io_dev, c->io_host, up, cudaMemcpyHostToDevice, c->L.stream));
+        CU(c, run_table_op(c->L, t, op, c->io_dev + koff, c->io_dev + voff, (int *)(c->io_dev + roff), k, flags));
+        size_t dfrom = op == TOP_LOOKUP ? voff : roff;
+        CU(c, cudaMemcpyAsync(c->io_host + dfrom, c->io_dev + dfrom, roff + rb - dfrom, cudaMemcpyDeviceToHost, c->L.stream));
+        CU(c, cudaStreamSynchronize(c->L.stream));
+        const int *res = (const int *)(c->io_host + roff);
+        for (u64 i = 0; i < k; i++)
+            if (res[i] && !*first_err) *first_err = res[i];
+        if (op == TOP_LOOKUP) {
+            for (u64 i = 0; i < k; i++)
+                if (!res[i])
+                    memcpy((u8 *)vals + (done + i) * t.value_size, c->io_host + voff + i * t.value_size, t.value_size);
+        }
+    }
+    return 0;
+}
+
+int lpm_upload(bng_ctx *c, MapReg *m) {
+    u32 n = (u32)(m->lpm_host.size() / 3);
+    if (n) CU(c, cudaMemcpyAsync(m->lpm->ents, m->lpm_host.data(), (size_t)n * 12, cudaMemcpyHostToDevice, c->L.stream));
+    CU(c, cudaMemcpyAsync(m->lpm->count, &n, 4, cudaMemcpyHostToDevice, c->L.stream));
+    CU(c, cudaStreamSynchronize(c->L.stream));
+    return 0;
+}
+
+bool lpm_same(u32 pl, u32 a, u32 b) { // first pl bits equal, bytes in memory order
+    u32 x = __builtin_bswap32(a) ^ __builtin_bswap32(b);
+    u32 mask = pl == 0 ? 0u : (pl >= 32 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (32 - pl)));
+    return (x & mask) == 0;
+}
+
+} // namespace
+
+// ===========================================================================
+extern "C" {
+
+uint32_t bng_abi_version(void) { return BNG_ABI_VERSION; }
+
+const char *bng_last_error(bng_ctx *ctx) { return ctx ? ctx->err.c_str() : g_open_err.c_str(); }
+
+uint32_t bng_shard_of_mac(uint64_t mac_key, uint32_t world) {
+    if (world <= 1) return 0;
+    return (uint32_t)(splitmix64(mac_key) % world);
+}
+
+void *bng_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 16) != cudaSuccess) return nullptr;
+    return p;
+}
+void bng_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+int bng_close(bng_ctx *c) {
+    if (!c) return -EINVAL;
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        cudaSetDevice(c->device);
+        if (c->L.stream) cudaStreamSynchronize(c->L.stream);
+        for (void *p : c->allocs) cudaFree(p);
+        Scratch &s = c->L.s;
+        void *sp[] = {s.key_a, s.key_b, s.val_a, s.val_b, s.qslot, s.pflag, s.cub_tmp, s.counters,
+                      c->io_dev, c->hb_pkts, c->hb_off, c->hb_len, c->hb_prio, c->hb_verdict};
+        for (void *p : sp)
+            if (p) cudaFree(p);
+        if (c->io_host) cudaFreeHost(c->io_host);
+        if (c->L.stream) cudaStreamDestroy(c->L.stream);
+    }
+    delete c;
+    return 0;
+}
+
+bng_ctx *bng_open(const bng_open_opts *o) {
+    bng_open_opts opts;
+    memset(&opts, 0, sizeof(opts));
+    opts.device = -1;
+    if (o) memcpy(&opts, o, std::min<size_t>(sizeof(opts), o->struct_size ? o->struct_size : sizeof(opts)));
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        fail(nullptr, 0, "no CUDA device (%s): the bng_b200 dataplane has no CPU path",
+             e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return nullptr;
+    }
+    bng_ctx *c = new bng_ctx();
+    int dev = opts.device;
+    if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    c->device = dev;
+#define OPEN_CU(call)                                                          \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) {                                              \
+            fail(nullptr, 0, "%s: %s", #call, cudaGetErrorString(e__));        \
+            bng_close(c);                                                      \
+            return nullptr;                                                    \
+        }                                                                      \
+    } while (0)
+#define OPEN_R(call)                                 \
+    do {                                             \
+        if ((call) != 0) {                           \
+            g_open_err = c->err;                     \
+            bng_close(c);                            \
+            return nullptr;                          \
+        }                                            \
+    } while (0)
+    OPEN_CU(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    OPEN_CU(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) {
+        fail(nullptr, 0, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, prop.major, prop.minor);
+        bng_close(c);
+        return nullptr;
+    }
+    c->L.num_sms = prop.multiProcessorCount;
+    OPEN_CU(cudaStreamCreateWithFlags(&c->L.stream, cudaStreamNonBlocking));
+
+    u32 max_subs = opts.max_subscribers ? opts.max_subscribers : 1000000u;
+    u32 max_sess = opts.max_nat_sessions ? opts.max_nat_sessions : 4000000u;
+    u32 max_eim = opts.max_eim_mappings ? opts.max_eim_mappings : 2000000u;
+    u32 ev_cap = opts.event_capacity ? opts.event_capacity : (1u << 21);
+    u32 max_vlan = std::min<u32>(100000u, std::max<u32>(max_subs, 64));
+    DevCtx &d = c->dev;
+
+    OPEN_R(make_table(c, &d.bindings, 8, 24, 8, max_subs));
+    OPEN_R(make_table(c, &d.qos_eg, 4, 32, 16, max_subs));
+    OPEN_R(make_table(c, &d.qos_in, 4, 32, 16, max_subs));
+    OPEN_R(make_table(c, &d.sub_nat, 4, 64, 8, max_subs));
+    OPEN_R(make_table(c, &d.sessions, 16, 80, 16, max_sess));
+    OPEN_R(make_table(c, &d.reverse, 16, 16, 16, max_sess));
+    OPEN_R(make_table(c, &d.eim, 8, 32, 8, max_eim));
+    OPEN_R(make_table(c, &d.hairpin, 4, 1, 8, 1000));
+    OPEN_R(make_table(c, &d.alg, 4, 8, 8, 64));
+    OPEN_R(make_table(c, &d.sub_pools, 8, 25, 8, max_subs));
+    OPEN_R(make_table(c, &d.vlan_pools, 4, 25, 8, max_vlan));
+    OPEN_R(make_table(c, &d.cid_subs, 32, 25, 32, max_subs));
+    OPEN_R(make_table(c, &d.ip_pools, 4, 28, 8, 10000));
+    OPEN_R(make_table(c, &d.cid_map, 8, 8, 8, max_subs));
+    OPEN_R(make_lpm(c, &d.ranges_v4, 256));
+    OPEN_R(make_lpm(c, &d.priv_ranges, 64));
+    OPEN_R(dev_alloc(c, (void **)&d.as_config, 16, 0));
+    OPEN_R(dev_alloc(c, (void **)&d.nat_config, 16, 0));
+    OPEN_R(dev_alloc(c, (void **)&d.server_config, 16, 0));
+    OPEN_R(dev_alloc(c, (void **)&d.nat_pool, 256 * 16, 0));
+    OPEN_R(dev_alloc(c, (void **)&d.stats, ST_COUNT * 8, 0));
+    OPEN_R(make_ring(c, &d.spoof_ev, 56, ev_cap, ST_EV_LOST_SPOOF));
+    OPEN_R(make_ring(c, &d.natlog_ev, 40, ev_cap, ST_EV_LOST_NATLOG));
+    OPEN_CU(cudaMalloc((void **)&c->L.s.counters, 64));
+    OPEN_R(ensure_scratch(c, opts.max_batch ? opts.max_batch : (1u << 22)));
+    OPEN_R(ensure_io(c, 1 << 20));
+
+    // registry: the reference's map names, types, sizes (bpf/antispoof.c:71-119,
+    // bpf/qos_ratelimit.c:37-65, bpf/nat44.c:218-320, bpf/maps.h:99-234)
+    add_hash(c, "subscriber_bindings", T_HASH, 8, 24, max_subs, &d.bindings);
+    add_array(c, "antispoof_config", 8, 1, &d.as_config);
+    add_stats(c, "antispoof_stats", T_PERCPU_ARRAY, 48, ST_AS);
+    add_event(c, "spoof_events", T_PERF, 4, 4, 0, &d.spoof_ev, 56);
+    add_lpm(c, "allowed_ranges_v4", 256, &d.ranges_v4);
+    add_hash(c, "qos_egress", T_HASH, 4, 32, max_subs, &d.qos_eg);
+    add_hash(c, "qos_ingress", T_HASH, 4, 32, max_subs, &d.qos_in);
+    add_stats(c, "qos_stats_map", T_PERCPU_ARRAY, 32, ST_QOS);
+    add_hash(c, "nat_sessions", T_LRU, 16, 80, max_sess, &d.sessions);
+    add_hash(c, "nat_reverse", T_LRU, 16, 16, max_sess, &d.reverse);
+    add_hash(c, "eim_table", T_LRU, 8, 32, max_eim, &d.eim);
+    add_hash(c, "subscriber_nat", T_HASH, 4, 64, max_subs, &d.sub_nat);
+    add_array(c, "nat_pool", 16, 256, &d.nat_pool);
+    add_hash(c, "hairpin_ips", T_HASH, 4, 1, 1000, &d.hairpin);
+    add_array(c, "nat_config_map", 16, 1, &d.nat_config);
+    add_stats(c, "nat_stats_map", T_PERCPU_ARRAY, 104, ST_NAT);
+    add_event(c, "nat_log_rb", T_RINGBUF, 0, 0, 1u << 20, &d.natlog_ev, 40);
+    add_hash(c, "alg_ports", T_HASH, 4, 8, 64, &d.alg);
+    add_lpm(c, "nat_private_ranges", 64, &d.priv_ranges);
+    add_hash(c, "subscriber_pools", T_HASH, 8, 25, max_subs, &d.sub_pools);
+    add_hash(c, "vlan_subscriber_pools", T_HASH, 4, 25, max_vlan, &d.vlan_pools);
+    add_hash(c, "ip_pools", T_HASH, 4, 28, 10000, &d.ip_pools);
+    add_array(c, "server_config", 16, 1, &d.server_config);
+    add_stats(c, "stats_map", T_ARRAY, 80, ST_DHCP);
+    add_hash(c, "circuit_id_map", T_HASH, 8, 8, max_subs, &d.cid_map);
+    add_hash(c, "circuit_id_subscribers", T_HASH, 32, 25, max_subs, &d.cid_subs);
+    cudaError_t se = cudaStreamSynchronize(c->L.stream);
+    if (se != cudaSuccess) {
+        fail(nullptr, 0, "init: %s", cudaGetErrorString(se));
+        bng_close(c);
+        return nullptr;
+    }
+    return c;
+}
+
+// ---------------------------------------------------------------------------
+// maps
+// ---------------------------------------------------------------------------
+int bng_map_id(bng_ctx *c, const char *name) {
+    if (!c || !name) return -EINVAL;
+    for (size_t i = 0; i < c->maps.size(); i++)
+        if (!strcmp(c->maps[i].name, name)) return (int)i;
+    return -ENOENT;
+}
+
+int bng_map_get_info(bng_ctx *c, int map, bng_map_info *out) {
+    MapReg *m = get_map(c, map);
+    if (!m || !out) return -EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    out->type = m->type;
+    out->key_size = m->key_size;
+    out->value_size = m->value_size;
+    out->max_entries = m->max_entries;
+    out->count = m->max_entries;
+    if (m->kind == KIND_HASH) {
+        u32 cnt = 0;
+        CU(c, cudaMemcpyAsync(&cnt, m->tbl->count, 4, cudaMemcpyDeviceToHost, c->L.stream));
+        CU(c, cudaStreamSynchronize(c->L.stream));
+        out->count = cnt;
+    } else if (m->kind == KIND_LPM) {
+        out->count = m->lpm_host.size() / 3;
+    } else if (m->kind == KIND_EVENT) {
+        u32 cnt = 0;
+        CU(c, cudaMemcpyAsync(&cnt, m->ring->count, 4, cudaMemcpyDeviceToHost, c->L.stream));
+        CU(c, cudaStreamSynchronize(c->L.stream));
+        out->count = cnt + m->ev_pending.size() / m->ev_payload;
+    }
+    return 0;
+}
+
+int bng_map_update_batch(bng_ctx *c, int map, const void *keys, const void *values, uint64_t n, uint64_t flags) {
+    MapReg *m = get_map(c, map);
+    if (!m || !keys || !values) return -EINVAL;
+    if (flags > BNG_EXIST) return -EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    switch (m->kind) {
+    case KIND_HASH: {
+        int first = 0;
+        int r = hash_cmd(c, m, TOP_UPDATE, keys, (void *)values, n, (u32)flags, &first);
+        return r ? r : first;
+    }
+    case KIND_ARRAY:
+    case KIND_STATS:
+        for (u64 i = 0; i < n; i++) {
+            u32 idx = ((const u32 *)keys)[i];
+            if (idx >= m->max_entries) return -E2BIG;
+            if (flags == BNG_NOEXIST) return -EEXIST;
+            u8 *dst = m->kind == KIND_ARRAY ? *m->arr + (size_t)idx * m->value_size : (u8 *)(c->dev.stats + m->stat_base);
+            CU(c, cudaMemcpyAsync(dst, (const u8 *)values + i * m->value_size, m->value_size, cudaMemcpyHostToDevice,
+                                  c->L.stream));
+        }
+        CU(c, cudaStreamSynchronize(c->L.stream));
+        return 0;
+    case KIND_LPM:
+        for (u64 i = 0; i < n; i++) {
+            const u32 *k = (const u32 *)((const u8 *)keys + i * 8);
+            u32 pl = k[0], addr = k[1], val = ((const u8 *)values)[i];
+            if (pl > 32) return -EINVAL;
+            bool found = false;
+            for (size_t e = 0; e < m->lpm_host.size(); e += 3)
+                if (m->lpm_host[e] == pl && lpm_same(pl, m->lpm_host[e + 1], addr)) {
+                    if (flags == BNG_NOEXIST) return -EEXIST;
+                    m->lpm_host[e + 2] = val;
+                    found = true;
+                }
+            if (!found) {
+                if (flags == BNG_EXIST) return -ENOENT;
+                if (m->lpm_host.size() / 3 >= m->max_entries) return -ENOSPC;
+                m->lpm_host.insert(m->lpm_host.end(), {pl, addr, val});
+            }
+        }
+        return lpm_upload(c, m);
+    default:
+        return -EINVAL;
+    }
+}
+
+int bng_map_update(bng_ctx *c, int map, const void *key, const void *value, uint64_t flags) {
+    return bng_map_update_batch(c, map, key, value, 1, flags);
+}
+
+int bng_map_lookup(bng_ctx *c, int map, const void *key, void *value_out) {
+    MapReg *m = get_map(c, map);
+    if (!m || !key || !value_out) return -EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    switch (m->kind) {
+    case KIND_HASH: {
+        int first = 0;
+        int r = hash_cmd(c, m, TOP_LOOKUP, key, value_out, 1, 0, &first);
+        return r ? r : first;
+    }
+    case KIND_ARRAY:
+    case KIND_STATS: {
+        u32 idx = *(const u32 *)key;
+        if (idx >= m->max_entries) return -ENOENT;
+        const u8 *src = m->kind == KIND_ARRAY ? *m->arr + (size_t)idx * m->value_size : (const u8 *)(c->dev.stats + m->stat_base);
+        CU(c, cudaMemcpyAsync(value_out, src, m->value_size, cudaMemcpyDeviceToHost, c->L.stream));
+        CU(c, cudaStreamSynchronize(c->L.stream));
+        return 0;
+    }
+    case KIND_LPM: {
+        const u32 *k = (const u32 *)key;
+        u32 pl = std::min<u32>(k[0], 32), addr = k[1];
+        int best = -1;
+        for (size_t e = 0; e < m->lpm_host.size(); e += 3) {
+            u32 epl = m->lpm_host[e];
+            if (epl > pl) continue;
+            if (best >= 0 && epl <= m->lpm_host[best]) continue;
+            if (lpm_same(epl, m->lpm_host[e + 1], addr)) best = (int)e;
+        }
+        if (best < 0) return -ENOENT;
+        *(u8 *)value_out = (u8)m->lpm_host[best + 2];
+        return 0;
+    }
+    default:
+        return -EINVAL;
+    }
+}
+
+int bng_map_delete(bng_ctx *c, int map, const void *key) {
+    MapReg *m = get_map(c, map);
+    if (!m || !key) return -EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    if (m->kind == KIND_HASH) {
+        int first = 0;
+        int r = hash_cmd(c, m, TOP_DELETE, key, nullptr, 1, 0, &first);
+        return r ? r : first;
+    }
+    if (m->kind == KIND_LPM) {
+        const u32 *k = (const u32 *)key;
+        for (size_t e = 0; e < m->lpm_host.size(); e += 3)
+            if (m->lpm_host[e] == k[0] && lpm_same(k[0], m->lpm_host[e + 1], k[1])) {
+                m->lpm_host.erase(m->lpm_host.begin() + e, m->lpm_host.begin() + e + 3);
+                return lpm_upload(c, m);
+            }
+        return -ENOENT;
+    }
+    return -EINVAL; // arrays cannot be deleted from (kernel: -EINVAL)
+}
+
+int64_t bng_map_dump(bng_ctx *c, int map, void *keys_out, void *values_out, uint64_t cap) {
+    MapReg *m = get_map(c, map);
+    if (!m || !keys_out || !values_out) return -EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    if (m->kind == KIND_LPM) {
+        u64 n = std::min<u64>(cap, m->lpm_host.size() / 3);
+        for (u64 i = 0; i < n; i++) {
+            memcpy((u8 *)keys_out + i * 8, &m->lpm_host[3 * i], 8);
+            ((u8 *)values_out)[i] = (u8)m->lpm_host[3 * i + 2];
+        }
+        return (int64_t)n;
+    }
+    if (m->kind == KIND_ARRAY || m->kind == KIND_STATS) {
+        u64 n = std::min<u64>(cap, m->max_entries);
+        const u8 *src = m->kind == KIND_ARRAY ? *m->arr : (const u8 *)(c->dev.stats + m->stat_base);
+        for (u32 i = 0; i < n; i++) ((u32 *)keys_out)[i] = i;
+        CU(c, cudaMemcpyAsync(values_out, src, n * m->value_size, cudaMemcpyDeviceToHost, c->L.stream));
+        CU(c, cudaStreamSynchronize(c->L.stream));
+        return (int64_t)n;
+    }
+    if (m->kind != KIND_HASH) return -EINVAL;
+    if (cap == 0) return 0;
+    const Tbl &t = *m->tbl;
+    u8 *dk = nullptr, *dv = nullptr;
+    u32 *dc = nullptr;
+    CU(c, cudaMalloc((void **)&dk, cap * t.key_size));
+    cudaError_t e2 = cudaMalloc((void **)&dv, cap * t.value_size);
+    cudaError_t e3 = cudaMalloc((void **)&dc, 16);
+    int rc = 0;
+    u32 cnt = 0;
+    if (e2 != cudaSuccess || e3 != cudaSuccess) {
+        rc = fail(c, -ENOMEM, "dump: out of device memory");
+    } else {
+        cudaMemsetAsync(dc, 0, 16, c->L.stream);
+        cudaError_t e = run_table_dump(c->L, t, dk, dv, dc, cap);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&cnt, dc, 4, cudaMemcpyDeviceToHost, c->L.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->L.stream);
+        if (e == cudaSuccess && cnt) {
+            u64 n = std::min<u64>(cnt, cap);
+            e = cudaMemcpy(keys_out, dk, n * t.key_size, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(values_out, dv, n * t.value_size, cudaMemcpyDeviceToHost);
+            cnt = (u32)n;
+        }
+        if (e != cudaSuccess) rc = fail(c, -EIO, "dump: %s", cudaGetErrorString(e));
+    }
+    cudaFree(dk);
+    if (dv) cudaFree(dv);
+    if (dc) cudaFree(dc);
+    return rc ? rc : (int64_t)cnt;
+}
+
+// ---------------------------------------------------------------------------
+// programs
+// ---------------------------------------------------------------------------
+static const char *const k_prog_names[] = {
+    "antispoof_ingress",  // bpf/antispoof.c:188-189
+    "qos_egress_prog",    // bpf/qos_ratelimit.c:126-127
+    "qos_ingress_prog",   // bpf/qos_ratelimit.c:178-179
+    "nat44_egress",       // bpf/nat44.c:565-566
+    "nat44_ingress",      // bpf/nat44.c:805-806
+    "nat44_hairpin_xdp",  // bpf/nat44.c:951-952
+    "dhcp_fastpath_prog", // bpf/dhcp_fastpath.c:619-620
+    "pipeline_up",        // antispoof_ingress -> nat44_egress -> qos_ingress_prog (pre-NAT key)
+};
+enum { P_ANTISPOOF, P_QOS_EG, P_QOS_IN, P_NAT_EG, P_NAT_IN, P_NAT_HAIRPIN, P_DHCP, P_PIPE_UP, P_COUNT };
+
+int bng_prog_id(bng_ctx *c, const char *name) {
+    if (!c || !name) return -EINVAL;
+    for (int i = 0; i < P_COUNT; i++)
+        if (!strcmp(k_prog_names[i], name)) return i;
+    return -ENOENT;
+}
+
+static int dispatch(bng_ctx *c, int prog, const DevBatch &b) {
+    cudaError_t e;
+    switch (prog) {
+    case P_ANTISPOOF: e = run_antispoof(c->L, c->dev, b); break;
+    case P_QOS_EG: e = run_qos(c->L, c->dev, b, true); break;
+    case P_QOS_IN: e = run_qos(c->L, c->dev, b, false); break;
+    case P_NAT_EG: e = run_nat_egress(c->L, c->dev, b); break;
+    case P_NAT_IN: e = run_nat_ingress(c->L, c->dev, b); break;
+    case P_NAT_HAIRPIN: e = run_nat_hairpin_xdp(c->L, c->dev, b); break;
+    case P_DHCP: e = run_dhcp_fastpath(c->L, c->dev, b); break;
+    case P_PIPE_UP: e = run_pipeline_up(c->L, c->dev, b); break;
+    default: return -EINVAL;
+    }
+    if (e != cudaSuccess) return fail(c, -EIO, "launch %s: %s", k_prog_names[prog], cudaGetErrorString(e));
+    return 0;
+}
+
+int bng_prog_run(bng_ctx *c, int prog, bng_batch *bb) {
+    if (!c || !bb || prog < 0 || prog >= P_COUNT) return -EINVAL;
+    if (bb->n == 0) return 0;
+    if (!bb->pkts || !bb->len || !bb->verdict) return -EINVAL;
+    if (!bb->off16 && (bb->stride == 0 || (bb->stride & 15))) return -EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    int r = ensure_scratch(c, bb->n);
+    if (r) return r;
+    c->dev.batch_seq++;
+    DevBatch b;
+    b.n = bb->n;
+    b.stride = bb->stride;
+    b.now = bb->now_ns;
+    if (bb->mem == BNG_MEM_DEVICE) {
+        b.pkts = (u8 *)bb->pkts;
+        b.off16 = bb->off16;
+        b.len = bb->len;
+        b.verdict = bb->verdict;
+        b.priority = bb->priority;
+        return dispatch(c, prog, b);
+    }
+    if (bb->mem != BNG_MEM_HOST) return -EINVAL;
+    size_t arena = bb->off16 ? (size_t)bb->arena_bytes * 16 : (size_t)bb->n * bb->stride;
+    if (arena == 0) return -EINVAL;
+    cudaStream_t st = c->L.stream;
+    if (arena > c->hb_arena) {
+        if (c->hb_pkts) cudaFree(c->hb_pkts);
+        c->hb_pkts = nullptr;
+        c->hb_arena = 0;
+        CU(c, cudaMalloc((void **)&c->hb_pkts, arena));
+        c->hb_arena = arena;
+    }
+    if (bb->n > c->hb_n) {
+        void **pp[] = {(void **)&c->hb_off, (void **)&c->hb_len, (void **)&c->hb_prio, (void **)&c->hb_verdict};
+        for (void **p : pp) {
+            if (*p) cudaFree(*p);
+            *p = nullptr;
+        }
+        c->hb_n = 0;
+        CU(c, cudaMalloc((void **)&c->hb_off, (size_t)bb->n * 4));
+        CU(c, cudaMalloc((void **)&c->hb_len, (size_t)bb->n * 4));
+        CU(c, cudaMalloc((void **)&c->hb_prio, (size_t)bb->n * 4));
+        CU(c, cudaMalloc((void **)&c->hb_verdict, (size_t)bb->n));
+        c->hb_n = bb->n;
+    }
+    CU(c, cudaMemcpyAsync(c->hb_pkts, bb->pkts, arena, cudaMemcpyHostToDevice, st));
+    if (bb->off16) CU(c, cudaMemcpyAsync(c->hb_off, bb->off16, (size_t)bb->n * 4, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(c->hb_len, bb->len, (size_t)bb->n * 4, cudaMemcpyHostToDevice, st));
+    if (bb->priority) CU(c, cudaMemcpyAsync(c->hb_prio, bb->priority, (size_t)bb->n * 4, cudaMemcpyHostToDevice, st));
+    b.pkts = c->hb_pkts;
+    b.off16 = bb->off16 ? c->hb_off : nullptr;
+    b.len = c->hb_len;
+    b.verdict = c->hb_verdict;
+    b.priority = bb->priority ? c->hb_prio : nullptr;
+    r = dispatch(c, prog, b);
+    if (r) return r;
+    CU(c, cudaMemcpyAsync(bb->pkts, c->hb_pkts, arena, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaMemcpyAsync(bb->len, c->hb_len, (size_t)bb->n * 4, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaMemcpyAsync(bb->verdict, c->hb_verdict, (size_t)bb->n, cudaMemcpyDeviceToHost, st));
+    if (bb->priority) CU(c, cudaMemcpyAsync(bb->priority, c->hb_prio, (size_t)bb->n * 4, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+    return 0;
+}
+
+int bng_sync(bng_ctx *c) {
+    if (!c) return -EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    CU(c, cudaStreamSynchronize(c->L.stream));
+    return 0;
+}
+
+void *bng_stream(bng_ctx *c) { return c ? (void *)c->L.stream : nullptr; }
+
+// ---------------------------------------------------------------------------
+// events
+// ---------------------------------------------------------------------------
+uint32_t bng_event_size(bng_ctx *c, int map) {
+    MapReg *m = get_map(c, map);
+    return (m && m->kind == KIND_EVENT) ? m->ev_payload : 0;
+}
+
+int bng_events_drain(bng_ctx *c, int map, void *buf, uint64_t cap_records, uint64_t *n_out) {
+    MapReg *m = get_map(c, map);
+    if (!m || m->kind != KIND_EVENT || !n_out) return -EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    EvRing &r = *m->ring;
+    u32 cnt = 0;
+    CU(c, cudaMemcpyAsync(&cnt, r.count, 4, cudaMemcpyDeviceToHost, c->L.stream));
+    CU(c, cudaStreamSynchronize(c->L.stream));
+    if (cnt > r.cap) cnt = r.cap;
+    if (cnt) {
+        std::vector<u8> raw((size_t)cnt * r.rec_bytes);
+        CU(c, cudaMemcpy(raw.data(), r.buf, raw.size(), cudaMemcpyDeviceToHost));
+        CU(c, cudaMemsetAsync(r.count, 0, 4, c->L.stream));
+        CU(c, cudaStreamSynchronize(c->L.stream));
+        // emission order of the reference: batch order, then frame index
+        std::vector<u32> order(cnt);
+        for (u32 i = 0; i < cnt; i++) order[i] = i;
+        const u8 *base = raw.data();
+        u32 rb = r.rec_bytes;
+        std::sort(order.begin(), order.end(), [&](u32 a, u32 b) {
+            const u32 *ta = (const u32 *)(base + (size_t)a * rb + rb - 8);
+            const u32 *tb = (const u32 *)(base + (size_t)b * rb + rb - 8);
+            if (ta[1] != tb[1]) return ta[1] < tb[1];
+            return ta[0] < tb[0];
+        });
+        // BPF_MAP_TYPE_RINGBUF capacity: 8-byte header + payload rounded to 8;
+        // a reserve fails once producer-consumer distance would exceed size-1
+        u64 per = ((u64)m->ev_payload + 8 + 7) & ~7ull;
+        u64 used = (m->ev_pending.size() / m->ev_payload) * per;
+        for (u32 i = 0; i < cnt; i++) {
+            if (m->type == T_RINGBUF) {
+                if (used + per > (u64)m->max_entries - 1) continue; // bpf_ringbuf_reserve() == NULL
+                used += per;
+            }
+            const u8 *rec = base + (size_t)order[i] * rb;
+            m->ev_pending.insert(m->ev_pending.end(), rec, rec + m->ev_payload);
+        }
+    }
+    u64 have = m->ev_pending.size() / m->ev_payload;
+    u64 n = std::min<u64>(have, cap_records);
+    if (n && buf) memcpy(buf, m->ev_pending.data(), n * m->ev_payload);
+    if (n) m->ev_pending.erase(m->ev_pending.begin(), m->ev_pending.begin() + n * m->ev_payload);
+    *n_out = n;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// multi-GPU plumbing and diagnostics
+// ---------------------------------------------------------------------------
+int bng_stats_device_ptr(bng_ctx *c, void **dptr, uint32_t *n_u64) {
+    if (!c || !dptr) return -EINVAL;
+    *dptr = c->dev.stats;
+    if (n_u64) *n_u64 = ST_COUNT;
+    return 0;
+}
+
+uint64_t bng_launch_count(bng_ctx *c) { return c ? c->L.launches : 0; }
+
+static uint64_t read_stat(bng_ctx *c, int idx) {
+    if (!c) return 0;
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    u64 v = 0;
+    if (cudaMemcpyAsync(&v, c->dev.stats + idx, 8, cudaMemcpyDeviceToHost, c->L.stream) != cudaSuccess) return 0;
+    cudaStreamSynchronize(c->L.stream);
+    return v;
+}
+uint64_t bng_lru_overflow(bng_ctx *c) { return read_stat(c, ST_LRU_OVERFLOW); }
+uint64_t bng_events_lost(bng_ctx *c) { return read_stat(c, ST_EV_LOST_SPOOF) + read_stat(c, ST_EV_LOST_NATLOG); }
+
+} // extern "C"

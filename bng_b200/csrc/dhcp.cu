@@ -1,0 +1,295 @@
+// bng_b200 — dhcp_fastpath_prog as a batch kernel (bpf/dhcp_fastpath.c:619-813
+// with bpf/maps.h).  One thread per frame: parse Eth/(QinQ)/IPv4/UDP/BOOTP,
+// identify the subscriber (VLAN pair -> circuit-id -> chaddr), and rewrite the
+// request into an OFFER/ACK in place.  No state depends on frame order, so the
+// whole program is a single data-parallel pass; counters go through per-block
+// shared accumulators.
+#include "kernels.h"
+#include "progs.cuh"
+
+#define XDP_PASS_ 2
+#define XDP_TX_ 3
+
+// pool_assignment (packed, 25 B) at `a`: pool_id@0 allocated_ip@4 vlan_id@8
+// client_class@12 lease_expiry@13 flags@21  (bpf/maps.h:89-97)
+__device__ __forceinline__ u64 rd_u64_unaligned(const u8 *p) {
+    u64 v = 0;
+#pragma unroll
+    for (int i = 7; i >= 0; i--) v = (v << 8) | p[i];
+    return v;
+}
+
+__device__ __forceinline__ void zero_range(u8 *q, u32 n) { // q 2-byte aligned, n even
+    while (n >= 2 && ((uintptr_t)q & 15)) {
+        *(u16 *)q = 0;
+        q += 2;
+        n -= 2;
+    }
+    while (n >= 16) {
+        *(uint4 *)q = make_uint4(0, 0, 0, 0);
+        q += 16;
+        n -= 16;
+    }
+    while (n >= 2) {
+        *(u16 *)q = 0;
+        q += 2;
+        n -= 2;
+    }
+}
+
+__device__ __forceinline__ void put_opt32(u8 *o, int &off, u8 code, u32 v_le) { // value bytes in memory order
+    o[off++] = code;
+    o[off++] = 4;
+    o[off++] = (u8)v_le;
+    o[off++] = (u8)(v_le >> 8);
+    o[off++] = (u8)(v_le >> 16);
+    o[off++] = (u8)(v_le >> 24);
+}
+
+__device__ __forceinline__ int dhcp_one(const DevCtx &c, BlockStats &bs, u8 *p, u32 &len, u64 now) {
+    // ---- parse_packet_headers(), :352-428 ----
+    if (len < 14) return XDP_PASS_;
+    u32 proto = rd16(p, 12);
+    u32 l3 = 14, vlan_off = 0, vlan_id = 0, inner_id = 0;
+    bool tagged = false;
+    if (proto == 0x0081u || proto == 0xA888u) { // 802.1Q / 802.1ad
+        if (len < 18) return XDP_PASS_;
+        tagged = true;
+        vlan_id = bswap16(rd16(p, 14)) & 0x0FFF;
+        vlan_off = 4;
+        proto = rd16(p, 16);
+        l3 = 18;
+        bstats_add(bs, ST_DHCP_VLAN, 1);
+        if (proto == 0x0081u) {
+            if (len < 22) return XDP_PASS_;
+            inner_id = bswap16(rd16(p, 18)) & 0x0FFF;
+            vlan_off = 8;
+            proto = rd16(p, 20);
+            l3 = 22;
+        }
+    }
+    if (proto != ETH_P_IP_LE) return XDP_PASS_;
+    if (l3 + 20 > len) return XDP_PASS_;
+    if (p[l3 + 9] != 17) return XDP_PASS_;
+    u32 udp = l3 + (u32)(p[l3] & 0x0f) * 4;
+    if (udp + 8 > len) return XDP_PASS_;
+    if (rd16(p, udp + 2) != 0x4300u) return XDP_PASS_; // bpf_htons(67)
+    u32 dh = udp + 8;
+    if (dh + 240 > len) return XDP_PASS_;
+
+    // ---- :627-645 ----
+    if (p[dh] != 1) return XDP_PASS_;
+    if (rd32(p, dh + 236) != 0x63538263u) return XDP_PASS_; // bpf_htonl(0x63825363)
+    bstats_add(bs, ST_DHCP_TOTAL, 1);
+    u32 opts = dh + 240;
+    u32 msg_type = 0;
+    if (opts + 12 <= len) { // get_dhcp_msg_type(), :216-250
+        const u8 *o = p + opts;
+        if (o[0] == 53 && o[1] == 1) msg_type = o[2];
+        else if (o[1] == 53 && o[2] == 1) msg_type = o[3];
+        else if (o[3] == 53 && o[4] == 1) msg_type = o[5];
+        else if (o[4] == 53 && o[5] == 1) msg_type = o[6];
+        else if (o[5] == 53 && o[6] == 1) msg_type = o[7];
+        else if (o[6] == 53 && o[7] == 1) msg_type = o[8];
+    }
+    if (msg_type != 1 && msg_type != 3) {
+        bstats_add(bs, ST_DHCP_MISS, 1);
+        return XDP_PASS_;
+    }
+
+    // ---- subscriber lookup, :653-687 ----
+    const u8 *a = nullptr; // -> pool_assignment
+    if (tagged) {
+        u64 vk = (u64)(vlan_id | (inner_id << 16));
+        const u8 *s = tbl_find<1, false>(c.vlan_pools, &vk);
+        if (s) a = s + c.vlan_pools.voff;
+    }
+    if (!a && opts + 64 <= len) { // extract_circuit_id_fixed(), :267-323
+        const u8 *o = p + opts;
+        int cid_at = -1;
+        u32 cid_len = 0;
+        if (o[3] == 82) {
+            u32 l82 = o[4];
+            if (l82 >= 4 && opts + 5 + l82 <= len && o[5] == 1) {
+                u32 cl = o[6];
+                if (cl > 0 && cl <= 32 && opts + 7 + cl <= len) {
+                    cid_at = 7;
+                    cid_len = cl;
+                }
+            }
+        }
+        if (cid_at < 0) {
+            for (int pos = 12; pos < 20; pos++) {
+                if (o[pos] == 82 && opts + pos + 8 <= len) {
+                    u32 l82 = o[pos + 1];
+                    if (l82 >= 4 && o[pos + 2] == 1) {
+                        u32 cl = o[pos + 3];
+                        if (cl > 0 && cl <= 32 && opts + pos + 4 + cl <= len) {
+                            cid_at = pos + 4;
+                            cid_len = cl;
+                            break;
+                        }
+                    }
+                }
+            }
+        }
+        if (cid_at >= 0) {
+            u64 ck[4] = {0, 0, 0, 0};
+            for (u32 k = 0; k < cid_len; k++) ck[k >> 3] |= (u64)o[cid_at + k] << ((k & 7) * 8);
+            const u8 *s = tbl_find<4, false>(c.cid_subs, ck);
+            if (s) {
+                a = s + c.cid_subs.voff;
+                bstats_add(bs, ST_DHCP_O82_PRESENT, 1);
+            }
+        }
+    }
+    if (!a) {
+        u64 mk = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) mk = (mk << 8) | p[dh + 28 + k]; // chaddr
+        const u8 *s = tbl_find<1, false>(c.sub_pools, &mk);
+        if (s) a = s + c.sub_pools.voff;
+    }
+    if (!a) {
+        bstats_add(bs, ST_DHCP_MISS, 1);
+        return XDP_PASS_;
+    }
+
+    // ---- lease / pool / config, :689-713 ----
+    u64 now_s = now / 1000000000ull;
+    if (now_s > rd_u64_unaligned(a + 13)) {
+        bstats_add(bs, ST_DHCP_EXPIRED, 1);
+        return XDP_PASS_;
+    }
+    u64 pk = *(const u32 *)a;
+    const u8 *pool = tbl_find<1, false>(c.ip_pools, &pk);
+    if (!pool) {
+        bstats_add(bs, ST_DHCP_ERROR, 1);
+        return XDP_PASS_;
+    }
+    pool += c.ip_pools.voff; // ip_pool: network@0 prefix_len@4 gateway@8 dns1@12 dns2@16 lease_time@20
+    bstats_add(bs, ST_DHCP_HIT, 1);
+    const u8 *cfg = c.server_config; // server_mac@0 server_ip@8
+    u32 allocated_ip = *(const u32 *)(a + 4);
+    u32 gateway = *(const u32 *)(pool + 8);
+    u32 cfg_ip = *(const u32 *)(cfg + 8);
+    u32 server_ip = cfg_ip != 0 ? cfg_ip : gateway;
+    u8 reply_type = msg_type == 1 ? 2 : 5;
+    u32 giaddr = rd32(p, dh + 24);
+    u16 smac0 = *(const u16 *)(cfg + 0), smac1 = *(const u16 *)(cfg + 2), smac2 = *(const u16 *)(cfg + 4);
+
+    if (giaddr != 0) { // relayed: unicast back to the relay agent, :726-743
+        wr16(p, 0, rd16(p, 6));
+        wr16(p, 2, rd16(p, 8));
+        wr16(p, 4, rd16(p, 10));
+        wr32(p, l3 + 16, giaddr);
+        wr16(p, udp + 2, 0x4300u);
+        bstats_add(bs, ST_DHCP_UCAST, 1);
+    } else { // setup_reply_l2_headers(), :436-482
+        u16 flags = bswap16(rd16(p, dh + 10));
+        bool bcast = (flags & 0x8000) || rd32(p, dh + 12) == 0;
+        if (bcast) {
+            wr16(p, 0, 0xFFFF);
+            wr16(p, 2, 0xFFFF);
+            wr16(p, 4, 0xFFFF);
+            bstats_add(bs, ST_DHCP_BCAST, 1);
+        } else {
+            wr16(p, 0, rd16(p, dh + 28));
+            wr16(p, 2, rd16(p, dh + 30));
+            wr16(p, 4, rd16(p, dh + 32));
+            bstats_add(bs, ST_DHCP_UCAST, 1);
+        }
+        wr32(p, l3 + 16, 0xFFFFFFFFu);
+        wr16(p, udp + 2, 0x4400u); // bpf_htons(68)
+    }
+    wr16(p, 6, smac0);
+    wr16(p, 8, smac1);
+    wr16(p, 10, smac2);
+    wr32(p, l3 + 12, server_ip);
+    p[l3 + 8] = 64;
+    wr16(p, l3 + 10, 0);
+    wr16(p, udp + 0, 0x4300u);
+    wr16(p, udp + 6, 0);
+
+    // ---- BOOTP fixed part, :758-766 ----
+    p[dh + 0] = 2;
+    p[dh + 3] = 0;
+    wr32(p, dh + 16, allocated_ip);
+    wr32(p, dh + 20, server_ip);
+    zero_range(p + dh + 44, 192);
+
+    // The options bounds check comes AFTER the header rewrite (:769): a frame
+    // shorter than options+64 leaves here rewritten but XDP_PASSed.
+    if (opts + 64 > len) return XDP_PASS_;
+
+    // ---- build_dhcp_options(), :519-602 ----
+    u8 *o = p + opts;
+    int off = 0;
+    u32 lease = *(const u32 *)(pool + 20);
+    u32 plen = pool[4];
+    u32 mask = plen == 0 ? 0u : (plen >= 32 ? 0xFFFFFFFFu : bswap32(0xFFFFFFFFu << (32 - plen)));
+    o[off++] = 53;
+    o[off++] = 1;
+    o[off++] = reply_type;
+    put_opt32(o, off, 54, server_ip);
+    put_opt32(o, off, 51, bswap32(lease));
+    put_opt32(o, off, 1, mask);
+    put_opt32(o, off, 3, gateway);
+    u32 dns1 = *(const u32 *)(pool + 12), dns2 = *(const u32 *)(pool + 16);
+    if (dns1 != 0) {
+        o[off++] = 6;
+        o[off++] = dns2 != 0 ? 8 : 4;
+        for (int k = 0; k < 4; k++) o[off++] = (u8)(dns1 >> (8 * k));
+        if (dns2 != 0)
+            for (int k = 0; k < 4; k++) o[off++] = (u8)(dns2 >> (8 * k));
+    }
+    put_opt32(o, off, 58, bswap32(lease / 2));
+    put_opt32(o, off, 59, bswap32((lease * 7u) / 8u));
+    o[off++] = 255;
+
+    // ---- lengths, checksum, tail adjust, :779-812 ----
+    u16 dhcp_len = (u16)(240 + off);
+    u16 udp_len = (u16)(8 + dhcp_len);
+    u16 ip_len = (u16)(20 + udp_len);
+    u16 total = (u16)(14 + vlan_off + ip_len);
+    wr16(p, l3 + 2, bswap16(ip_len));
+    wr16(p, udp + 4, bswap16(udp_len));
+    u32 sum = 0;
+#pragma unroll
+    for (int k = 0; k < 10; k++) sum += rd16(p, l3 + 2 * k); // ip_checksum(), :488-503 (check is 0 here)
+    sum = (sum & 0xFFFF) + (sum >> 16);
+    sum = (sum & 0xFFFF) + (sum >> 16);
+    wr16(p, l3 + 10, (u16)~sum);
+    int delta = (int)total - (int)(u16)len;
+    if (delta != 0) {
+        long nl = (long)len + delta;
+        if (nl < 14) { // bpf_xdp_adjust_tail() refuses to go below the Ethernet header
+            bstats_add(bs, ST_DHCP_ERROR, 1);
+            return XDP_PASS_;
+        }
+        len = (u32)nl;
+    }
+    return XDP_TX_;
+}
+
+__global__ void __launch_bounds__(256) k_dhcp_fastpath(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b) {
+    __shared__ BlockStats bs;
+    bstats_init(bs);
+    for (u32 i = blockIdx.x * 256 + threadIdx.x; i < b.n; i += gridDim.x * 256) {
+        u32 len = b.len[i];
+        u32 l0 = len;
+        int v = dhcp_one(c, bs, frame_ptr(b, i), len, b.now);
+        b.verdict[i] = (u8)v;
+        if (len != l0) b.len[i] = len;
+    }
+    bstats_flush(bs, c.stats);
+}
+
+cudaError_t run_dhcp_fastpath(Launcher &L, const DevCtx &c, const DevBatch &b) {
+    long want = ((long)b.n + 255) / 256;
+    long cap = (long)L.num_sms * 6;
+    int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+    k_dhcp_fastpath<<<grid, 256, 0, L.stream>>>(c, b);
+    L.launches++;
+    return cudaGetLastError();
+}

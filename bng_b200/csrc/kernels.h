@@ -1,0 +1,36 @@
+// bng_b200 — internal interface between the C-ABI layer (ctx.cu) and the
+// kernel translation units.
+#pragma once
+#include "common.cuh"
+
+struct Scratch {
+    u32 *key_a, *key_b, *val_a, *val_b; // ordering keys / frame indices, unsorted and grouped
+    u32 *qslot;                         // pipeline: qos bucket slot per frame
+    u8 *pflag;                          // pipeline: per-frame flags
+    void *cub_tmp;
+    size_t cub_tmp_bytes;
+    u32 *counters; // 16 x u32 of per-run device counters
+    u32 cap;       // frames the arrays above can hold
+};
+
+struct Launcher {
+    cudaStream_t stream;
+    int num_sms;
+    Scratch s;
+    unsigned long long launches;
+};
+
+size_t sort_temp_bytes(u32 n);
+
+cudaError_t run_antispoof(Launcher &L, const DevCtx &c, const DevBatch &b);
+cudaError_t run_qos(Launcher &L, const DevCtx &c, const DevBatch &b, bool egress);
+cudaError_t run_nat_egress(Launcher &L, const DevCtx &c, const DevBatch &b);
+cudaError_t run_nat_ingress(Launcher &L, const DevCtx &c, const DevBatch &b);
+cudaError_t run_nat_hairpin_xdp(Launcher &L, const DevCtx &c, const DevBatch &b);
+cudaError_t run_pipeline_up(Launcher &L, const DevCtx &c, const DevBatch &b);
+cudaError_t run_dhcp_fastpath(Launcher &L, const DevCtx &c, const DevBatch &b);
+
+// table maintenance (tableops.cu); keys/values/results are device pointers
+enum { TOP_UPDATE = 0, TOP_LOOKUP = 1, TOP_DELETE = 2 };
+cudaError_t run_table_op(Launcher &L, const Tbl &t, int op, const u8 *keys, u8 *vals, int *results, u64 n, u32 flags);
+cudaError_t run_table_dump(Launcher &L, const Tbl &t, u8 *keys_out, u8 *vals_out, u32 *count_out, u64 cap);

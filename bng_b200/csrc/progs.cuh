@@ -1,0 +1,525 @@
+// bng_b200 — per-frame logic of the reference's TC programs, written for the
+// batch model: a data-parallel CLASSIFY phase that does everything whose
+// result does not depend on the order of frames inside the batch, and an
+// ordered RESOLVE phase (one sequential worker per subscriber, frames in index
+// order) for the rest.  Field offsets are those of the reference's structs;
+// each function cites the lines it must agree with bit for bit.
+#pragma once
+#include "common.cuh"
+
+#define ETH_P_IP_LE 0x0008u   // bpf_htons(0x0800) as the programs compare it
+#define ETH_P_IPV6_LE 0xDD86u // bpf_htons(0x86DD)
+#define NO_KEY 0xFFFFFFFFu
+
+#define TC_OK 0
+#define TC_SHOT 2
+
+// nat_config.flags, bpf/nat44.c:56-62
+#define NATF_EIM 0x01u
+#define NATF_HAIRPIN 0x04u
+#define NATF_ALG_FTP 0x08u
+#define NATF_ALG_SIP 0x10u
+#define NATF_PARITY 0x20u
+
+// ---------------------------------------------------------------------------
+// antispoof_ingress — bpf/antispoof.c:188-293.  Stateless apart from counters
+// and the violation log, so it is entirely a classify-phase program.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void spoof_log(const DevCtx &c, BlockStats &bs, u32 idx, u64 now, const Hdr64 &h,
+                                          u32 spoofed, u32 allowed_ip, bool v6) {
+    // log_violation(), bpf/antispoof.c:150-175: the record is emitted, then
+    // packets_logged is bumped whether or not the output succeeded.
+    u8 *r = ev_reserve(c, c.spoof_ev, idx);
+    if (r) {
+        uint4 z = make_uint4(0, 0, 0, 0);
+        u32 m01 = (u32)h.b16(6) | ((u32)h.b16(8) << 16);
+        u32 m2 = (u32)h.b16(10) | ((v6 ? 6u : 4u) << 16);
+        ((uint4 *)r)[0] = make_uint4((u32)now, (u32)(now >> 32), m01, m2);
+        ((uint4 *)r)[1] = make_uint4(v6 ? 0 : spoofed, v6 ? 0 : allowed_ip, 0, 0);
+        ((uint4 *)r)[2] = z;
+        ((uint2 *)r)[6] = make_uint2(0, 0);
+    }
+    bstats_add(bs, ST_AS_LOGGED, 1);
+}
+
+__device__ __forceinline__ int antispoof_one(const DevCtx &c, BlockStats &bs, const Hdr64 &h, u32 len, u32 idx,
+                                             u64 now) {
+    if (len < 14) return TC_OK; // :195-196, no stats
+    u64 mk = mac_key(h, 6);
+    u32 cfg = *(const u16 *)c.as_config; // default_mode | log_violations << 8
+    u32 default_mode = cfg & 0xff, log_viol = (cfg >> 8) & 0xff;
+    const u8 *bind = tbl_find<1, false>(c.bindings, &mk);
+    u32 b_ipv4 = 0, b_flags = 0; // flags word: ipv4_valid | ipv6_valid<<8 | mode<<16
+    if (bind) {
+        b_ipv4 = *(const u32 *)(bind + 8);
+        b_flags = *(const u32 *)(bind + 28);
+    }
+    u32 mode = bind ? ((b_flags >> 16) & 0xff) : default_mode;
+    if (mode == 0) { // ANTISPOOF_DISABLED :213-216
+        bstats_add(bs, ST_AS_ALLOWED, 1);
+        return TC_OK;
+    }
+    u32 proto = h.b16(12);
+    if (proto == ETH_P_IP_LE) {
+        if (len < 34) return TC_OK; // :221-222, no stats
+        u32 src = h.b32(26);
+        bool allowed = false;
+        if (bind && (b_flags & 0xff)) {
+            if (mode == 1 || mode == 3) allowed = (src == b_ipv4);
+        } else if (mode == 2) {
+            allowed = lpm_match(c.ranges_v4, src, 32);
+        }
+        if (!allowed) {
+            if (log_viol) spoof_log(c, bs, idx, now, h, src, bind ? b_ipv4 : 0, false);
+            if (mode == 3) {
+                bstats_add(bs, ST_AS_ALLOWED, 1);
+                return TC_OK;
+            }
+            bstats_add(bs, ST_AS_DROPPED, 1);
+            bstats_add(bs, ST_AS_V4_VIOL, 1);
+            return TC_SHOT;
+        }
+        bstats_add(bs, ST_AS_ALLOWED, 1);
+        return TC_OK;
+    }
+    if (proto == ETH_P_IPV6_LE) {
+        if (len < 54) return TC_OK; // :258-259
+        bool allowed = false;
+        if (bind && ((b_flags >> 8) & 0xff)) {
+            allowed = true;
+#pragma unroll
+            for (int k = 0; k < 4; k++) // ip6->saddr at frame bytes 22..37, binding ipv6_addr at value+4
+                allowed = allowed && (h.b32(22 + 4 * k) == *(const u32 *)(bind + 12 + 4 * k));
+        } else if (mode == 2) {
+            allowed = true;
+        }
+        if (!allowed && mode != 3) {
+            if (log_viol) spoof_log(c, bs, idx, now, h, 0, 0, true);
+            bstats_add(bs, ST_AS_DROPPED, 1);
+            bstats_add(bs, ST_AS_V6_VIOL, 1);
+            return TC_SHOT;
+        }
+        bstats_add(bs, ST_AS_ALLOWED, 1);
+        return TC_OK;
+    }
+    bstats_add(bs, ST_AS_ALLOWED, 1); // :290-292
+    return TC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// QoS — bpf/qos_ratelimit.c.  token_bucket at slot+16:
+//   tokens@16 last_update@24 rate_bps@32 burst_bytes@40 priority@44
+// ---------------------------------------------------------------------------
+struct TokenBucket {
+    u64 tokens, last_update, rate_bps;
+    u32 burst;
+    u32 prio;
+};
+
+__device__ __forceinline__ void tb_load(TokenBucket &tb, const u8 *slot) {
+    tb.tokens = *(const u64 *)(slot + 16);
+    tb.last_update = *(const u64 *)(slot + 24);
+    tb.rate_bps = *(const u64 *)(slot + 32);
+    tb.burst = *(const u32 *)(slot + 40);
+    tb.prio = *(const u8 *)(slot + 44);
+}
+
+// token_bucket_check(), bpf/qos_ratelimit.c:70-104, one frame; all arithmetic
+// is u64 with natural wrap-around, exactly as the eBPF program computes it.
+__device__ __forceinline__ bool tb_step(TokenBucket &tb, u64 now, u32 pkt_len) {
+    u64 elapsed = now - tb.last_update;
+    u64 add = (elapsed * (tb.rate_bps / 8)) / 1000000000ull;
+    tb.tokens += add;
+    if (tb.tokens > (u64)tb.burst) tb.tokens = tb.burst;
+    tb.last_update = now;
+    if (tb.tokens >= (u64)pkt_len) {
+        tb.tokens -= pkt_len;
+        return true;
+    }
+    return false;
+}
+
+// classify for qos_{egress,ingress}_prog (:126-172, :178-222): returns the
+// ordering key (bucket slot index) when the frame has to go through the
+// ordered token-bucket walk, NO_KEY when its verdict is already final.
+__device__ __forceinline__ u32 qos_classify_one(const DevCtx &c, BlockStats &bs, const Tbl &t, const Hdr64 &h,
+                                                u32 len, bool egress, u32 *prio_out, bool *prio_set) {
+    *prio_set = false;
+    if (len < 14) return NO_KEY;
+    if (h.b16(12) != ETH_P_IP_LE) return NO_KEY;
+    if (len < 34) return NO_KEY;
+    u64 k = egress ? h.b32(30) : h.b32(26);
+    const u8 *slot = tbl_find<1, false>(t, &k);
+    if (!slot) return NO_KEY; // no policy: TC_ACT_OK without statistics
+    u64 rate = *(const u64 *)(slot + 32);
+    if (rate == 0) { // unlimited: pass, bucket untouched (:77-78)
+        bstats_add(bs, ST_QOS_PASS_PKTS, 1);
+        bstats_add(bs, ST_QOS_PASS_BYTES, len);
+        if (egress) {
+            *prio_out = *(const u8 *)(slot + 44);
+            *prio_set = true;
+        }
+        return NO_KEY;
+    }
+    return (u32)((slot - t.slots) / t.slot_bytes);
+}
+
+// ---------------------------------------------------------------------------
+// NAT44 — bpf/nat44.c.  Slot layouts (key, then the reference value verbatim):
+//   subscriber_nat: key u32 @0, value @8:  block.public_ip@8 port_start@12 port_end@14
+//                   next_port@16 ports_in_use@20 allocated_at@24 subscriber_id@32
+//                   sessions_active@40 sessions_total@48 bytes_out@56 bytes_in@64
+//   nat_sessions:   key 16 B @0, value @16: nat_ip@16 nat_port@20 orig_port@22 orig_ip@24
+//                   dest_ip@28 dest_port@32 last_seen@40 created@48 packets_out@56
+//                   packets_in@64 bytes_out@72 bytes_in@80 state@88 protocol@89 flags@90 is_hairpin@91
+//   nat_reverse:    key 16 B @0, value (nat_key) @16
+//   eim_table:      key 8 B @0,  value @8: external_ip@8 external_port@12 created@16
+//                   last_used@24 ref_count@32 flags@36
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool is_private_ip(u32 ip_le) { // bpf/nat44.c:340-363
+    u32 o1 = ip_le & 0xff, o2 = (ip_le >> 8) & 0xff;       // first/second octet on the wire
+    if (o1 == 10) return true;
+    if (o1 == 172 && o2 >= 16 && o2 <= 31) return true;
+    if (o1 == 192 && o2 == 168) return true;
+    if (o1 == 100 && o2 >= 64 && o2 <= 127) return true;
+    return false;
+}
+
+__device__ __forceinline__ void nat_log(const DevCtx &c, u32 idx, u64 now, u32 type, u32 sub_id, u32 priv_ip,
+                                        u32 pub_ip, u16 priv_port, u16 pub_port, u32 dst_ip, u16 dst_port, u8 proto,
+                                        u8 flags) { // log_nat_event(), :531-562
+    u8 *r = ev_reserve(c, c.natlog_ev, idx);
+    if (!r) return;
+    ((u64 *)r)[0] = now;
+    ((u32 *)r)[2] = type;
+    ((u32 *)r)[3] = sub_id;
+    ((u32 *)r)[4] = priv_ip;
+    ((u32 *)r)[5] = pub_ip;
+    ((u32 *)r)[6] = (u32)priv_port | ((u32)pub_port << 16);
+    ((u32 *)r)[7] = dst_ip;
+    ((u32 *)r)[8] = (u32)dst_port | ((u32)proto << 16) | ((u32)flags << 24);
+    ((u32 *)r)[9] = 0;
+}
+
+// allocate_port_from_block(), :408-466.  `sub` is the subscriber_nat slot;
+// only the subscriber's own resolve worker touches next_port.
+__device__ __forceinline__ u16 nat_alloc_port(const DevCtx &c, u8 *sub, bool parity, u16 orig_port, u32 internal_ip,
+                                              u8 proto) {
+    u32 port_start = *(const u16 *)(sub + 12), port_end = *(const u16 *)(sub + 14);
+    u32 next = *(volatile u32 *)(sub + 16);
+    u16 found = 0;
+    for (int i = 0; i < 64; i++) {
+        u16 port = (u16)next;
+        next += 1;
+        if (port > port_end) port = (u16)port_start;
+        if (next > port_end) next = port_start;
+        if (parity && ((port & 1) != (orig_port & 1))) continue;
+        u64 ek = (u64)internal_ip | ((u64)port << 32) | ((u64)proto << 48);
+        if (tbl_find<1, true>(c.eim, &ek)) continue;
+        found = port;
+        break;
+    }
+    *(volatile u32 *)(sub + 16) = next;
+    return found;
+}
+
+// Applies the SNAT rewrite of :752-798 to the frame in global memory.
+__device__ __forceinline__ void nat_snat_rewrite(u8 *p, u32 l4, u32 proto, u32 old_ip, u32 nat_ip, u16 nat_port) {
+    wr32(p, 26, nat_ip);
+    wr16(p, 24, csum_upd32(rd16(p, 24), old_ip, nat_ip));
+    if (proto == 6) {
+        u16 old_port = rd16(p, l4);
+        wr16(p, l4, nat_port);
+        u16 ck = rd16(p, l4 + 16);
+        ck = csum_upd32(ck, old_ip, nat_ip);
+        ck = csum_upd16(ck, old_port, nat_port);
+        wr16(p, l4 + 16, ck);
+    } else if (proto == 17) {
+        u16 old_port = rd16(p, l4);
+        wr16(p, l4, nat_port);
+        u16 ck = rd16(p, l4 + 6);
+        if (ck != 0) {
+            ck = csum_upd32(ck, old_ip, nat_ip);
+            ck = csum_upd16(ck, old_port, nat_port);
+            if (ck == 0) ck = 0xffff;
+            wr16(p, l4 + 6, ck);
+        }
+    } else if (proto == 1) {
+        u16 old_id = rd16(p, l4 + 4);
+        wr16(p, l4 + 4, nat_port);
+        wr16(p, l4 + 2, csum_upd16(rd16(p, l4 + 2), old_id, nat_port));
+    }
+}
+
+struct NatOut {
+    int verdict;
+    u32 order_key; // subscriber_nat slot index when the frame needs the ordered phase
+};
+
+// nat44_egress, :565-802.
+//   RESOLVE=false (classify): everything up to the session lookup, the hit
+//     path, and the rewrite for hits.  A session miss returns order_key.
+//   RESOLVE=true: full sequential semantics for one frame, executed by the
+//     subscriber's worker in frame-index order; counters that classify
+//     already bumped for this frame (hairpin) are not bumped again.
+template <bool RESOLVE>
+__device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs, u8 *p, u32 len, u32 idx, u64 now) {
+    NatOut o;
+    o.verdict = TC_OK;
+    o.order_key = NO_KEY;
+    if (len < 14) return o;
+    if (rd16(p, 12) != ETH_P_IP_LE) return o;
+    if (len < 34) return o;
+    u32 saddr = rd32(p, 26);
+    if (!is_private_ip(saddr)) return o;
+    u64 sk = saddr;
+    u8 *sub = tbl_find<1, RESOLVE>(c.sub_nat, &sk);
+    if (!sub) {
+        if (!RESOLVE) bstats_add(bs, ST_NAT_PASSED, 1);
+        return o;
+    }
+    u32 cfg_flags = *(const u32 *)c.nat_config;
+    u32 daddr = rd32(p, 30);
+    u32 proto = p[23];
+    u32 l4 = 14 + (u32)(p[14] & 0x0f) * 4;
+    u16 sport = 0, dport = 0;
+    if (proto == 6 || proto == 17) {
+        if (l4 + (proto == 6 ? 20u : 8u) > len) return o;
+        sport = rd16(p, l4);
+        dport = rd16(p, l4 + 2);
+        u32 alg_mask = proto == 6 ? (NATF_ALG_FTP | NATF_ALG_SIP) : NATF_ALG_SIP;
+        if (cfg_flags & alg_mask) {
+            u64 ak = ((u32)bswap16(dport) << 16) | proto;
+            const u8 *alg = tbl_find<1, false>(c.alg, &ak);
+            if (alg) { // ALG traffic goes to userspace untranslated (:615-642)
+                if (!RESOLVE) {
+                    bstats_add(bs, ST_NAT_ALG, 1);
+                    nat_log(c, idx, now, 7, *(const u32 *)(sub + 32), saddr, 0, sport, 0, daddr, dport, (u8)proto,
+                            alg[8 + 3]);
+                }
+                return o;
+            }
+        }
+    } else if (proto == 1) {
+        if (l4 + 8 > len) return o;
+        sport = rd16(p, l4 + 4); // echo id stands in for the source port (:647-649)
+        dport = 0;
+    } else {
+        return o;
+    }
+    u8 is_hairpin = 0;
+    if (cfg_flags & NATF_HAIRPIN) {
+        u64 hk = daddr;
+        if (tbl_find<1, false>(c.hairpin, &hk)) {
+            is_hairpin = 1;
+            if (!RESOLVE) bstats_add(bs, ST_NAT_HAIRPIN, 1);
+        }
+    }
+    u64 key[2];
+    key[0] = (u64)saddr | ((u64)daddr << 32);
+    key[1] = (u64)sport | ((u64)dport << 16) | ((u64)proto << 32);
+    u8 *ses = tbl_find<2, RESOLVE>(c.sessions, key);
+    u32 nat_ip;
+    u16 nat_port;
+    if (ses) { // :674-680
+        nat_ip = *(const u32 *)(ses + 16);
+        nat_port = *(const u16 *)(ses + 20);
+        *(u64 *)(ses + 40) = now;
+        atomicAdd((u64 *)(ses + 56), 1ull);
+        atomicAdd((u64 *)(ses + 72), (u64)len);
+    } else {
+        if (!RESOLVE) {
+            o.order_key = (u32)((sub - c.sub_nat.slots) / c.sub_nat.slot_bytes);
+            return o;
+        }
+        u32 sub_id = *(const u32 *)(sub + 32);
+        u32 pub_ip = *(const u32 *)(sub + 8);
+        bool have = false;
+        if (cfg_flags & NATF_EIM) { // get_eim_mapping(), :469-528
+            u64 ek = (u64)saddr | ((u64)sport << 32) | ((u64)proto << 48);
+            u8 *m = tbl_find<1, true>(c.eim, &ek);
+            if (m) {
+                *(u64 *)(m + 24) = now;
+                *(u32 *)(m + 32) += 1;
+                bstats_add(bs, ST_NAT_EIM_HIT, 1);
+            } else {
+                u16 ext = nat_alloc_port(c, sub, (cfg_flags & NATF_PARITY) != 0, sport, saddr, (u8)proto);
+                if (ext == 0) {
+                    bstats_add(bs, ST_NAT_EXHAUST, 1);
+                } else {
+                    bool created;
+                    m = tbl_find_or_claim<1>(c.eim, &ek, &created);
+                    if (m && created) {
+                        *(u32 *)(m + 8) = pub_ip;
+                        *(u32 *)(m + 12) = ext; // external_port (host order) + zero pad
+                        *(u64 *)(m + 16) = now;
+                        *(u64 *)(m + 24) = now;
+                        *(u32 *)(m + 32) = 1;
+                        *(u32 *)(m + 36) = 0;
+                        tbl_publish(m, ek);
+                        bstats_add(bs, ST_NAT_EIM_MISS, 1);
+                    } else if (m) { // "someone else created it" branch (:521-527)
+                        *(u32 *)(m + 32) += 1;
+                        bstats_add(bs, ST_NAT_EIM_HIT, 1);
+                    } else {
+                        bstats_add(bs, ST_LRU_OVERFLOW, 1);
+                    }
+                }
+            }
+            if (m) {
+                nat_ip = *(const u32 *)(m + 8);
+                nat_port = bswap16(*(const u16 *)(m + 12));
+                have = true;
+            }
+        }
+        if (!have) { // :694-708
+            u16 ap = nat_alloc_port(c, sub, (cfg_flags & NATF_PARITY) != 0, bswap16(sport), saddr, (u8)proto);
+            if (ap == 0) {
+                bstats_add(bs, ST_NAT_EXHAUST, 1);
+                bstats_add(bs, ST_NAT_DROPPED, 1);
+                nat_log(c, idx, now, 5, sub_id, saddr, pub_ip, sport, 0, daddr, dport, (u8)proto, 0);
+                o.verdict = TC_SHOT;
+                return o;
+            }
+            nat_ip = pub_ip;
+            nat_port = bswap16(ap);
+        }
+        bool created;
+        u8 *ns = tbl_find_or_claim<2>(c.sessions, key, &created); // BPF_ANY (:730)
+        if (ns) {
+            *(u32 *)(ns + 16) = nat_ip;
+            *(u32 *)(ns + 20) = (u32)nat_port | ((u32)sport << 16);
+            *(u32 *)(ns + 24) = saddr;
+            *(u32 *)(ns + 28) = daddr;
+            *(u64 *)(ns + 32) = (u64)dport;
+            *(u64 *)(ns + 40) = now;
+            *(u64 *)(ns + 48) = now;
+            *(u64 *)(ns + 56) = 1;
+            *(u64 *)(ns + 64) = 0;
+            *(u64 *)(ns + 72) = (u64)len;
+            *(u64 *)(ns + 80) = 0;
+            *(u64 *)(ns + 88) = (u64)proto << 8 | ((u64)is_hairpin << 24);
+            if (created) tbl_publish(ns, key[0]);
+        } else {
+            bstats_add(bs, ST_LRU_OVERFLOW, 1);
+        }
+        u64 rk[2];
+        rk[0] = (u64)daddr | ((u64)nat_ip << 32);
+        rk[1] = (u64)dport | ((u64)nat_port << 16) | ((u64)proto << 32);
+        u8 *rs = tbl_find_or_claim<2>(c.reverse, rk, &created); // BPF_ANY (:740)
+        if (rs) {
+            *(u64 *)(rs + 16) = key[0];
+            *(u64 *)(rs + 24) = key[1];
+            if (created) tbl_publish(rs, rk[0]);
+        } else {
+            bstats_add(bs, ST_LRU_OVERFLOW, 1);
+        }
+        atomicAdd((u64 *)(sub + 40), 1ull);
+        atomicAdd((u64 *)(sub + 48), 1ull);
+        bstats_add(bs, ST_NAT_CREATED, 1);
+        nat_log(c, idx, now, 1, sub_id, saddr, nat_ip, sport, nat_port, daddr, dport, (u8)proto, is_hairpin);
+    }
+    nat_snat_rewrite(p, l4, proto, saddr, nat_ip, nat_port);
+    bstats_add(bs, ST_NAT_SNAT, 1);
+    return o;
+}
+
+// nat44_ingress, :805-948.  Every update is commutative (or made so with a
+// CAS on the state byte), so this is a classify-only program.
+__device__ __forceinline__ int nat_ingress_one(const DevCtx &c, BlockStats &bs, u8 *p, u32 len, u64 now) {
+    if (len < 14) return TC_OK;
+    if (rd16(p, 12) != ETH_P_IP_LE) return TC_OK;
+    if (len < 34) return TC_OK;
+    u32 saddr = rd32(p, 26), daddr = rd32(p, 30);
+    u32 proto = p[23];
+    u32 l4 = 14 + (u32)(p[14] & 0x0f) * 4;
+    u16 sport = 0, dport = 0;
+    if (proto == 6) {
+        if (l4 + 20 > len) return TC_OK;
+        sport = rd16(p, l4);
+        dport = rd16(p, l4 + 2);
+    } else if (proto == 17) {
+        if (l4 + 8 > len) return TC_OK;
+        sport = rd16(p, l4);
+        dport = rd16(p, l4 + 2);
+    } else if (proto == 1) {
+        if (l4 + 8 > len) return TC_OK;
+        sport = 0;
+        dport = rd16(p, l4 + 4);
+    } else {
+        return TC_OK;
+    }
+    u64 rk[2];
+    rk[0] = (u64)saddr | ((u64)daddr << 32);
+    rk[1] = (u64)sport | ((u64)dport << 16) | ((u64)proto << 32);
+    u8 *rs = tbl_find<2, true>(c.reverse, rk);
+    if (!rs) {
+        bstats_add(bs, ST_NAT_PASSED, 1);
+        return TC_OK;
+    }
+    u64 ok[2];
+    ok[0] = *(const u64 *)(rs + 16);
+    ok[1] = *(const u64 *)(rs + 24);
+    u8 *ses = tbl_find<2, false>(c.sessions, ok);
+    if (!ses) {
+        // Stale reverse entry: the first frame (in index order) deletes it and
+        // counts sessions_expired, later ones miss the reverse map (:871-876,
+        // :861-867).  Which frame wins the erase is immaterial: all are passed
+        // unmodified and the counters sum the same.
+        if (tbl_erase<2>(c.reverse, rk))
+            bstats_add(bs, ST_NAT_EXPIRED, 1);
+        else
+            bstats_add(bs, ST_NAT_PASSED, 1);
+        return TC_OK;
+    }
+    *(u64 *)(ses + 40) = now;
+    atomicAdd((u64 *)(ses + 64), 1ull);
+    atomicAdd((u64 *)(ses + 80), (u64)len);
+    if (proto == 6) { // :885-895; CLOSING(3) is absorbing, NEW(0)->ESTABLISHED(1) on ack
+        u32 tf = p[l4 + 13];
+        bool finrst = (tf & 0x05) != 0, ack = (tf & 0x10) != 0;
+        if (finrst || ack) {
+            u32 *sw = (u32 *)(ses + 88);
+            u32 cur = *(volatile u32 *)sw;
+            while (true) {
+                u32 st = cur & 0xff, nst = st;
+                if (finrst)
+                    nst = 3;
+                else if (st == 0)
+                    nst = 1;
+                if (nst == st) break;
+                u32 prev = atomicCAS(sw, cur, (cur & ~0xffu) | nst);
+                if (prev == cur) break;
+                cur = prev;
+            }
+        }
+    }
+    u32 new_ip = *(const u32 *)(ses + 24);
+    u16 new_port = *(const u16 *)(ses + 22);
+    wr32(p, 30, new_ip);
+    wr16(p, 24, csum_upd32(rd16(p, 24), daddr, new_ip));
+    if (proto == 6) {
+        u16 old_port = rd16(p, l4 + 2);
+        wr16(p, l4 + 2, new_port);
+        u16 ck = rd16(p, l4 + 16);
+        ck = csum_upd32(ck, daddr, new_ip);
+        ck = csum_upd16(ck, old_port, new_port);
+        wr16(p, l4 + 16, ck);
+    } else if (proto == 17) {
+        u16 old_port = rd16(p, l4 + 2);
+        wr16(p, l4 + 2, new_port);
+        u16 ck = rd16(p, l4 + 6);
+        if (ck != 0) {
+            ck = csum_upd32(ck, daddr, new_ip);
+            ck = csum_upd16(ck, old_port, new_port);
+            if (ck == 0) ck = 0xffff;
+            wr16(p, l4 + 6, ck);
+        }
+    } else {
+        u16 old_id = rd16(p, l4 + 4);
+        wr16(p, l4 + 4, new_port);
+        wr16(p, l4 + 2, csum_upd16(rd16(p, l4 + 2), old_id, new_port));
+    }
+    bstats_add(bs, ST_NAT_DNAT, 1);
+    return TC_OK;
+}

@@ -1,0 +1,145 @@
+/* bng_b200 — C ABI of the B200-native subscriber dataplane.
+ *
+ * This is the drop-in boundary for the reference's eBPF hot path: everything
+ * the Go control plane does to the dataplane goes through cilium/ebpf
+ * `*ebpf.Map` Put/Lookup/Delete calls and program attach
+ * (reference pkg/ebpf/loader.go:211-315,357-655; pkg/antispoof/manager.go:127-381;
+ * pkg/qos/manager.go:89-320; pkg/nat/manager.go:563-821).  The functions below
+ * are what a cgo shim binds instead: maps are addressed
+ * by the reference's map names and use the reference's key/value byte layouts
+ * verbatim (bpf/antispoof.c:36-119, bpf/qos_ratelimit.c:24-65,
+ * bpf/nat44.c:92-320, bpf/maps.h:89-234); programs are addressed by the
+ * reference's program (ELF section function) names and run over BATCHES of
+ * frames on the GPU instead of per packet in the kernel.
+ *
+ * Conventions
+ *   - every function returns 0 or a negative errno, as bpf(2) does
+ *     (-ENOENT lookup/delete miss, -EEXIST BPF_NOEXIST clash, -E2BIG map full,
+ *     -EINVAL bad argument, -ENOMEM, -EIO CUDA failure; bng_last_error() has text)
+ *   - key/value buffers are borrowed for the duration of the call only
+ *   - all entry points are thread-safe (one mutex per context); program runs
+ *     on one context are serialised on that context's CUDA stream
+ *   - PERCPU_ARRAY statistics maps read back as aggregated totals
+ *   - there is NO CPU fallback: without a CUDA device bng_open() fails
+ */
+#ifndef BNG_B200_H
+#define BNG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNG_ABI_VERSION 1
+
+/* bpf(2) BPF_MAP_UPDATE_ELEM flags (include/uapi/linux/bpf.h) */
+#define BNG_ANY 0u
+#define BNG_NOEXIST 1u
+#define BNG_EXIST 2u
+
+/* verdict codes, identical to the kernel's */
+#define BNG_TC_ACT_OK 0
+#define BNG_TC_ACT_SHOT 2
+#define BNG_XDP_DROP 1
+#define BNG_XDP_PASS 2
+#define BNG_XDP_TX 3
+
+/* where the buffers of a bng_batch live */
+#define BNG_MEM_DEVICE 0u /* device pointers; the run is asynchronous on bng_stream() */
+#define BNG_MEM_HOST 1u   /* host pointers; the call copies in, runs, copies out, and returns synchronised */
+
+typedef struct bng_ctx bng_ctx;
+
+typedef struct bng_open_opts {
+    uint32_t struct_size;      /* sizeof(bng_open_opts) */
+    int32_t device;            /* CUDA device ordinal, -1 = current device */
+    uint32_t max_batch;        /* largest bng_batch.n this context will see (scratch sizing); 0 = 1<<22 */
+    uint32_t max_subscribers;  /* capacity of the per-subscriber hashes; 0 = reference MAX_SUBSCRIBERS (1e6) */
+    uint32_t max_nat_sessions; /* nat_sessions / nat_reverse; 0 = reference MAX_NAT_SESSIONS (4e6) */
+    uint32_t max_eim_mappings; /* eim_table; 0 = reference MAX_EIM_MAPPINGS (2e6) */
+    uint32_t event_capacity;   /* staged event records per ring; 0 = 1<<21 */
+    uint32_t rank;             /* this context's shard index (informational; see bng_shard_of_mac) */
+    uint32_t world;            /* number of shards */
+} bng_open_opts;
+
+typedef struct bng_map_info {
+    uint32_t type; /* enum bpf_map_type value the reference declares */
+    uint32_t key_size;
+    uint32_t value_size;
+    uint32_t max_entries;
+    uint64_t count; /* live entries (hash maps) */
+} bng_map_info;
+
+/* One batch of Ethernet frames (no FCS).  Frame i occupies bytes
+ * [off16[i]*16, off16[i]*16 + len[i]) of the arena, or starts at i*stride when
+ * off16 is NULL; every frame's storage must be readable and writable up to the
+ * next multiple of 16 bytes.  Frames are applied in index order: the result is
+ * bit-identical to running the reference program on frame 0, then 1, ...
+ * with bpf_ktime_get_ns() returning now_ns throughout the batch. */
+typedef struct bng_batch {
+    void *pkts;            /* arena base */
+    const uint32_t *off16; /* [n] frame offsets in 16-byte units, or NULL */
+    uint32_t *len;         /* [n] in: frame length (skb->len / data_end-data); out: length after the program */
+    uint8_t *verdict;      /* [n] out: TC_ACT_* (tc programs, pipelines) or XDP_* (xdp programs) */
+    uint32_t *priority;    /* [n] in/out skb->priority (qos_egress_prog writes it); may be NULL */
+    uint32_t n;
+    uint32_t stride;       /* bytes between frames when off16 == NULL (multiple of 16) */
+    uint64_t now_ns;       /* bpf_ktime_get_ns() for this batch */
+    uint32_t mem;          /* BNG_MEM_DEVICE or BNG_MEM_HOST */
+    uint32_t arena_bytes;  /* size of the arena in 16-byte units (needed for BNG_MEM_HOST copies) */
+} bng_batch;
+
+/* ---- lifecycle (replaces ebpf.LoadCollectionSpec/NewCollection/Collection.Close,
+ *      pkg/ebpf/loader.go:211-222,337-339) ---- */
+bng_ctx *bng_open(const bng_open_opts *opts);
+int bng_close(bng_ctx *ctx);
+const char *bng_last_error(bng_ctx *ctx); /* ctx may be NULL: error of the last failed bng_open on this thread */
+uint32_t bng_abi_version(void);
+
+/* ---- maps (replaces coll.Maps[name] + Map.Put/Lookup/Delete) ---- */
+int bng_map_id(bng_ctx *ctx, const char *name);
+int bng_map_get_info(bng_ctx *ctx, int map, bng_map_info *out);
+int bng_map_update(bng_ctx *ctx, int map, const void *key, const void *value, uint64_t flags);
+int bng_map_update_batch(bng_ctx *ctx, int map, const void *keys, const void *values, uint64_t n, uint64_t flags);
+int bng_map_lookup(bng_ctx *ctx, int map, const void *key, void *value_out);
+int bng_map_delete(bng_ctx *ctx, int map, const void *key);
+/* copies up to cap (key,value) pairs out; returns the number written or a negative errno */
+int64_t bng_map_dump(bng_ctx *ctx, int map, void *keys_out, void *values_out, uint64_t cap);
+
+/* ---- programs (replaces coll.Programs[name] + link.AttachXDP / netlink FilterAdd;
+ *      a batch run is the analogue of BPF_PROG_TEST_RUN over n frames) ---- */
+int bng_prog_id(bng_ctx *ctx, const char *name);
+int bng_prog_run(bng_ctx *ctx, int prog, bng_batch *batch);
+int bng_sync(bng_ctx *ctx);     /* wait for everything queued on the context's stream */
+void *bng_stream(bng_ctx *ctx); /* the context's cudaStream_t */
+
+/* ---- events (spoof_events perf buffer, nat_log_rb ring buffer) ----
+ * Records come out in the order the reference would have emitted them (batch
+ * order, then frame index); nat_log_rb applies the kernel ring's capacity
+ * (records that would not have fitted are dropped, as bpf_ringbuf_reserve
+ * failing does in bpf/nat44.c:545-547). */
+int bng_events_drain(bng_ctx *ctx, int map, void *buf, uint64_t cap_records, uint64_t *n_out);
+uint32_t bng_event_size(bng_ctx *ctx, int map);
+
+/* ---- multi-GPU plumbing ----
+ * Frames shard by subscriber MAC: shard = bng_shard_of_mac(mac_key, world).
+ * The packed statistics vector (all PERCPU/array counters of the four
+ * programs, BNG_NUM_STATS u64) can be all-reduced in place by the host's
+ * collective library (NCCL) between batches. */
+#define BNG_NUM_STATS 40
+uint32_t bng_shard_of_mac(uint64_t mac_key, uint32_t world);
+int bng_stats_device_ptr(bng_ctx *ctx, void **dptr, uint32_t *n_u64);
+
+/* ---- diagnostics ---- */
+uint64_t bng_launch_count(bng_ctx *ctx);  /* kernels launched by this context so far */
+uint64_t bng_lru_overflow(bng_ctx *ctx);  /* inserts refused because an LRU map was full (eviction not modelled) */
+uint64_t bng_events_lost(bng_ctx *ctx);   /* event records dropped because the staging buffer was full */
+void *bng_host_alloc(size_t bytes);       /* pinned host memory for BNG_MEM_HOST batches */
+void bng_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNG_B200_H */
