@@ -696,6 +696,7 @@ int bng_prog_run(bng_ctx *c, int prog, bng_batch *bb) {
     CU(c, cudaMemcpyAsync(bb->verdict, c->hb_verdict, (size_t)bb->n, cudaMemcpyDeviceToHost, st));
     if (bb->priority) CU(c, cudaMemcpyAsync(bb->priority, c->hb_prio, (size_t)bb->n * 4, cudaMemcpyDeviceToHost, st));
     CU(c, cudaStreamSynchronize(st));
+    prof_collect(c->L);
     return 0;
 }
 
@@ -704,6 +705,7 @@ int bng_sync(bng_ctx *c) {
     std::lock_guard<std::mutex> g(c->mu);
     cudaSetDevice(c->device);
     CU(c, cudaStreamSynchronize(c->L.stream));
+    prof_collect(c->L);
     return 0;
 }
 
@@ -775,6 +777,35 @@ int bng_stats_device_ptr(bng_ctx *c, void **dptr, uint32_t *n_u64) {
 }
 
 uint64_t bng_launch_count(bng_ctx *c) { return c ? c->L.launches : 0; }
+
+int bng_prof_enable(bng_ctx *c, int on) {
+    if (!c) return -EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->L.stream);
+    prof_collect(c->L);
+    c->L.prof = on ? 1 : 0;
+    if (on) c->L.nacc = 0;
+    return 0;
+}
+
+int64_t bng_prof_read(bng_ctx *c, char *buf, uint64_t cap) {
+    if (!c || !buf || !cap) return -EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->L.stream);
+    prof_collect(c->L);
+    std::string out;
+    char line[256];
+    for (int i = 0; i < c->L.nacc; i++) {
+        snprintf(line, sizeof(line), "%s %llu %.6f\n", c->L.acc_name[i], c->L.acc_n[i], c->L.acc_ms[i]);
+        out += line;
+    }
+    size_t n = std::min<size_t>(out.size(), cap - 1);
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+    return (int64_t)n;
+}
 
 static uint64_t read_stat(bng_ctx *c, int idx) {
     if (!c) return 0;

@@ -289,7 +289,9 @@ cudaError_t run_dhcp_fastpath(Launcher &L, const DevCtx &c, const DevBatch &b) {
     long want = ((long)b.n + 255) / 256;
     long cap = (long)L.num_sms * 6;
     int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+    prof_begin(L, "k_dhcp_fastpath");
     k_dhcp_fastpath<<<grid, 256, 0, L.stream>>>(c, b);
+    prof_end(L);
     L.launches++;
     return cudaGetLastError();
 }

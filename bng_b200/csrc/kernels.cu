@@ -10,6 +10,8 @@
 // order inside a group, and RESOLVE kernels walk each group sequentially.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <string.h>
+
 #include "kernels.h"
 #include "progs.cuh"
 
@@ -296,13 +298,55 @@ static cudaError_t group_by_key(Launcher &L, u32 n, u32 key_space) {
     if (end_bit > 32) end_bit = 32;
     size_t tb = L.s.cub_tmp_bytes;
     L.launches += (end_bit + 7) / 8 + 1;
-    return cub::DeviceRadixSort::SortPairs(L.s.cub_tmp, tb, L.s.key_a, L.s.key_b, L.s.val_a, L.s.val_b, (int)n, 0, end_bit,
-                                           L.stream);
+    prof_begin(L, "group_by_key");
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(L.s.cub_tmp, tb, L.s.key_a, L.s.key_b, L.s.val_a, L.s.val_b, (int)n, 0,
+                                                    end_bit, L.stream);
+    prof_end(L);
+    return e;
+}
+
+void prof_begin(Launcher &L, const char *name) {
+    if (!L.prof || L.npend >= 32) return;
+    int acc = -1;
+    for (int i = 0; i < L.nacc; i++)
+        if (L.acc_name[i] == name || !strcmp(L.acc_name[i], name)) acc = i;
+    if (acc < 0) {
+        if (L.nacc >= 32) return;
+        acc = L.nacc++;
+        L.acc_name[acc] = name;
+        L.acc_ms[acc] = 0;
+        L.acc_n[acc] = 0;
+    }
+    ProfPending &p = L.pend[L.npend];
+    p.acc = acc;
+    if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return;
+    cudaEventRecord(p.a, L.stream);
+    L.npend++;
+    L.prof = 2; // a begin is open
+}
+void prof_end(Launcher &L) {
+    if (L.prof != 2) return;
+    cudaEventRecord(L.pend[L.npend - 1].b, L.stream);
+    L.prof = 1;
+}
+void prof_collect(Launcher &L) {
+    for (int i = 0; i < L.npend; i++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, L.pend[i].a, L.pend[i].b) == cudaSuccess) {
+            L.acc_ms[L.pend[i].acc] += ms;
+            L.acc_n[L.pend[i].acc]++;
+        }
+        cudaEventDestroy(L.pend[i].a);
+        cudaEventDestroy(L.pend[i].b);
+    }
+    L.npend = 0;
 }
 
 #define LAUNCH(kern, n, bps, ...)                                      \
     do {                                                               \
+        prof_begin(L, #kern);                                          \
         kern<<<grid_for(L, n, bps), BLOCK, 0, L.stream>>>(__VA_ARGS__); \
+        prof_end(L);                                                   \
         L.launches++;                                                  \
     } while (0)
 

@@ -13,12 +13,29 @@ struct Scratch {
     u32 cap;       // frames the arrays above can hold
 };
 
+// optional per-kernel timing (bng_prof_enable): CUDA events around every launch
+struct ProfPending {
+    int acc;
+    cudaEvent_t a, b;
+};
+
 struct Launcher {
     cudaStream_t stream;
     int num_sms;
     Scratch s;
     unsigned long long launches;
+    int prof;
+    ProfPending pend[32];
+    int npend;
+    const char *acc_name[32];
+    double acc_ms[32];
+    unsigned long long acc_n[32];
+    int nacc;
 };
+
+void prof_begin(Launcher &L, const char *name);
+void prof_end(Launcher &L);
+void prof_collect(Launcher &L); // call after the stream has been synchronised
 
 size_t sort_temp_bytes(u32 n);
 

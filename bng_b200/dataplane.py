@@ -86,6 +86,8 @@ def load_library() -> C.CDLL:
         "bng_launch_count": ([vp], u64),
         "bng_lru_overflow": ([vp], u64),
         "bng_events_lost": ([vp], u64),
+        "bng_prof_enable": ([vp, i32], i32),
+        "bng_prof_read": ([vp, C.c_char_p, u64], C.c_int64),
         "bng_host_alloc": ([C.c_size_t], vp),
         "bng_host_free": ([vp], None),
     }
@@ -101,8 +103,8 @@ EXPORTED_SYMBOLS = (
     "bng_open", "bng_close", "bng_last_error", "bng_abi_version", "bng_map_id", "bng_map_get_info",
     "bng_map_update", "bng_map_update_batch", "bng_map_lookup", "bng_map_delete", "bng_map_dump", "bng_prog_id",
     "bng_prog_run", "bng_sync", "bng_stream", "bng_events_drain", "bng_event_size", "bng_shard_of_mac",
-    "bng_stats_device_ptr", "bng_launch_count", "bng_lru_overflow", "bng_events_lost", "bng_host_alloc",
-    "bng_host_free",
+    "bng_stats_device_ptr", "bng_launch_count", "bng_lru_overflow", "bng_events_lost", "bng_prof_enable",
+    "bng_prof_read", "bng_host_alloc", "bng_host_free",
 )
 
 
@@ -283,6 +285,19 @@ class Dataplane:
         n = C.c_uint32()
         self._chk(self.lib.bng_stats_device_ptr(self.h, C.byref(p), C.byref(n)), "stats_device_ptr")
         return p.value, n.value
+
+    def prof_enable(self, on: bool = True):
+        self._chk(self.lib.bng_prof_enable(self.h, 1 if on else 0), "prof_enable")
+
+    def prof_read(self) -> dict:
+        """{kernel name: (launches, total_ms)} since prof_enable(True)."""
+        buf = C.create_string_buffer(8192)
+        self._chk(self.lib.bng_prof_read(self.h, buf, 8192), "prof_read")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.rsplit(" ", 2)
+            out[name] = (int(n), float(ms))
+        return out
 
     @property
     def launch_count(self) -> int:

@@ -1,0 +1,234 @@
+"""The synthetic workloads of BASELINE.json / SURVEY.md §8(d), built per shard.
+
+Each builder returns a :class:`Workload`: the map contents to load (numpy,
+reference layouts), the frame headers (u8[n,64] or wider for DHCP), frame
+lengths, and the program to run.  Subscribers are global; a shard keeps those
+with ``splitmix64(mac_key) % world == rank`` and draws its frames from them,
+so every subscriber's state lives on exactly one GPU and no data-path
+collective is needed.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import layouts as L
+from . import synth as S
+
+GW_MAC = 0x02FFFFFFFFFE
+
+# algorithmic HBM bytes per frame (SURVEY.md §8d / BASELINE.md §3)
+ALGO_BYTES = {
+    "antispoof_64": 97,
+    "nat_steady_64": 317,
+    "nat_cold_64": 541,
+    "pipeline_imix": 405,
+    "pipeline_64": 405,
+    "qos_64": 64 + 36 + 16 + 1,
+    "dhcp": 748,
+}
+
+
+@dataclass
+class Workload:
+    name: str
+    prog: str
+    maps: list = field(default_factory=list)  # [(map name, keys, values)]
+    headers: np.ndarray = None                # u8[n, w]
+    lens: np.ndarray = None                   # u32[n]
+    imix: bool = False                        # frames laid out back to back at 16 B granularity
+    now0: int = 1_000_000_000
+    now_step: int = 1_000_000                 # bpf_ktime_get_ns() advance per batch
+    prewarm: list = field(default_factory=list)  # [(prog, headers, lens)] run once before timing
+    n_subs_local: int = 0
+    info: dict = field(default_factory=dict)
+
+    @property
+    def n(self):
+        return int(self.lens.shape[0])
+
+
+def local_subscribers(n_subs: int, rank: int, world: int) -> np.ndarray:
+    idx = np.arange(n_subs, dtype=np.uint32)
+    if world <= 1:
+        return idx
+    return idx[S.shard_of_mac(S.sub_mac_key(idx), world) == rank]
+
+
+def _pick(seed, n, hi):
+    return (S.splitmix64_array(seed, n) % np.uint64(hi)).astype(np.int64)
+
+
+def antispoof(n: int, rank=0, world=1, n_subs=10_000, seed=0xB2000002) -> Workload:
+    """Config #2: 10k bindings (STRICT), 64 B frames: 97 % legitimate, 1 % spoofed source (drop + event),
+    1 % unknown MAC (drop), 0.5 % IPv6 without binding (drop in strict), 0.5 % ARP (allow)."""
+    subs = local_subscribers(n_subs, rank, world)
+    keys, v = S.bindings(n_subs)
+    w = Workload("antispoof_64", "antispoof_ingress")
+    cfg = np.zeros(1, L.antispoof_config)
+    cfg["default_mode"], cfg["log_violations"] = L.ANTISPOOF_STRICT, 1
+    w.maps = [("subscriber_bindings", keys[subs], v[subs]), ("antispoof_config", np.zeros(1, "<u4"), cfg)]
+    sub = subs[_pick(seed + rank, n, len(subs))]
+    r = (S.splitmix64_array(seed ^ 0x77 + rank, n) % np.uint64(1000)).astype(np.int64)
+    src = S.sub_ip(sub)
+    src = np.where(r < 10, src ^ np.uint32(0x00100000), src)
+    mac = S.sub_mac_key(sub)
+    mac = np.where((r >= 10) & (r < 20), mac | np.uint64(0x00F000000000), mac)
+    lens = np.full(n, 64, np.uint32)
+    hdr = S.ipv4_headers(mac, np.uint64(GW_MAC), src, np.uint32(0x08080808), 6, 40000, 443, lens, l4_check=0x1234)
+    v6 = (r >= 20) & (r < 25)
+    hdr[v6, 12], hdr[v6, 13] = 0x86, 0xDD
+    arp = (r >= 25) & (r < 30)
+    hdr[arp, 12], hdr[arp, 13] = 0x08, 0x06
+    w.headers, w.lens, w.n_subs_local = hdr, lens, len(subs)
+    return w
+
+
+def _nat_maps(subs_global: int, subs: np.ndarray, flags=0x0F):
+    keys, v, pubs = S.nat_blocks(subs_global)
+    return [("subscriber_nat", keys[subs], v[subs]),
+            ("nat_config_map", np.zeros(1, "<u4"), S.nat_config(flags)),
+            ("hairpin_ips", S.ip_bytes(pubs), np.ones(len(pubs), np.uint8)),
+            ("alg_ports", np.array([(21 << 16) | 6], "<u4"), np.array([(21, 6, 1, 0)], L.alg_config))]
+
+
+def nat(n: int, rank=0, world=1, n_subs=16_384, flows_per_sub=64, cold=False, seed=0xB2000003) -> Workload:
+    """Config #3: 16 384 subscribers x 64 flows = 1 M 5-tuples (61 % TCP, 37 % UDP incl. a zero-checksum slice,
+    2 % ICMP echo), blocks of 1024 ports via the AllocateNAT rule, flags EIM+EIF+HAIRPIN+ALG_FTP.
+    cold: every flow once (100 % miss: session + reverse + EIM inserts, port allocation, log);
+    steady: frames uniform over the pre-created flows (100 % hit)."""
+    subs = local_subscribers(n_subs, rank, world)
+    fl = S.flows(n_subs, flows_per_sub, seed)
+    mine = np.nonzero(np.isin(fl["sub"], subs))[0]
+    w = Workload("nat_cold_64" if cold else "nat_steady_64", "nat44_egress")
+    w.maps = _nat_maps(n_subs, subs)
+    every = mine
+    if cold:
+        pick = every[:n] if n < len(every) else every
+        w.headers = S.flow_frames(fl, pick, np.full(len(pick), 64, np.uint32), udp_zero_every=97)
+        w.lens = np.full(len(pick), 64, np.uint32)
+    else:
+        w.prewarm = [("nat44_egress", S.flow_frames(fl, every, np.full(len(every), 64, np.uint32), udp_zero_every=97),
+                      np.full(len(every), 64, np.uint32))]
+        pick = every[_pick(seed + 17 + rank, n, len(every))]
+        w.headers = S.flow_frames(fl, pick, np.full(n, 64, np.uint32), udp_zero_every=97)
+        w.lens = np.full(n, 64, np.uint32)
+    w.n_subs_local = len(subs)
+    w.info = {"flows": int(len(every))}
+    return w
+
+
+def pipeline(n: int, rank=0, world=1, n_subs=10_000, flows_per_sub=64, imix=True, seed=0xB2000004) -> Workload:
+    """Config #4: antispoof -> NAT44 -> QoS over 10 k subscribers (binding + port block + upload bucket with
+    the reference's policy tiers round-robin), 64 pre-warmed flows each, IMIX 7:4:1 or all-64 B frames,
+    1 % spoofed sources; bpf_ktime_get_ns() advances 1 ms per batch so buckets refill and most tiers drop."""
+    subs = local_subscribers(n_subs, rank, world)
+    fl = S.flows(n_subs, flows_per_sub, seed)
+    mine = np.nonzero(np.isin(fl["sub"], subs))[0]
+    w = Workload("pipeline_imix" if imix else "pipeline_64", "pipeline_up", imix=imix)
+    bk, bv = S.bindings(n_subs)
+    qk, qv = S.qos_buckets(n_subs, upload=True)
+    cfg = np.zeros(1, L.antispoof_config)
+    cfg["default_mode"], cfg["log_violations"] = L.ANTISPOOF_STRICT, 1
+    w.maps = [("subscriber_bindings", bk[subs], bv[subs]), ("antispoof_config", np.zeros(1, "<u4"), cfg),
+              ("qos_ingress", qk[subs], qv[subs])] + _nat_maps(n_subs, subs)
+    w.prewarm = [("nat44_egress", S.flow_frames(fl, mine, np.full(len(mine), 64, np.uint32), udp_zero_every=97),
+                  np.full(len(mine), 64, np.uint32))]
+    pick = mine[_pick(seed + 29 + rank, n, len(mine))]
+    lens = S.imix_lengths(n, seed + 31 + rank) if imix else np.full(n, 64, np.uint32)
+    hdr = S.flow_frames(fl, pick, lens, udp_zero_every=97)
+    spoof = (S.splitmix64_array(seed + 37 + rank, n) % np.uint64(100)) == 0
+    hdr[spoof, 27] ^= 0x10  # source address outside the binding
+    w.headers, w.lens, w.n_subs_local = hdr, lens, len(subs)
+    w.info = {"flows": int(len(mine)), "avg_frame_bytes": float(lens.mean())}
+    return w
+
+
+def qos(n: int, rank=0, world=1, n_subs=10_000, seed=0xB2000006) -> Workload:
+    subs = local_subscribers(n_subs, rank, world)
+    qk, qv = S.qos_buckets(n_subs, upload=True)
+    w = Workload("qos_64", "qos_ingress_prog")
+    w.maps = [("qos_ingress", qk[subs], qv[subs])]
+    sub = subs[_pick(seed + rank, n, len(subs))]
+    lens = np.full(n, 64, np.uint32)
+    w.headers = S.ipv4_headers(S.sub_mac_key(sub), np.uint64(GW_MAC), S.sub_ip(sub), np.uint32(0x08080808), 17, 5000, 53, lens)
+    w.lens, w.n_subs_local = lens, len(subs)
+    return w
+
+
+def dhcp(n: int, rank=0, world=1, n_subs=1 << 20, seed=0xB2000005, frame_len=362) -> Workload:
+    """Config #5: 1 M subscriber_pools entries over 64 ip_pools (/18, both DNS set => 50 B of options),
+    362 B requests (BOOTP 320 B), 80 % REQUEST / 20 % DISCOVER, option 53 first; 99 % known MAC (XDP_TX),
+    1 % unknown (XDP_PASS)."""
+    subs = local_subscribers(n_subs, rank, world)
+    w = Workload("dhcp", "dhcp_fastpath_prog")
+    pa = np.zeros(len(subs), L.pool_assignment)
+    pa["pool_id"] = 1 + (subs % 64)
+    pa["allocated_ip"] = S.ip_bytes(np.uint32(0x0A000000) + subs)
+    pa["lease_expiry"] = 1 << 62
+    pa["client_class"] = 1
+    pools = np.zeros(64, L.ip_pool)
+    base = (np.uint32(0x0A000000) + (np.arange(64, dtype=np.uint32) << 14)).astype(np.uint32)
+    pools["network"] = S.ip_bytes(base)
+    pools["prefix_len"] = 18
+    pools["gateway"] = S.ip_bytes(base + 1)
+    pools["dns_primary"] = S.ip_bytes(np.full(64, 0x08080808, np.uint32))
+    pools["dns_secondary"] = S.ip_bytes(np.full(64, 0x08080404, np.uint32))
+    pools["lease_time"] = 3600
+    cfg = np.zeros(1, L.dhcp_server_config)
+    cfg["server_mac"] = [[0x02, 0xAA, 0xBB, 0xCC, 0xDD, 0x01]]
+    cfg["server_ip"] = [[10, 255, 0, 1]]
+    w.maps = [("subscriber_pools", S.sub_mac_key(subs), pa), ("ip_pools", np.arange(1, 65, dtype="<u4"), pools),
+              ("server_config", np.zeros(1, "<u4"), cfg)]
+    sub = subs[_pick(seed + rank, n, len(subs))]
+    r = (S.splitmix64_array(seed ^ 0x99 + rank, n) % np.uint64(100)).astype(np.int64)
+    mac = S.sub_mac_key(sub)
+    mac = np.where(r == 0, mac | np.uint64(0x00F000000000), mac)
+    width = ((frame_len + 15) // 16) * 16
+    h = np.zeros((n, width), np.uint8)
+    h[:, 0:6] = 0xFF
+    h[:, 6:12] = S.mac_bytes(mac)
+    h[:, 12] = 0x08
+    h[:, 14] = 0x45
+    h[:, 16:18] = S.port_bytes(np.full(n, frame_len - 14))
+    h[:, 22], h[:, 23] = 64, 17
+    h[:, 30:34] = 0xFF
+    h[:, 24:26] = S.ip_checksum(h[:, 14:34])
+    h[:, 34:36] = S.port_bytes(np.full(n, 68))
+    h[:, 36:38] = S.port_bytes(np.full(n, 67))
+    h[:, 38:40] = S.port_bytes(np.full(n, frame_len - 34))
+    h[:, 42:46] = [1, 1, 6, 0]
+    xid = S.splitmix64_array(seed + 5 + rank, n)
+    for k in range(4):
+        h[:, 46 + k] = ((xid >> np.uint64(8 * k)) & np.uint64(0xFF)).astype(np.uint8)
+    h[:, 70:76] = S.mac_bytes(mac)
+    h[:, 278:282] = [0x63, 0x82, 0x53, 0x63]
+    h[:, 282:285] = np.stack([np.full(n, 53), np.full(n, 1), np.where(r % 5 == 1, 1, 3)], axis=1)
+    h[:, 285:292] = [55, 4, 1, 3, 15, 6, 255]
+    w.headers, w.lens, w.n_subs_local = h, np.full(n, frame_len, np.uint32), len(subs)
+    return w
+
+
+BUILDERS = {
+    "pipeline_imix": lambda n, r, wd: pipeline(n, r, wd, imix=True),
+    "pipeline_64": lambda n, r, wd: pipeline(n, r, wd, imix=False),
+    "antispoof_64": antispoof,
+    "nat_steady_64": lambda n, r, wd: nat(n, r, wd, cold=False),
+    "nat_cold_64": lambda n, r, wd: nat(n, r, wd, cold=True),
+    "qos_64": qos,
+    "dhcp": dhcp,
+}
+
+
+def slot16(lens: np.ndarray, imix: bool, width: int):
+    """Arena layout: (off16 u32[n] or None, stride, total 16-byte granules)."""
+    if not imix:
+        stride = ((width + 15) // 16) * 16
+        return None, stride, lens.shape[0] * stride // 16
+    slots = (lens.astype(np.uint64) + 15) // 16
+    off = np.zeros(lens.shape[0], np.uint64)
+    np.cumsum(slots[:-1], out=off[1:])
+    total = int(off[-1] + slots[-1]) + 4
+    assert total < (1 << 32)
+    return off.astype(np.uint32), 0, total

@@ -136,6 +136,9 @@ int bng_stats_device_ptr(bng_ctx *ctx, void **dptr, uint32_t *n_u64);
 uint64_t bng_launch_count(bng_ctx *ctx);  /* kernels launched by this context so far */
 uint64_t bng_lru_overflow(bng_ctx *ctx);  /* inserts refused because an LRU map was full (eviction not modelled) */
 uint64_t bng_events_lost(bng_ctx *ctx);   /* event records dropped because the staging buffer was full */
+/* per-kernel device timing (CUDA events around every launch); read returns "name launches total_ms\n" lines */
+int bng_prof_enable(bng_ctx *ctx, int on);
+int64_t bng_prof_read(bng_ctx *ctx, char *buf, uint64_t cap);
 void *bng_host_alloc(size_t bytes);       /* pinned host memory for BNG_MEM_HOST batches */
 void bng_host_free(void *p);
 
