@@ -100,9 +100,30 @@ struct DevCtx {
     u64 *stats;        // ST_COUNT counters
     EvRing spoof_ev;   // spoof_events, payload 56 B
     EvRing natlog_ev;  // nat_log_rb,   payload 40 B
+    const struct SmallTabs *small; // compact image of the tiny read-mostly maps (TMA-staged into shared memory)
     u32 batch_seq;
     u32 pad;
 };
+
+// Compact image of the maps that every frame consults but only the control
+// plane writes: antispoof_config, nat_config_map.flags, alg_ports (<= 64
+// entries) and hairpin_ips (<= 1000 entries, as a 2048-slot u32 hash).  The
+// host rebuilds it on every update of one of those maps; kernels bulk-copy it
+// into shared memory (cp.async.bulk + mbarrier) at block start.
+#define HP_SLOTS 2048
+#define HP_EMPTY 0xFFFFFFFFu
+struct __align__(16) SmallTabs {
+    u32 as_cfg;    // default_mode | log_violations << 8
+    u32 nat_flags; // nat_config.flags
+    u32 alg_n;
+    u32 hp_n;
+    u32 alg_key[64];  // (port << 16) | protocol, as the alg_ports key
+    u8 alg_type[64];  // alg_config.alg_type
+    u32 hp_hash[HP_SLOTS];
+};
+static_assert(sizeof(SmallTabs) % 16 == 0, "bulk copies move multiples of 16 bytes");
+
+__host__ __device__ __forceinline__ u32 hp_index(u32 ip) { return (ip * 0x9E3779B1u) >> 21; }
 
 // one batch, device view
 struct DevBatch {
@@ -138,11 +159,21 @@ __host__ __device__ __forceinline__ u64 splitmix64(u64 x) {
 __device__ __forceinline__ u16 bswap16(u16 x) { return (u16)((x << 8) | (x >> 8)); }
 __device__ __forceinline__ u32 bswap32(u32 x) { return __byte_perm(x, 0, 0x0123); }
 
+// 32-bit multiply/xorshift hash of the key words (cheap on the integer pipes;
+// slot placement is an internal matter, not part of the ABI).
+__device__ __forceinline__ u32 hash_word(u64 k, u32 seed) {
+    u32 h = ((u32)k * 0x9E3779B1u) ^ ((u32)(k >> 32) * 0x85EBCA77u) ^ seed;
+    h ^= h >> 16;
+    h *= 0x7FEB352Du;
+    h ^= h >> 15;
+    return h;
+}
+
 template <int KW>
-__device__ __forceinline__ u64 tbl_hash(const u64 *k) {
-    u64 h = 0x9e3779b97f4a7c15ull;
+__device__ __forceinline__ u32 tbl_hash(const u64 *k) {
+    u32 h = 0x2545F491u;
 #pragma unroll
-    for (int i = 0; i < KW; i++) h = mix64(h ^ k[i]);
+    for (int i = 0; i < KW; i++) h = hash_word(k[i], h);
     return h;
 }
 
@@ -282,6 +313,18 @@ __device__ __forceinline__ void bstats_flush(BlockStats &s, u64 *g) {
         if (s.v[i]) atomicAdd(&g[i], s.v[i]);
 }
 
+// Flush a per-thread register counter: warp reduction, one shared atomic per
+// warp.  Must be reached by all 32 lanes.
+__device__ __forceinline__ void warp_stat_flush(BlockStats &s, int idx, u32 v) {
+    u32 t = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && t) atomicAdd(&s.v[idx], (u64)t);
+}
+__device__ __forceinline__ void warp_stat_flush64(BlockStats &s, int idx, u64 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s.v[idx], v);
+}
+
 // Warp-aggregated increment of a shared counter: one shared atomic per warp.
 __device__ __forceinline__ void bstats_inc_pred(BlockStats &s, int idx, bool pred) {
     unsigned m = __ballot_sync(__activemask(), pred);
@@ -388,4 +431,78 @@ __device__ __forceinline__ u16 csum_upd16(u16 csum, u16 old_val, u16 new_val) {
     sum += ~(u32)old_val & 0xffff;
     sum += (u32)new_val & 0xffff;
     return csum_fold32(sum);
+}
+
+// ---------------------------------------------------------------------------
+// TMA bulk copy of a small global image into shared memory (sm_90+/sm_100a):
+// one thread arms an mbarrier with the byte count and issues cp.async.bulk;
+// everyone waits on the barrier's phase 0.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void smem_stage_begin(void *smem_dst, const void *gsrc, u32 bytes, u64 *bar) {
+    if (threadIdx.x == 0) {
+        u32 bar_a = (u32)__cvta_generic_to_shared(bar);
+        u32 dst_a = (u32)__cvta_generic_to_shared(smem_dst);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_a),
+                     "l"(gsrc), "r"(bytes), "r"(bar_a)
+                     : "memory");
+    }
+    __syncthreads(); // the barrier is initialised before anyone polls it
+}
+__device__ __forceinline__ void smem_stage_wait(u64 *bar) {
+    u32 bar_a = (u32)__cvta_generic_to_shared(bar);
+    u32 done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar_a)
+            : "memory");
+    }
+}
+
+__device__ __forceinline__ bool hp_contains(const SmallTabs &st, u32 ip) {
+    if (ip == HP_EMPTY) return (st.hp_n >> 31) != 0;
+    if ((st.hp_n & 0x7fffffffu) == 0) return false;
+    u32 i = hp_index(ip);
+    for (u32 probe = 0; probe < HP_SLOTS; probe++) {
+        u32 v = st.hp_hash[i];
+        if (v == ip) return true;
+        if (v == HP_EMPTY) return false;
+        i = (i + 1) & (HP_SLOTS - 1);
+    }
+    return false;
+}
+__device__ __forceinline__ int alg_find(const SmallTabs &st, u32 key) { // index into alg_type[] or -1
+    for (u32 i = 0; i < st.alg_n; i++)
+        if (st.alg_key[i] == key) return (int)i;
+    return -1;
+}
+
+// Continue a probe whose first slot (index i0) has already been fetched:
+// w0 is that slot's state word, rest_eq whether the remaining key words
+// matched.  Read-only tables (no concurrent inserts in this kernel).
+template <int KW>
+__device__ __forceinline__ u8 *tbl_finish(const Tbl &t, const u64 *k, u32 i0, u64 w0, bool rest_eq) {
+    if (k[0] >= K_BUSY) return nullptr;
+    if (w0 == k[0] && rest_eq) return tbl_slot(t, i0);
+    if (w0 == K_EMPTY) return nullptr;
+    u32 i = (i0 + 1) & t.mask;
+    for (u32 probe = 1; probe <= t.mask; probe++) {
+        u8 *s = tbl_slot(t, i);
+        u64 w = *(const u64 *)s;
+        if (w == K_EMPTY) return nullptr;
+        if (w == k[0]) {
+            bool eq = true;
+#pragma unroll
+            for (int j = 1; j < KW; j++) eq = eq && (((const u64 *)s)[j] == k[j]);
+            if (eq) return s;
+        }
+        i = (i + 1) & t.mask;
+    }
+    return nullptr;
 }

@@ -242,6 +242,9 @@ bool lpm_same(u32 pl, u32 a, u32 b) { // first pl bits equal, bytes in memory or
 // ===========================================================================
 extern "C" {
 
+static int small_refresh(bng_ctx *c);
+static bool feeds_small_tabs(const MapReg *m);
+
 uint32_t bng_abi_version(void) { return BNG_ABI_VERSION; }
 
 const char *bng_last_error(bng_ctx *ctx) { return ctx ? ctx->err.c_str() : g_open_err.c_str(); }
@@ -356,6 +359,7 @@ bng_ctx *bng_open(const bng_open_opts *o) {
     OPEN_CU(cudaMalloc((void **)&c->L.s.counters, 64));
     OPEN_R(ensure_scratch(c, opts.max_batch ? opts.max_batch : (1u << 22)));
     OPEN_R(ensure_io(c, 1 << 20));
+    OPEN_R(dev_alloc(c, (void **)&d.small, sizeof(SmallTabs), 0xFF));
 
     // registry: the reference's map names, types, sizes (bpf/antispoof.c:71-119,
     // bpf/qos_ratelimit.c:37-65, bpf/nat44.c:218-320, bpf/maps.h:99-234)
@@ -385,6 +389,7 @@ bng_ctx *bng_open(const bng_open_opts *o) {
     add_stats(c, "stats_map", T_ARRAY, 80, ST_DHCP);
     add_hash(c, "circuit_id_map", T_HASH, 8, 8, max_subs, &d.cid_map);
     add_hash(c, "circuit_id_subscribers", T_HASH, 32, 25, max_subs, &d.cid_subs);
+    OPEN_R(small_refresh(c));
     cudaError_t se = cudaStreamSynchronize(c->L.stream);
     if (se != cudaSuccess) {
         fail(nullptr, 0, "init: %s", cudaGetErrorString(se));
@@ -430,6 +435,9 @@ int bng_map_get_info(bng_ctx *c, int map, bng_map_info *out) {
     return 0;
 }
 
+static int small_refresh(bng_ctx *c);
+static bool feeds_small_tabs(const MapReg *m);
+
 int bng_map_update_batch(bng_ctx *c, int map, const void *keys, const void *values, uint64_t n, uint64_t flags) {
     MapReg *m = get_map(c, map);
     if (!m || !keys || !values) return -EINVAL;
@@ -440,6 +448,7 @@ int bng_map_update_batch(bng_ctx *c, int map, const void *keys, const void *valu
     case KIND_HASH: {
         int first = 0;
         int r = hash_cmd(c, m, TOP_UPDATE, keys, (void *)values, n, (u32)flags, &first);
+        if (!r && feeds_small_tabs(m)) r = small_refresh(c);
         return r ? r : first;
     }
     case KIND_ARRAY:
@@ -453,7 +462,7 @@ int bng_map_update_batch(bng_ctx *c, int map, const void *keys, const void *valu
                                   c->L.stream));
         }
         CU(c, cudaStreamSynchronize(c->L.stream));
-        return 0;
+        return feeds_small_tabs(m) ? small_refresh(c) : 0;
     case KIND_LPM:
         for (u64 i = 0; i < n; i++) {
             const u32 *k = (const u32 *)((const u8 *)keys + i * 8);
@@ -529,6 +538,7 @@ int bng_map_delete(bng_ctx *c, int map, const void *key) {
     if (m->kind == KIND_HASH) {
         int first = 0;
         int r = hash_cmd(c, m, TOP_DELETE, key, nullptr, 1, 0, &first);
+        if (!r && !first && feeds_small_tabs(m)) r = small_refresh(c);
         return r ? r : first;
     }
     if (m->kind == KIND_LPM) {
@@ -543,11 +553,78 @@ int bng_map_delete(bng_ctx *c, int map, const void *key) {
     return -EINVAL; // arrays cannot be deleted from (kernel: -EINVAL)
 }
 
+static int64_t map_dump_locked(bng_ctx *c, MapReg *m, void *keys_out, void *values_out, uint64_t cap);
+
 int64_t bng_map_dump(bng_ctx *c, int map, void *keys_out, void *values_out, uint64_t cap) {
     MapReg *m = get_map(c, map);
     if (!m || !keys_out || !values_out) return -EINVAL;
     std::lock_guard<std::mutex> g(c->mu);
     cudaSetDevice(c->device);
+    return map_dump_locked(c, m, keys_out, values_out, cap);
+}
+
+// Rebuilds the SmallTabs image from the authoritative device state of
+// antispoof_config, nat_config_map, alg_ports and hairpin_ips and uploads it.
+static int small_refresh(bng_ctx *c) {
+    SmallTabs *im = new SmallTabs();
+    memset(im, 0, sizeof(*im));
+    for (u32 i = 0; i < HP_SLOTS; i++) im->hp_hash[i] = HP_EMPTY;
+    u8 cfg[16];
+    int rc = 0;
+    cudaError_t e = cudaMemcpy(cfg, c->dev.as_config, 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) {
+        im->as_cfg = (u32)cfg[0] | ((u32)cfg[1] << 8);
+        e = cudaMemcpy(cfg, c->dev.nat_config, 16, cudaMemcpyDeviceToHost);
+    }
+    if (e == cudaSuccess) memcpy(&im->nat_flags, cfg, 4);
+    if (e != cudaSuccess) rc = fail(c, -EIO, "small_refresh: %s", cudaGetErrorString(e));
+    MapReg *alg = nullptr, *hp = nullptr;
+    for (auto &m : c->maps) {
+        if (!strcmp(m.name, "alg_ports")) alg = &m;
+        if (!strcmp(m.name, "hairpin_ips")) hp = &m;
+    }
+    if (!rc && alg) {
+        u32 keys[64];
+        u8 vals[64 * 8];
+        int64_t n = map_dump_locked(c, alg, keys, vals, 64);
+        if (n < 0) rc = (int)n;
+        for (int64_t i = 0; !rc && i < n; i++) {
+            im->alg_key[i] = keys[i];
+            im->alg_type[i] = vals[i * 8 + 3];
+        }
+        if (!rc) im->alg_n = (u32)n;
+    }
+    if (!rc && hp) {
+        std::vector<u32> keys(1000);
+        std::vector<u8> vals(1000);
+        int64_t n = map_dump_locked(c, hp, keys.data(), vals.data(), 1000);
+        if (n < 0) rc = (int)n;
+        u32 bcast = 0;
+        for (int64_t i = 0; !rc && i < n; i++) {
+            if (keys[i] == HP_EMPTY) { // 255.255.255.255 cannot live in the u32 hash: flagged in hp_n bit 31
+                bcast = 0x80000000u;
+                continue;
+            }
+            u32 s = hp_index(keys[i]);
+            while (im->hp_hash[s] != HP_EMPTY) s = (s + 1) & (HP_SLOTS - 1);
+            im->hp_hash[s] = keys[i];
+        }
+        if (!rc) im->hp_n = (u32)n | bcast;
+    }
+    if (!rc) {
+        e = cudaMemcpy((void *)c->dev.small, im, sizeof(SmallTabs), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) rc = fail(c, -EIO, "small_refresh upload: %s", cudaGetErrorString(e));
+    }
+    delete im;
+    return rc;
+}
+
+static bool feeds_small_tabs(const MapReg *m) {
+    return !strcmp(m->name, "antispoof_config") || !strcmp(m->name, "nat_config_map") || !strcmp(m->name, "alg_ports") ||
+           !strcmp(m->name, "hairpin_ips");
+}
+
+static int64_t map_dump_locked(bng_ctx *c, MapReg *m, void *keys_out, void *values_out, uint64_t cap) {
     if (m->kind == KIND_LPM) {
         u64 n = std::min<u64>(cap, m->lpm_host.size() / 3);
         for (u64 i = 0; i < n; i++) {

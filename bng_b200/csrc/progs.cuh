@@ -42,13 +42,13 @@ __device__ __forceinline__ void spoof_log(const DevCtx &c, BlockStats &bs, u32 i
     bstats_add(bs, ST_AS_LOGGED, 1);
 }
 
-__device__ __forceinline__ int antispoof_one(const DevCtx &c, BlockStats &bs, const Hdr64 &h, u32 len, u32 idx,
-                                             u64 now) {
+// `bind` is the subscriber_bindings slot of the frame's source MAC (or null),
+// `cfg` = default_mode | log_violations << 8; packets_allowed is counted in the
+// caller's register counter n_allowed (flushed once per thread).
+__device__ __forceinline__ int antispoof_eval(const DevCtx &c, BlockStats &bs, const Hdr64 &h, u32 len, u32 idx, u64 now,
+                                              const u8 *bind, u32 cfg, u32 &n_allowed) {
     if (len < 14) return TC_OK; // :195-196, no stats
-    u64 mk = mac_key(h, 6);
-    u32 cfg = *(const u16 *)c.as_config; // default_mode | log_violations << 8
     u32 default_mode = cfg & 0xff, log_viol = (cfg >> 8) & 0xff;
-    const u8 *bind = tbl_find<1, false>(c.bindings, &mk);
     u32 b_ipv4 = 0, b_flags = 0; // flags word: ipv4_valid | ipv6_valid<<8 | mode<<16
     if (bind) {
         b_ipv4 = *(const u32 *)(bind + 8);
@@ -56,7 +56,7 @@ __device__ __forceinline__ int antispoof_one(const DevCtx &c, BlockStats &bs, co
     }
     u32 mode = bind ? ((b_flags >> 16) & 0xff) : default_mode;
     if (mode == 0) { // ANTISPOOF_DISABLED :213-216
-        bstats_add(bs, ST_AS_ALLOWED, 1);
+        n_allowed++;
         return TC_OK;
     }
     u32 proto = h.b16(12);
@@ -72,14 +72,14 @@ __device__ __forceinline__ int antispoof_one(const DevCtx &c, BlockStats &bs, co
         if (!allowed) {
             if (log_viol) spoof_log(c, bs, idx, now, h, src, bind ? b_ipv4 : 0, false);
             if (mode == 3) {
-                bstats_add(bs, ST_AS_ALLOWED, 1);
+                n_allowed++;
                 return TC_OK;
             }
             bstats_add(bs, ST_AS_DROPPED, 1);
             bstats_add(bs, ST_AS_V4_VIOL, 1);
             return TC_SHOT;
         }
-        bstats_add(bs, ST_AS_ALLOWED, 1);
+        n_allowed++;
         return TC_OK;
     }
     if (proto == ETH_P_IPV6_LE) {
@@ -99,10 +99,10 @@ __device__ __forceinline__ int antispoof_one(const DevCtx &c, BlockStats &bs, co
             bstats_add(bs, ST_AS_V6_VIOL, 1);
             return TC_SHOT;
         }
-        bstats_add(bs, ST_AS_ALLOWED, 1);
+        n_allowed++;
         return TC_OK;
     }
-    bstats_add(bs, ST_AS_ALLOWED, 1); // :290-292
+    n_allowed++; // :290-292
     return TC_OK;
 }
 
@@ -126,6 +126,17 @@ __device__ __forceinline__ void tb_load(TokenBucket &tb, const u8 *slot) {
 
 // token_bucket_check(), bpf/qos_ratelimit.c:70-104, one frame; all arithmetic
 // is u64 with natural wrap-around, exactly as the eBPF program computes it.
+// The refill half of token_bucket_check() (:80-94).  Idempotent for a given
+// `now`: a second call sees elapsed == 0 and tokens already clamped.
+__device__ __forceinline__ void tb_refill(TokenBucket &tb, u64 now) {
+    if (tb.last_update == now && tb.tokens <= (u64)tb.burst) return;
+    u64 elapsed = now - tb.last_update;
+    u64 add = (elapsed * (tb.rate_bps / 8)) / 1000000000ull;
+    tb.tokens += add;
+    if (tb.tokens > (u64)tb.burst) tb.tokens = tb.burst;
+    tb.last_update = now;
+}
+
 __device__ __forceinline__ bool tb_step(TokenBucket &tb, u64 now, u32 pkt_len) {
     u64 elapsed = now - tb.last_update;
     u64 add = (elapsed * (tb.rate_bps / 8)) / 1000000000ull;
