@@ -198,12 +198,13 @@ def run_gpu(a):
         dist.init_process_group("nccl", device_id=dev)
     n = a.frames
     wl = W.BUILDERS[a.workload](n, rank, world)
-    dp = Dataplane(device=local, max_batch=max(n, 1 << 20), rank=rank, world=world)
+    dp = Dataplane(device=local, max_batch=max(n, 1 << 20), rank=rank, world=world,
+                   **({} if a.reference_capacities else W.sizing(wl)))
     for m, k, v in wl.maps:
         r = dp.update_batch(m, as_bytes(k), as_bytes(v))
         assert r == 0, (m, r)
     hw = wl.headers.shape[1]
-    off16, stride, total16 = W.slot16(wl.lens, wl.imix, hw)
+    off16, stride, total16 = W.slot16(wl.lens, wl.imix, hw, a.align)
     hdr_d = torch.from_numpy(wl.headers).to(dev)
     len0_d = torch.from_numpy(wl.lens.astype(np.int32)).to(dev)
     len_d = len0_d.clone()
@@ -217,12 +218,15 @@ def run_gpu(a):
     lib_stream = torch.cuda.ExternalStream(dp.stream, device=dev)
 
     def restore():
+        dp.sync()  # the previous step (asynchronous on the library's stream) must be done with the arena
         if off16 is None:
             arena_d[: n * stride].view(n, stride)[:, :hw] = hdr_d
         else:
             a16[gidx.reshape(-1)] = hdr_d.view(-1, 16)
         len_d.copy_(len0_d)
         torch.cuda.synchronize()
+        for ring in ("spoof_events", "nat_log_rb"):  # the event consumer keeps the staging rings empty (untimed)
+            dp.drain(ring)
 
     for prog, h, l in wl.prewarm:  # e.g. create the NAT sessions of every flow once (cold start)
         ph = torch.from_numpy(h).to(dev).reshape(-1)
@@ -259,7 +263,8 @@ def run_gpu(a):
     dp.sync()
     torch.cuda.synchronize()
     launches = dp.launch_count - launches0
-    total_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    total_ms = sum(step_ms)
     tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.barrier()
@@ -353,7 +358,10 @@ def run_gpu(a):
             "dtype": "u8/u32/u64 integer", "data": "synthetic",
             "config": {"workload": wl.name, "program": wl.prog, "frames_per_gpu_per_step": n,
                        "subscribers_this_gpu": wl.n_subs_local, "sharding": f"splitmix64(mac) % {world}",
-                       "avg_frame_bytes": round(float(wl.lens.mean()), 1),
+                       "avg_frame_bytes": round(float(wl.lens.mean()), 1), "frame_align": a.align if wl.imix else stride,
+                       "step_ms_min_med_max": [round(float(x), 4) for x in
+                                               (min(step_ms), float(np.median(step_ms)), max(step_ms))],
+                       "step_ms_all": [round(float(x), 3) for x in step_ms],
                        "l2_policy": "inputs larger than L2 (arena %.0f MB + tables) and rewritten between steps" % (arena_bytes / 1e6),
                        **wl.info},
             "wire_gbps": round(value * 1e6 * float(wl.lens.mean()) * 8 / 1e9, 1),
@@ -382,6 +390,9 @@ def main():
     ap.add_argument("--frames", type=int, default=1 << 22)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--reference-capacities", action="store_true",
+                    help="size every table for the reference's compile-time max_entries instead of the workload")
+    ap.add_argument("--align", type=int, default=64, help="frame placement granularity in the IMIX arena (16 or 64)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":

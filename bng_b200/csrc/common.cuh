@@ -59,7 +59,49 @@ struct Tbl {
     u32 max_entries; // the reference map's max_entries
     u32 key_size;
     u32 value_size;
+    u32 vlayout; // 0: value stored verbatim at voff; VL_SESSION: nat_sessions hot/cold layout below
+    u32 pad;
 };
+
+// nat_sessions slots are 128 B: the first 64-byte DRAM granule holds everything
+// the per-frame hit paths read or update (key, translation, counters), the
+// second the fields only creation / control-plane reads touch.  The reference
+// layout of struct nat_session (bpf/nat44.c:123-141) is restored by
+// ses_abi_to_slot() whenever a value crosses the ABI.
+#define VL_SESSION 1u
+enum {
+    SES_NAT_IP = 16,    // u32
+    SES_NAT_PORT = 20,  // u16
+    SES_ORIG_PORT = 22, // u16
+    SES_ORIG_IP = 24,   // u32
+    SES_STATE = 28,     // u8 state, protocol@29, flags@30, is_hairpin@31
+    SES_LAST_SEEN = 32, // u64
+    SES_PKTS_OUT = 40,
+    SES_BYTES_OUT = 48,
+    SES_PKTS_IN = 56,
+    SES_BYTES_IN = 64,
+    SES_CREATED = 72,
+    SES_DEST_IP = 80,   // u32
+    SES_DEST_PORT = 84, // u16, _pad1@86, implicit padding@88, tail padding@92
+};
+// byte offset inside struct nat_session -> byte offset inside the slot
+__host__ __device__ __forceinline__ u32 ses_abi_to_slot(u32 a) {
+    if (a < 4) return SES_NAT_IP + a;
+    if (a < 6) return SES_NAT_PORT + (a - 4);
+    if (a < 8) return SES_ORIG_PORT + (a - 6);
+    if (a < 12) return SES_ORIG_IP + (a - 8);
+    if (a < 16) return SES_DEST_IP + (a - 12);
+    if (a < 20) return SES_DEST_PORT + (a - 16);
+    if (a < 24) return 88 + (a - 20);
+    if (a < 32) return SES_LAST_SEEN + (a - 24);
+    if (a < 40) return SES_CREATED + (a - 32);
+    if (a < 48) return SES_PKTS_OUT + (a - 40);
+    if (a < 56) return SES_PKTS_IN + (a - 48);
+    if (a < 64) return SES_BYTES_OUT + (a - 56);
+    if (a < 72) return SES_BYTES_IN + (a - 64);
+    if (a < 76) return SES_STATE + (a - 72);
+    return 92 + (a - 76);
+}
 
 struct LpmTbl { // BPF_MAP_TYPE_LPM_TRIE with a 4-byte address: {prefixlen, addr bytes, value}
     u32 *ents;  // 3 x u32 per entry: prefixlen, addr (memory order), value

@@ -95,14 +95,17 @@ int dev_alloc(bng_ctx *c, void **p, size_t bytes, int fill) {
     return 0;
 }
 
-int make_table(bng_ctx *c, Tbl *t, u32 key_size, u32 value_size, u32 voff, u32 max_entries) {
+int make_table(bng_ctx *c, Tbl *t, u32 key_size, u32 value_size, u32 voff, u32 max_entries, u32 vlayout = 0,
+               u32 slot_bytes = 0) {
     u32 cap = pow2_at_least(std::max<u64>(64, (u64)max_entries * 2));
     t->mask = cap - 1;
     t->voff = voff;
     t->key_size = key_size;
     t->value_size = value_size;
     t->max_entries = max_entries;
-    t->slot_bytes = (voff + value_size + 31u) & ~31u;
+    t->vlayout = vlayout;
+    t->pad = 0;
+    t->slot_bytes = slot_bytes ? slot_bytes : ((voff + value_size + 31u) & ~31u);
     int r = dev_alloc(c, (void **)&t->slots, (size_t)cap * t->slot_bytes, 0xFF);
     if (r) return r;
     return dev_alloc(c, (void **)&t->count, 16, 0);
@@ -337,7 +340,7 @@ bng_ctx *bng_open(const bng_open_opts *o) {
     OPEN_R(make_table(c, &d.qos_eg, 4, 32, 16, max_subs));
     OPEN_R(make_table(c, &d.qos_in, 4, 32, 16, max_subs));
     OPEN_R(make_table(c, &d.sub_nat, 4, 64, 8, max_subs));
-    OPEN_R(make_table(c, &d.sessions, 16, 80, 16, max_sess));
+    OPEN_R(make_table(c, &d.sessions, 16, 80, 16, max_sess, VL_SESSION, 128));
     OPEN_R(make_table(c, &d.reverse, 16, 16, 16, max_sess));
     OPEN_R(make_table(c, &d.eim, 8, 32, 8, max_eim));
     OPEN_R(make_table(c, &d.hairpin, 4, 1, 8, 1000));

@@ -126,162 +126,7 @@ __global__ void __launch_bounds__(BLOCK) k_nat_hairpin_xdp(const __grid_constant
     bstats_flush(bs, c.stats);
 }
 
-// ---------------------------------------------------------------------------
-// pipeline_up classify: antispoof_ingress -> nat44_egress -> qos_ingress_prog
-// keyed on the pre-NAT source address.  All three stages
-// key their mutable state on the subscriber's private address, so one
-// group-by serves both the NAT new-flow ordering and the token-bucket
-// ordering.  Ordering key: the qos_ingress bucket slot when the subscriber
-// has a bucket, else qos capacity + subscriber_nat slot.  MISS_FLAG in the
-// value marks frames whose NAT session has to be created in the ordered phase.
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(BLOCK, 6)
-    k_pipe_classify(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b, u32 *skey, u32 *sval) {
-    __shared__ SmallTabs st;
-    __shared__ BlockStats bs;
-    __shared__ u64 bar;
-    smem_stage_begin(&st, c.small, (u32)sizeof(SmallTabs), &bar);
-    bstats_init(bs);
-    smem_stage_wait(&bar);
-    const u32 as_cfg = st.as_cfg, nflags = st.nat_flags;
-    u32 n_allowed = 0, n_snat = 0;
-    for (u32 i = blockIdx.x * BLOCK + threadIdx.x; i < b.n; i += gridDim.x * BLOCK) {
-        u32 len = b.len[i];
-        u8 *p = frame_ptr(b, i);
-        Hdr64 h;
-        hdr_load(h, p, len);
-
-        // ---- issue the first probe of every table this frame may need ----
-        const bool ip4 = len >= 34 && h.b16(12) == ETH_P_IP_LE;
-        const u32 saddr = h.b32(26), daddr = h.b32(30), proto = h.b8(23);
-        const bool ihl5 = (h.b8(14) & 0x0f) == 5;
-        u64 mk = mac_key(h, 6);
-        u32 bi = tbl_hash<1>(&mk) & c.bindings.mask;
-        u64 bw0 = *(const u64 *)tbl_slot(c.bindings, bi);
-        u64 sk = saddr;
-        u32 ai = tbl_hash<1>(&sk); // subscriber_nat and qos_ingress share the key, hence the hash
-        u32 si = ai & c.sub_nat.mask, qi = ai & c.qos_in.mask;
-        u16 sport = 0, dport = 0;
-        if (proto == 1) {
-            sport = h.b16(38);
-        } else {
-            sport = h.b16(34);
-            dport = h.b16(36);
-        }
-        u64 key[2];
-        key[0] = (u64)saddr | ((u64)daddr << 32);
-        key[1] = (u64)sport | ((u64)dport << 16) | ((u64)proto << 32);
-        u32 hi = tbl_hash<2>(key) & c.sessions.mask;
-        u64 sw0 = K_EMPTY, qw0 = K_EMPTY, kw0 = K_EMPTY, kw1 = 0;
-        if (ip4) {
-            sw0 = *(const u64 *)tbl_slot(c.sub_nat, si);
-            qw0 = *(const u64 *)tbl_slot(c.qos_in, qi);
-            const ulonglong2 kk = *(const ulonglong2 *)tbl_slot(c.sessions, hi);
-            kw0 = kk.x;
-            kw1 = kk.y;
-        }
-
-        // ---- antispoof_ingress ----
-        const u8 *bind = len >= 14 ? tbl_finish<1>(c.bindings, &mk, bi, bw0, true) : nullptr;
-        int v = antispoof_eval(c, bs, h, len, i, b.now, bind, as_cfg, n_allowed);
-        u32 okey = NO_KEY, oval = i;
-        if (v != TC_SHOT && ip4) {
-            // ---- qos_ingress bucket of the pre-NAT source (nothing counted yet) ----
-            const u8 *qsl = tbl_finish<1>(c.qos_in, &sk, qi, qw0, true);
-            u32 qs = qsl ? (u32)((qsl - c.qos_in.slots) / c.qos_in.slot_bytes) : NO_KEY;
-            // ---- nat44_egress ----
-            bool miss = false;
-            u32 sub_idx = 0;
-            if (!ihl5) { // IPv4 options: fields are not at fixed offsets, take the generic path
-                NatOut o = nat_egress_one<false>(c, bs, p, len, i, b.now);
-                v = o.verdict;
-                miss = o.order_key != NO_KEY;
-                sub_idx = o.order_key;
-            } else if (is_private_ip(saddr)) {
-                const u8 *sub = tbl_finish<1>(c.sub_nat, &sk, si, sw0, true);
-                if (!sub) {
-                    bstats_add(bs, ST_NAT_PASSED, 1);
-                } else {
-                    bool stop = false;
-                    if (proto == 6 || proto == 17) {
-                        if ((proto == 6 ? 54u : 42u) > len) {
-                            stop = true;
-                        } else if ((nflags & (proto == 6 ? (NATF_ALG_FTP | NATF_ALG_SIP) : NATF_ALG_SIP)) && st.alg_n) {
-                            int ai2 = alg_find(st, ((u32)bswap16(dport) << 16) | proto);
-                            if (ai2 >= 0) { // bpf/nat44.c:615-642
-                                bstats_add(bs, ST_NAT_ALG, 1);
-                                nat_log(c, i, b.now, 7, *(const u32 *)(sub + 32), saddr, 0, sport, 0, daddr, dport, (u8)proto,
-                                        st.alg_type[ai2]);
-                                stop = true;
-                            }
-                        }
-                    } else if (proto == 1) {
-                        if (42u > len) stop = true;
-                    } else {
-                        stop = true;
-                    }
-                    if (!stop) {
-                        if ((nflags & NATF_HAIRPIN) && hp_contains(st, daddr)) bstats_add(bs, ST_NAT_HAIRPIN, 1);
-                        u8 *ses = tbl_finish<2>(c.sessions, key, hi, kw0, kw1 == key[1]);
-                        if (ses) { // bpf/nat44.c:674-680 and the rewrite of :752-798, on the register copy
-                            u32 nat_ip = *(const u32 *)(ses + 16);
-                            u16 nat_port = *(const u16 *)(ses + 20);
-                            *(u64 *)(ses + 40) = b.now;
-                            atomicAdd((u64 *)(ses + 56), 1ull);
-                            atomicAdd((u64 *)(ses + 72), (u64)len);
-                            h.s32(26, nat_ip);
-                            h.s16(24, csum_upd32(h.b16(24), saddr, nat_ip));
-                            if (proto == 6) {
-                                h.s16(34, nat_port);
-                                u16 ck = csum_upd32(h.b16(50), saddr, nat_ip);
-                                h.s16(50, csum_upd16(ck, sport, nat_port));
-                                hdr_store_chunk(h, p, 3);
-                            } else if (proto == 17) {
-                                h.s16(34, nat_port);
-                                u16 ck = h.b16(40);
-                                if (ck != 0) {
-                                    ck = csum_upd32(ck, saddr, nat_ip);
-                                    ck = csum_upd16(ck, sport, nat_port);
-                                    if (ck == 0) ck = 0xffff;
-                                    h.s16(40, ck);
-                                }
-                            } else {
-                                h.s16(38, nat_port);
-                                h.s16(36, csum_upd16(h.b16(36), sport, nat_port));
-                            }
-                            hdr_store_chunk(h, p, 1);
-                            hdr_store_chunk(h, p, 2);
-                            n_snat++;
-                        } else {
-                            miss = true;
-                            sub_idx = (u32)((sub - c.sub_nat.slots) / c.sub_nat.slot_bytes);
-                        }
-                    }
-                }
-            }
-            if (v != TC_SHOT) {
-                if (qs != NO_KEY) {
-                    u64 rate = *(const u64 *)(qsl + 32);
-                    if (!miss && rate == 0) { // unlimited bucket and nothing left to order
-                        bstats_add(bs, ST_QOS_PASS_PKTS, 1);
-                        bstats_add(bs, ST_QOS_PASS_BYTES, len);
-                    } else {
-                        okey = qs;
-                    }
-                } else if (miss) {
-                    okey = (c.qos_in.mask + 1) + sub_idx;
-                }
-                if (miss) oval |= MISS_FLAG;
-            }
-        }
-        b.verdict[i] = (u8)v;
-        skey[i] = okey;
-        sval[i] = oval;
-    }
-    warp_stat_flush(bs, ST_AS_ALLOWED, n_allowed);
-    warp_stat_flush(bs, ST_NAT_SNAT, n_snat);
-    bstats_flush(bs, c.stats);
-}
+#include "pipe_classify.cuh"
 
 // ---------------------------------------------------------------------------
 // GROUP: stable LSD radix sort with compaction and device-side counts.
@@ -299,7 +144,7 @@ __device__ __forceinline__ void rs_range(u32 total, u32 &lo, u32 &hi) {
     hi = r < total ? (u32)r : total;
 }
 
-__global__ void __launch_bounds__(BLOCK) k_rs_hist(const u32 *keys, u32 n_host, const u32 *cnt, int first, int shift, u32 *H) {
+__global__ void __launch_bounds__(BLOCK) k_rs_hist(const u32 *keys, u32 n_host, const u32 *cnt, int first, int shift, u32 *H, u32 *T) {
     __shared__ u32 h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
@@ -311,32 +156,49 @@ __global__ void __launch_bounds__(BLOCK) k_rs_hist(const u32 *keys, u32 n_host, 
         if (k != NO_KEY) atomicAdd(&h[(k >> shift) & 0xff], 1u);
     }
     __syncthreads();
-    H[threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];
+    u32 v = h[threadIdx.x];
+    H[threadIdx.x * gridDim.x + blockIdx.x] = v;
+    if (v) atomicAdd(&T[threadIdx.x], v); // per-digit totals over all blocks
 }
 
-// exclusive scan of the 256 x nblocks histogram in (digit, block) order; single block of 1024 threads
-__global__ void __launch_bounds__(1024) k_rs_scan(u32 *H, u32 nblocks, u32 *cnt, int first) {
-    __shared__ u32 part[1024];
-    u32 total = 256 * nblocks;
-    u32 per = (total + 1023) / 1024;
-    u32 lo = threadIdx.x * per, hi = lo + per < total ? lo + per : total;
-    u32 s = 0;
-    for (u32 i = lo; i < hi; i++) s += H[i];
-    part[threadIdx.x] = s;
+// Exclusive scan of the 256 x nblocks histogram in (digit, block) order.  One block per digit:
+// base = total of the smaller digits (from T), then a block-wide scan of the digit's row.
+__global__ void __launch_bounds__(1024) k_rs_scan(u32 *H, const u32 *T, u32 nblocks, u32 *cnt, int first) {
+    __shared__ u32 wsum[32];
+    __shared__ u32 s_base;
+    const u32 d = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    u32 t = (threadIdx.x < 256 && threadIdx.x < d) ? T[threadIdx.x] : 0; // digits below d
+    t = __reduce_add_sync(0xffffffffu, t);
+    if (lane == 0) wsum[w] = t;
     __syncthreads();
-    for (u32 off = 1; off < 1024; off <<= 1) { // Hillis-Steele inclusive scan
-        u32 v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
-        __syncthreads();
-        part[threadIdx.x] += v;
-        __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 b = 0;
+        for (int i = 0; i < 8; i++) b += wsum[i];
+        s_base = b;
     }
-    u32 run = part[threadIdx.x] - s;
-    for (u32 i = lo; i < hi; i++) {
-        u32 v = H[i];
-        H[i] = run;
-        run += v;
+    __syncthreads();
+    u32 v = threadIdx.x < nblocks ? H[d * nblocks + threadIdx.x] : 0;
+    u32 inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (u32)o) inc += n;
     }
-    if (first && threadIdx.x == 1023) cnt[CNT_M] = part[1023];
+    __syncthreads();
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        u32 x = wsum[lane], xi = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 n = __shfl_up_sync(0xffffffffu, xi, o);
+            if (lane >= (u32)o) xi += n;
+        }
+        wsum[lane] = xi - x; // exclusive warp offsets
+    }
+    __syncthreads();
+    if (threadIdx.x < nblocks) H[d * nblocks + threadIdx.x] = s_base + wsum[w] + inc - v;
+    if (first && d == 255 && threadIdx.x == 1023) cnt[CNT_M] = s_base + wsum[31] + inc; // = number of valid keys
 }
 
 __global__ void __launch_bounds__(BLOCK) k_rs_scatter(const u32 *keys, const u32 *vals, u32 *okeys, u32 *ovals, u32 n_host,
@@ -512,7 +374,7 @@ static int bits_for(u64 max_key_exclusive) {
 
 size_t sort_temp_bytes(u32 n) { // histogram matrix: 256 digits x blocks
     (void)n;
-    return (size_t)256 * 4096 * sizeof(u32);
+    return (size_t)(256 * 1024 + 4 * 256) * sizeof(u32);
 }
 
 void prof_begin(Launcher &L, const char *name) {
@@ -567,16 +429,17 @@ static cudaError_t group_by_key(Launcher &L, u32 n, u64 key_space, const u32 **s
     Scratch &s = L.s;
     int passes = (bits_for(key_space) + 7) / 8;
     int rsb = L.num_sms * RS_BLOCKS_PER_SM;
-    if (rsb > 4096) rsb = 4096;
-    u32 *H = (u32 *)s.cub_tmp;
+    if (rsb > 1024) rsb = 1024;
+    u32 *H = (u32 *)s.cub_tmp, *T = H + 256 * 1024;
     cudaError_t e = cudaMemsetAsync(s.counters, 0, 64, L.stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(T, 0, 4 * 256 * sizeof(u32), L.stream);
     if (e != cudaSuccess) return e;
     u32 *ik = s.key_a, *iv = s.val_a, *ok = s.key_b, *ov = s.val_b;
     prof_begin(L, "group_by_key");
     for (int p = 0; p < passes; p++) {
         int first = p == 0;
-        k_rs_hist<<<rsb, BLOCK, 0, L.stream>>>(ik, n, s.counters, first, 8 * p, H);
-        k_rs_scan<<<1, 1024, 0, L.stream>>>(H, (u32)rsb, s.counters, first);
+        k_rs_hist<<<rsb, BLOCK, 0, L.stream>>>(ik, n, s.counters, first, 8 * p, H, T + 256 * p);
+        k_rs_scan<<<256, 1024, 0, L.stream>>>(H, T + 256 * p, (u32)rsb, s.counters, first);
         k_rs_scatter<<<rsb, BLOCK, 0, L.stream>>>(ik, iv, ok, ov, n, s.counters, first, 8 * p, H);
         L.launches += 3;
         u32 *t = ik;
@@ -632,7 +495,7 @@ cudaError_t run_nat_hairpin_xdp(Launcher &L, const DevCtx &c, const DevBatch &b)
 }
 
 cudaError_t run_pipeline_up(Launcher &L, const DevCtx &c, const DevBatch &b) {
-    LAUNCH(k_pipe_classify, b.n, 6, c, b, L.s.key_a, L.s.val_a);
+    LAUNCH(k_pipe_classify, b.n, 5, c, b, L.s.key_a, L.s.val_a);
     u64 space = (u64)(c.qos_in.mask + 1) + (c.sub_nat.mask + 1);
     const u32 *sk, *sv;
     cudaError_t e = group_by_key(L, b.n, space, &sk, &sv);

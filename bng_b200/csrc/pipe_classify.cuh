@@ -1,0 +1,167 @@
+// bng_b200 — pipeline_up CLASSIFY kernel: antispoof_ingress -> nat44_egress ->
+// qos_ingress_prog keyed on the pre-NAT source address.
+//
+// All three stages key their mutable state on the subscriber's private
+// address, so one group-by serves both the NAT new-flow ordering and the
+// token-bucket ordering.  Ordering key: the qos_ingress bucket slot when the
+// subscriber has a bucket, else qos capacity + subscriber_nat slot.  MISS_FLAG
+// in the value marks frames whose NAT session must be created in the ordered
+// phase.
+//
+// The body is written as a sequence of warp-convergent phases (a predicate per
+// frame, __syncwarp() between phases): divergence would serialise the memory
+// latency of every phase once per divergent group, which is what bounds a
+// gather-heavy kernel like this one.
+#pragma once
+
+__global__ void __launch_bounds__(BLOCK, 5)
+    k_pipe_classify(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b, u32 *skey, u32 *sval) {
+    __shared__ SmallTabs st;
+    __shared__ BlockStats bs;
+    __shared__ u64 bar;
+    smem_stage_begin(&st, c.small, (u32)sizeof(SmallTabs), &bar);
+    bstats_init(bs);
+    smem_stage_wait(&bar);
+    const u32 as_cfg = st.as_cfg, nflags = st.nat_flags;
+    const u32 lane = threadIdx.x & 31;
+    u32 n_allowed = 0, n_snat = 0;
+    // warp-uniform trip count: every lane stays in the loop, inactive lanes are predicated off
+    for (u32 base = blockIdx.x * BLOCK + (threadIdx.x & ~31u); base < b.n; base += gridDim.x * BLOCK) {
+        const u32 i = base + lane;
+        const bool act = i < b.n;
+        const u32 len = act ? b.len[i] : 0;
+        u8 *p = act ? frame_ptr(b, i) : b.pkts;
+        Hdr64 h;
+        hdr_load(h, p, len);
+
+        // ---- phase 1: keys, and the first probe of every table this frame may need ----
+        const bool ip4 = len >= 34 && h.b16(12) == ETH_P_IP_LE;
+        const u32 saddr = h.b32(26), daddr = h.b32(30), proto = h.b8(23);
+        const bool ihl5 = (h.b8(14) & 0x0f) == 5;
+        u64 mk = mac_key(h, 6);
+        const u32 bi = tbl_hash<1>(&mk) & c.bindings.mask;
+        u64 sk = saddr;
+        const u32 ai = tbl_hash<1>(&sk); // subscriber_nat and qos_ingress share the key, hence the hash
+        const u32 si = ai & c.sub_nat.mask, qi = ai & c.qos_in.mask;
+        u16 sport, dport;
+        if (proto == 1) {
+            sport = h.b16(38); // echo id stands in for the source port (bpf/nat44.c:647-649)
+            dport = 0;
+        } else {
+            sport = h.b16(34);
+            dport = h.b16(36);
+        }
+        u64 key[2];
+        key[0] = (u64)saddr | ((u64)daddr << 32);
+        key[1] = (u64)sport | ((u64)dport << 16) | ((u64)proto << 32);
+        const u32 hi = tbl_hash<2>(key) & c.sessions.mask;
+        u64 bw0 = K_EMPTY, sw0 = K_EMPTY, qw0 = K_EMPTY, kw0 = K_EMPTY, kw1 = 0;
+        if (len >= 14) bw0 = *(const u64 *)tbl_slot(c.bindings, bi);
+        if (ip4) {
+            sw0 = *(const u64 *)tbl_slot(c.sub_nat, si);
+            qw0 = *(const u64 *)tbl_slot(c.qos_in, qi);
+            const ulonglong2 kk = *(const ulonglong2 *)tbl_slot(c.sessions, hi);
+            kw0 = kk.x;
+            kw1 = kk.y;
+        }
+
+        // ---- phase 2: antispoof_ingress ----
+        const u8 *bind = len >= 14 ? tbl_finish<1>(c.bindings, &mk, bi, bw0, true) : nullptr;
+        __syncwarp();
+        int v = antispoof_eval(c, bs, h, len, i, b.now, bind, as_cfg, n_allowed);
+        __syncwarp();
+        const bool alive = act && v != TC_SHOT && ip4;
+
+        // ---- phase 3: table lookups of the NAT / QoS stages ----
+        const u8 *qsl = alive ? tbl_finish<1>(c.qos_in, &sk, qi, qw0, true) : nullptr;
+        __syncwarp();
+        const bool priv = alive && ihl5 && is_private_ip(saddr);
+        const u8 *sub = priv ? tbl_finish<1>(c.sub_nat, &sk, si, sw0, true) : nullptr;
+        __syncwarp();
+        if (priv && !sub) bstats_add(bs, ST_NAT_PASSED, 1); // no allocation: to userspace (bpf/nat44.c:592-596)
+        // L4 header in bounds and a translatable protocol (:608-653)
+        bool go = sub != nullptr && (proto == 6 ? len >= 54u : ((proto == 17 || proto == 1) && len >= 42u));
+        if (go && proto != 1 && (nflags & (proto == 6 ? (NATF_ALG_FTP | NATF_ALG_SIP) : NATF_ALG_SIP)) && st.alg_n) {
+            int ax = alg_find(st, ((u32)bswap16(dport) << 16) | proto);
+            if (ax >= 0) { // ALG traffic goes to userspace untranslated (:615-642)
+                bstats_add(bs, ST_NAT_ALG, 1);
+                nat_log(c, i, b.now, 7, *(const u32 *)(sub + 32), saddr, 0, sport, 0, daddr, dport, (u8)proto, st.alg_type[ax]);
+                go = false;
+            }
+        }
+        __syncwarp();
+        if (go && (nflags & NATF_HAIRPIN) && hp_contains(st, daddr)) bstats_add(bs, ST_NAT_HAIRPIN, 1);
+        __syncwarp();
+        u8 *ses = go ? tbl_finish<2>(c.sessions, key, hi, kw0, kw1 == key[1]) : nullptr;
+        __syncwarp();
+
+        // ---- phase 4: session hit: counters and the SNAT rewrite (:674-680, :752-798) ----
+        bool miss = go && !ses;
+        u32 sub_idx = miss ? (u32)((sub - c.sub_nat.slots) / c.sub_nat.slot_bytes) : 0;
+        if (ses) {
+            const u32 nat_ip = *(const u32 *)(ses + SES_NAT_IP);
+            const u16 nat_port = *(const u16 *)(ses + SES_NAT_PORT);
+            *(u64 *)(ses + SES_LAST_SEEN) = b.now;
+            atomicAdd((u64 *)(ses + SES_PKTS_OUT), 1ull);
+            atomicAdd((u64 *)(ses + SES_BYTES_OUT), (u64)len);
+            h.s32(26, nat_ip);
+            h.s16(24, csum_upd32(h.b16(24), saddr, nat_ip));
+            if (proto == 6) {
+                h.s16(34, nat_port);
+                u16 ck = csum_upd32(h.b16(50), saddr, nat_ip);
+                h.s16(50, csum_upd16(ck, sport, nat_port));
+            } else if (proto == 17) {
+                h.s16(34, nat_port);
+                u16 ck = h.b16(40);
+                if (ck != 0) {
+                    ck = csum_upd32(ck, saddr, nat_ip);
+                    ck = csum_upd16(ck, sport, nat_port);
+                    if (ck == 0) ck = 0xffff;
+                    h.s16(40, ck);
+                }
+            } else {
+                h.s16(38, nat_port);
+                h.s16(36, csum_upd16(h.b16(36), sport, nat_port));
+            }
+            hdr_store_chunk(h, p, 1);
+            hdr_store_chunk(h, p, 2);
+            if (proto == 6) hdr_store_chunk(h, p, 3);
+            n_snat++;
+        }
+        __syncwarp();
+
+        // ---- IPv4 options: fields are not at fixed offsets, take the generic path (rare) ----
+        if (alive && !ihl5) {
+            NatOut o = nat_egress_one<false>(c, bs, p, len, i, b.now);
+            v = o.verdict;
+            miss = o.order_key != NO_KEY;
+            sub_idx = o.order_key;
+        }
+        __syncwarp();
+
+        // ---- phase 5: ordering key ----
+        u32 okey = NO_KEY, oval = i;
+        if (alive && v != TC_SHOT) {
+            if (qsl) {
+                const u64 rate = *(const u64 *)(qsl + 32);
+                if (!miss && rate == 0) { // unlimited bucket and nothing left to order
+                    bstats_add(bs, ST_QOS_PASS_PKTS, 1);
+                    bstats_add(bs, ST_QOS_PASS_BYTES, len);
+                } else {
+                    okey = (u32)((qsl - c.qos_in.slots) / c.qos_in.slot_bytes);
+                }
+            } else if (miss) {
+                okey = (c.qos_in.mask + 1) + sub_idx;
+            }
+            if (miss) oval |= MISS_FLAG;
+        }
+        if (act) {
+            b.verdict[i] = (u8)v;
+            skey[i] = okey;
+            sval[i] = oval;
+        }
+    }
+    warp_stat_flush(bs, ST_AS_ALLOWED, n_allowed);
+    warp_stat_flush(bs, ST_NAT_SNAT, n_snat);
+    bstats_flush(bs, c.stats);
+}

@@ -180,9 +180,7 @@ __device__ __forceinline__ u32 qos_classify_one(const DevCtx &c, BlockStats &bs,
 //   subscriber_nat: key u32 @0, value @8:  block.public_ip@8 port_start@12 port_end@14
 //                   next_port@16 ports_in_use@20 allocated_at@24 subscriber_id@32
 //                   sessions_active@40 sessions_total@48 bytes_out@56 bytes_in@64
-//   nat_sessions:   key 16 B @0, value @16: nat_ip@16 nat_port@20 orig_port@22 orig_ip@24
-//                   dest_ip@28 dest_port@32 last_seen@40 created@48 packets_out@56
-//                   packets_in@64 bytes_out@72 bytes_in@80 state@88 protocol@89 flags@90 is_hairpin@91
+//   nat_sessions:   key 16 B @0, then the hot/cold layout of common.cuh (SES_* offsets)
 //   nat_reverse:    key 16 B @0, value (nat_key) @16
 //   eim_table:      key 8 B @0,  value @8: external_ip@8 external_port@12 created@16
 //                   last_used@24 ref_count@32 flags@36
@@ -333,11 +331,11 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
     u32 nat_ip;
     u16 nat_port;
     if (ses) { // :674-680
-        nat_ip = *(const u32 *)(ses + 16);
-        nat_port = *(const u16 *)(ses + 20);
-        *(u64 *)(ses + 40) = now;
-        atomicAdd((u64 *)(ses + 56), 1ull);
-        atomicAdd((u64 *)(ses + 72), (u64)len);
+        nat_ip = *(const u32 *)(ses + SES_NAT_IP);
+        nat_port = *(const u16 *)(ses + SES_NAT_PORT);
+        *(u64 *)(ses + SES_LAST_SEEN) = now;
+        atomicAdd((u64 *)(ses + SES_PKTS_OUT), 1ull);
+        atomicAdd((u64 *)(ses + SES_BYTES_OUT), (u64)len);
     } else {
         if (!RESOLVE) {
             o.order_key = (u32)((sub - c.sub_nat.slots) / c.sub_nat.slot_bytes);
@@ -398,18 +396,19 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
         bool created;
         u8 *ns = tbl_find_or_claim<2>(c.sessions, key, &created); // BPF_ANY (:730)
         if (ns) {
-            *(u32 *)(ns + 16) = nat_ip;
-            *(u32 *)(ns + 20) = (u32)nat_port | ((u32)sport << 16);
-            *(u32 *)(ns + 24) = saddr;
-            *(u32 *)(ns + 28) = daddr;
-            *(u64 *)(ns + 32) = (u64)dport;
-            *(u64 *)(ns + 40) = now;
-            *(u64 *)(ns + 48) = now;
-            *(u64 *)(ns + 56) = 1;
-            *(u64 *)(ns + 64) = 0;
-            *(u64 *)(ns + 72) = (u64)len;
-            *(u64 *)(ns + 80) = 0;
-            *(u64 *)(ns + 88) = (u64)proto << 8 | ((u64)is_hairpin << 24);
+            *(u32 *)(ns + SES_NAT_IP) = nat_ip;
+            *(u32 *)(ns + SES_NAT_PORT) = (u32)nat_port | ((u32)sport << 16); // nat_port, orig_port
+            *(u32 *)(ns + SES_ORIG_IP) = saddr;
+            *(u32 *)(ns + SES_STATE) = (proto << 8) | ((u32)is_hairpin << 24); // state NEW, protocol, flags 0, hairpin
+            *(u64 *)(ns + SES_LAST_SEEN) = now;
+            *(u64 *)(ns + SES_PKTS_OUT) = 1;
+            *(u64 *)(ns + SES_BYTES_OUT) = (u64)len;
+            *(u64 *)(ns + SES_PKTS_IN) = 0;
+            *(u64 *)(ns + SES_BYTES_IN) = 0;
+            *(u64 *)(ns + SES_CREATED) = now;
+            *(u32 *)(ns + SES_DEST_IP) = daddr;
+            *(u32 *)(ns + SES_DEST_PORT) = (u32)dport; // dest_port, _pad1 = 0
+            *(u64 *)(ns + 88) = 0;                      // the struct's padding bytes
             if (created) tbl_publish(ns, key[0]);
         } else {
             bstats_add(bs, ST_LRU_OVERFLOW, 1);
@@ -483,14 +482,14 @@ __device__ __forceinline__ int nat_ingress_one(const DevCtx &c, BlockStats &bs, 
             bstats_add(bs, ST_NAT_PASSED, 1);
         return TC_OK;
     }
-    *(u64 *)(ses + 40) = now;
-    atomicAdd((u64 *)(ses + 64), 1ull);
-    atomicAdd((u64 *)(ses + 80), (u64)len);
+    *(u64 *)(ses + SES_LAST_SEEN) = now;
+    atomicAdd((u64 *)(ses + SES_PKTS_IN), 1ull);
+    atomicAdd((u64 *)(ses + SES_BYTES_IN), (u64)len);
     if (proto == 6) { // :885-895; CLOSING(3) is absorbing, NEW(0)->ESTABLISHED(1) on ack
         u32 tf = p[l4 + 13];
         bool finrst = (tf & 0x05) != 0, ack = (tf & 0x10) != 0;
         if (finrst || ack) {
-            u32 *sw = (u32 *)(ses + 88);
+            u32 *sw = (u32 *)(ses + SES_STATE);
             u32 cur = *(volatile u32 *)sw;
             while (true) {
                 u32 st = cur & 0xff, nst = st;
@@ -505,8 +504,8 @@ __device__ __forceinline__ int nat_ingress_one(const DevCtx &c, BlockStats &bs, 
             }
         }
     }
-    u32 new_ip = *(const u32 *)(ses + 24);
-    u16 new_port = *(const u16 *)(ses + 22);
+    u32 new_ip = *(const u32 *)(ses + SES_ORIG_IP);
+    u16 new_port = *(const u16 *)(ses + SES_ORIG_PORT);
     wr32(p, 30, new_ip);
     wr16(p, 24, csum_upd32(rd16(p, 24), daddr, new_ip));
     if (proto == 6) {

@@ -19,6 +19,22 @@ __device__ __forceinline__ void copy_bytes(u8 *dst, const u8 *src, u32 n) {
     for (u32 i = 0; i < n; i++) dst[i] = src[i];
 }
 
+// value in reference (ABI) layout <-> value as stored in the slot
+__device__ __forceinline__ void val_to_slot(const Tbl &t, u8 *slot, const u8 *abi) {
+    if (t.vlayout == VL_SESSION) {
+        for (u32 i = 0; i < t.value_size; i++) slot[ses_abi_to_slot(i)] = abi[i];
+    } else {
+        copy_bytes(slot + t.voff, abi, t.value_size);
+    }
+}
+__device__ __forceinline__ void val_from_slot(const Tbl &t, u8 *abi, const u8 *slot) {
+    if (t.vlayout == VL_SESSION) {
+        for (u32 i = 0; i < t.value_size; i++) abi[i] = slot[ses_abi_to_slot(i)];
+    } else {
+        copy_bytes(abi, slot + t.voff, t.value_size);
+    }
+}
+
 template <int KW>
 __global__ void k_table_op(const __grid_constant__ Tbl t, int op, const u8 *keys, u8 *vals, int *results, u64 n, u32 flags) {
     for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
@@ -30,7 +46,7 @@ __global__ void k_table_op(const __grid_constant__ Tbl t, int op, const u8 *keys
         } else if (op == TOP_LOOKUP) {
             const u8 *s = tbl_find<KW, true>(t, kw);
             if (s)
-                copy_bytes(vals + i * t.value_size, s + t.voff, t.value_size);
+                val_from_slot(t, vals + i * t.value_size, s);
             else
                 r = -ENOENT;
         } else if (op == TOP_DELETE) {
@@ -40,7 +56,7 @@ __global__ void k_table_op(const __grid_constant__ Tbl t, int op, const u8 *keys
             if (flags == 2) { // BPF_EXIST
                 u8 *s = tbl_find<KW, true>(t, kw);
                 if (s)
-                    copy_bytes(s + t.voff, v, t.value_size);
+                    val_to_slot(t, s, v);
                 else
                     r = -ENOENT;
             } else {
@@ -53,7 +69,7 @@ __global__ void k_table_op(const __grid_constant__ Tbl t, int op, const u8 *keys
                 } else {
                     if (created) // bytes between the key and the value, and the slot tail, stay defined
                         for (u32 z = 8 * KW; z < t.slot_bytes; z += 8) *(u64 *)(s + z) = 0;
-                    copy_bytes(s + t.voff, v, t.value_size);
+                    val_to_slot(t, s, v);
                     if (created) tbl_publish(s, kw[0]);
                 }
             }
@@ -71,7 +87,7 @@ __global__ void k_table_dump(const __grid_constant__ Tbl t, u8 *keys_out, u8 *va
         u32 pos = atomicAdd(count_out, 1u);
         if (pos >= cap) continue;
         copy_bytes(keys_out + (u64)pos * t.key_size, s, t.key_size);
-        copy_bytes(vals_out + (u64)pos * t.value_size, s + t.voff, t.value_size);
+        val_from_slot(t, vals_out + (u64)pos * t.value_size, s);
     }
 }
 

@@ -221,12 +221,23 @@ BUILDERS = {
 }
 
 
-def slot16(lens: np.ndarray, imix: bool, width: int):
-    """Arena layout: (off16 u32[n] or None, stride, total 16-byte granules)."""
+def sizing(wl: "Workload") -> dict:
+    """bng_open capacities for this workload: the control plane sizes the tables for the subscribers and
+    flows it provisions (2x head-room) instead of the reference's compile-time maxima."""
+    subs = max(1024, 2 * wl.n_subs_local)
+    flows = max(4096, 2 * int(wl.info.get("flows", 0)))
+    return {"max_subscribers": subs, "max_nat_sessions": flows, "max_eim_mappings": flows}
+
+
+def slot16(lens: np.ndarray, imix: bool, width: int, align: int = 64):
+    """Arena layout: (off16 u32[n] or None, stride, total 16-byte granules).  Variable-length frames are
+    placed on `align`-byte boundaries (64 = one DRAM access granule per header, as a NIC's cache-line
+    aligned receive buffers would be; 16 = densest packing the ABI allows)."""
     if not imix:
         stride = ((width + 15) // 16) * 16
         return None, stride, lens.shape[0] * stride // 16
-    slots = (lens.astype(np.uint64) + 15) // 16
+    a16 = max(1, align // 16)
+    slots = ((lens.astype(np.uint64) + align - 1) // align) * a16
     off = np.zeros(lens.shape[0], np.uint64)
     np.cumsum(slots[:-1], out=off[1:])
     total = int(off[-1] + slots[-1]) + 4
