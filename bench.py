@@ -198,6 +198,7 @@ def run_gpu(a):
         dist.init_process_group("nccl", device_id=dev)
     n = a.frames
     wl = W.BUILDERS[a.workload](n, rank, world)
+    n = wl.n  # a workload may hold fewer frames than asked for (nat_cold: one frame per flow)
     dp = Dataplane(device=local, max_batch=max(n, 1 << 20), rank=rank, world=world,
                    **({} if a.reference_capacities else W.sizing(wl)))
     for m, k, v in wl.maps:
@@ -227,6 +228,12 @@ def run_gpu(a):
         torch.cuda.synchronize()
         for ring in ("spoof_events", "nat_log_rb"):  # the event consumer keeps the staging rings empty (untimed)
             dp.drain(ring)
+        if wl.name == "nat_cold_64":  # every step starts from empty flow tables and fresh port blocks
+            for m in ("nat_sessions", "nat_reverse", "eim_table"):
+                dp.clear(m)
+            for m, k, v in wl.maps:
+                if m == "subscriber_nat":
+                    dp.update_batch(m, as_bytes(k), as_bytes(v))
 
     for prog, h, l in wl.prewarm:  # e.g. create the NAT sessions of every flow once (cold start)
         ph = torch.from_numpy(h).to(dev).reshape(-1)

@@ -177,6 +177,8 @@ struct DevBatch {
     u32 n;
     u32 stride;
     u64 now;
+    u32 base; // index of frame 0 within the caller's batch (event records carry base + i)
+    u32 pad;
 };
 
 // ---------------------------------------------------------------------------

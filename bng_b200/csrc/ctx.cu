@@ -59,6 +59,13 @@ struct bng_ctx {
     size_t hb_arena = 0;
     u32 hb_n = 0;
     u64 lost_base[2] = {0, 0};
+    // zero-copy pipeline for BNG_MEM_HOST batches in pinned memory: two chunk buffers, three streams
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    u8 *zc_hdr[2] = {nullptr, nullptr}, *zc_verdict[2] = {nullptr, nullptr};
+    u32 *zc_off[2] = {nullptr, nullptr}, *zc_len[2] = {nullptr, nullptr}, *zc_len0[2] = {nullptr, nullptr},
+        *zc_prio[2] = {nullptr, nullptr};
+    u32 zc_hb = 0;
 };
 
 namespace {
@@ -279,6 +286,16 @@ int bng_close(bng_ctx *c) {
         for (void *p : sp)
             if (p) cudaFree(p);
         if (c->io_host) cudaFreeHost(c->io_host);
+        for (int i = 0; i < 2; i++) {
+            void *zp[] = {c->zc_hdr[i], c->zc_verdict[i], c->zc_off[i], c->zc_len[i], c->zc_len0[i], c->zc_prio[i]};
+            for (void *p : zp)
+                if (p) cudaFree(p);
+            if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+            if (c->ev_comp[i]) cudaEventDestroy(c->ev_comp[i]);
+            if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+        }
+        if (c->s_in) cudaStreamDestroy(c->s_in);
+        if (c->s_out) cudaStreamDestroy(c->s_out);
         if (c->L.stream) cudaStreamDestroy(c->L.stream);
     }
     delete c;
@@ -558,6 +575,19 @@ int bng_map_delete(bng_ctx *c, int map, const void *key) {
 
 static int64_t map_dump_locked(bng_ctx *c, MapReg *m, void *keys_out, void *values_out, uint64_t cap);
 
+// Removes every entry of a hash map (the control plane's equivalent of closing and re-creating the map).
+int bng_map_clear(bng_ctx *c, int map) {
+    MapReg *m = get_map(c, map);
+    if (!m || m->kind != KIND_HASH) return -EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    const Tbl &t = *m->tbl;
+    CU(c, cudaMemsetAsync(t.slots, 0xFF, ((size_t)t.mask + 1) * t.slot_bytes, c->L.stream));
+    CU(c, cudaMemsetAsync(t.count, 0, 4, c->L.stream));
+    CU(c, cudaStreamSynchronize(c->L.stream));
+    return feeds_small_tabs(m) ? small_refresh(c) : 0;
+}
+
 int64_t bng_map_dump(bng_ctx *c, int map, void *keys_out, void *values_out, uint64_t cap) {
     MapReg *m = get_map(c, map);
     if (!m || !keys_out || !values_out) return -EINVAL;
@@ -714,6 +744,88 @@ static int dispatch(bng_ctx *c, int prog, const DevBatch &b) {
     return 0;
 }
 
+// BNG_MEM_HOST with a pinned arena: chunked three-stage pipeline
+//   s_in   : header gather straight from the mapped host arena (+ offsets / lengths H2D)
+//   stream : the program on the compact device copy (chunks strictly in order: index-order semantics)
+//   s_out  : header scatter back into the host arena (+ verdict / length D2H)
+// so PCIe reads, PCIe writes and compute of successive chunks overlap, and only the bytes a
+// program can touch ever cross the bus.
+#define ZC_CHUNK (1u << 19)
+static int run_host_zero_copy(bng_ctx *c, int prog, bng_batch *bb, u8 *arena_dev) {
+    const u32 hb = prog == P_DHCP ? 448u : 64u;
+    const u32 first_chunk = prog == P_DHCP ? 0u : 1u; // TC programs never write the Ethernet addresses
+    if (!c->s_in) {
+        CU(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+        CU(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CU(c, cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+            CU(c, cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming));
+            CU(c, cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+            CU(c, cudaMalloc((void **)&c->zc_off[i], ZC_CHUNK * 4));
+            CU(c, cudaMalloc((void **)&c->zc_len[i], ZC_CHUNK * 4));
+            CU(c, cudaMalloc((void **)&c->zc_len0[i], ZC_CHUNK * 4));
+            CU(c, cudaMalloc((void **)&c->zc_prio[i], ZC_CHUNK * 4));
+            CU(c, cudaMalloc((void **)&c->zc_verdict[i], ZC_CHUNK));
+        }
+    }
+    if (c->zc_hb < hb) {
+        for (int i = 0; i < 2; i++) {
+            if (c->zc_hdr[i]) cudaFree(c->zc_hdr[i]);
+            c->zc_hdr[i] = nullptr;
+        }
+        c->zc_hb = 0;
+        for (int i = 0; i < 2; i++) CU(c, cudaMalloc((void **)&c->zc_hdr[i], (size_t)ZC_CHUNK * hb));
+        c->zc_hb = hb;
+    }
+    cudaStream_t sc = c->L.stream;
+    const u32 nchunks = (bb->n + ZC_CHUNK - 1) / ZC_CHUNK;
+    for (u32 k = 0; k < nchunks; k++) {
+        const int buf = k & 1;
+        const u32 base = k * ZC_CHUNK, cn = std::min<u32>(ZC_CHUNK, bb->n - base);
+        // ---- in ----
+        if (k >= 2) CU(c, cudaStreamWaitEvent(c->s_in, c->ev_out[buf], 0));
+        if (bb->off16) CU(c, cudaMemcpyAsync(c->zc_off[buf], bb->off16 + base, (size_t)cn * 4, cudaMemcpyHostToDevice, c->s_in));
+        CU(c, cudaMemcpyAsync(c->zc_len[buf], bb->len + base, (size_t)cn * 4, cudaMemcpyHostToDevice, c->s_in));
+        if (bb->priority)
+            CU(c, cudaMemcpyAsync(c->zc_prio[buf], bb->priority + base, (size_t)cn * 4, cudaMemcpyHostToDevice, c->s_in));
+        u8 *chunk_arena = bb->off16 ? arena_dev : arena_dev + (size_t)base * bb->stride;
+        CU(c, run_gather_frames(c->s_in, c->L.num_sms, chunk_arena, bb->off16 ? c->zc_off[buf] : nullptr, c->zc_len[buf],
+                                bb->stride, cn, hb, c->zc_hdr[buf], c->zc_len0[buf]));
+        c->L.launches++;
+        CU(c, cudaEventRecord(c->ev_in[buf], c->s_in));
+        // ---- compute ----
+        CU(c, cudaStreamWaitEvent(sc, c->ev_in[buf], 0));
+        DevBatch b{};
+        b.pkts = c->zc_hdr[buf];
+        b.off16 = nullptr;
+        b.len = c->zc_len[buf];
+        b.verdict = c->zc_verdict[buf];
+        b.priority = bb->priority ? c->zc_prio[buf] : nullptr;
+        b.n = cn;
+        b.stride = hb;
+        b.now = bb->now_ns;
+        b.base = base;
+        int r = dispatch(c, prog, b);
+        if (r) return r;
+        CU(c, cudaEventRecord(c->ev_comp[buf], sc));
+        // ---- out ----
+        CU(c, cudaStreamWaitEvent(c->s_out, c->ev_comp[buf], 0));
+        CU(c, run_scatter_frames(c->s_out, c->L.num_sms, chunk_arena, bb->off16 ? c->zc_off[buf] : nullptr, c->zc_len0[buf],
+                                 bb->stride, cn, hb, c->zc_hdr[buf], first_chunk));
+        c->L.launches++;
+        CU(c, cudaMemcpyAsync(bb->verdict + base, c->zc_verdict[buf], cn, cudaMemcpyDeviceToHost, c->s_out));
+        if (prog == P_DHCP)
+            CU(c, cudaMemcpyAsync(bb->len + base, c->zc_len[buf], (size_t)cn * 4, cudaMemcpyDeviceToHost, c->s_out));
+        if (bb->priority)
+            CU(c, cudaMemcpyAsync(bb->priority + base, c->zc_prio[buf], (size_t)cn * 4, cudaMemcpyDeviceToHost, c->s_out));
+        CU(c, cudaEventRecord(c->ev_out[buf], c->s_out));
+    }
+    CU(c, cudaStreamSynchronize(c->s_out));
+    CU(c, cudaStreamSynchronize(sc));
+    prof_collect(c->L);
+    return 0;
+}
+
 int bng_prog_run(bng_ctx *c, int prog, bng_batch *bb) {
     if (!c || !bb || prog < 0 || prog >= P_COUNT) return -EINVAL;
     if (bb->n == 0) return 0;
@@ -724,7 +836,7 @@ int bng_prog_run(bng_ctx *c, int prog, bng_batch *bb) {
     int r = ensure_scratch(c, bb->n);
     if (r) return r;
     c->dev.batch_seq++;
-    DevBatch b;
+    DevBatch b{};
     b.n = bb->n;
     b.stride = bb->stride;
     b.now = bb->now_ns;
@@ -737,6 +849,12 @@ int bng_prog_run(bng_ctx *c, int prog, bng_batch *bb) {
         return dispatch(c, prog, b);
     }
     if (bb->mem != BNG_MEM_HOST) return -EINVAL;
+    {
+        void *mapped = nullptr; // pinned (cudaHostAlloc / cudaHostRegister) arenas are read in place
+        if (cudaHostGetDevicePointer(&mapped, bb->pkts, 0) == cudaSuccess && mapped)
+            return run_host_zero_copy(c, prog, bb, (u8 *)mapped);
+        cudaGetLastError(); // pageable memory: fall back to whole-arena staging copies
+    }
     size_t arena = bb->off16 ? (size_t)bb->arena_bytes * 16 : (size_t)bb->n * bb->stride;
     if (arena == 0) return -EINVAL;
     cudaStream_t st = c->L.stream;

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(BLOCK) k_antispoof(const __grid_constant__ Dev
         hdr_load(h, p, len);
         u64 mk = mac_key(h, 6);
         const u8 *bind = len >= 14 ? tbl_find<1, false>(c.bindings, &mk) : nullptr;
-        b.verdict[i] = (u8)antispoof_eval(c, bs, h, len, i, b.now, bind, cfg, n_allowed);
+        b.verdict[i] = (u8)antispoof_eval(c, bs, h, len, i + b.base, b.now, bind, cfg, n_allowed);
     }
     warp_stat_flush(bs, ST_AS_ALLOWED, n_allowed);
     bstats_flush(bs, c.stats);
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(BLOCK) k_resolve(const __grid_constant__ DevCt
                     u32 l = __ffs(mm) - 1;
                     mm &= mm - 1;
                     if (lane == l) {
-                        NatOut o = nat_egress_one<true>(c, bs, frame_ptr(b, idx), len, idx, b.now);
+                        NatOut o = nat_egress_one<true>(c, bs, frame_ptr(b, idx), len, idx + b.base, b.now);
                         if (o.verdict == TC_SHOT) {
                             b.verdict[idx] = TC_SHOT;
                             dropped = true;
@@ -476,7 +476,7 @@ cudaError_t run_qos(Launcher &L, const DevCtx &c, const DevBatch &b, bool egress
 }
 
 cudaError_t run_nat_egress(Launcher &L, const DevCtx &c, const DevBatch &b) {
-    LAUNCH(k_nat_eg_classify, b.n, 6, c, b, L.s.key_a, L.s.val_a);
+    LAUNCH((k_pipe_classify<false, false>), b.n, 5, c, b, L.s.key_a, L.s.val_a);
     const u32 *sk, *sv;
     cudaError_t e = group_by_key(L, b.n, (u64)c.sub_nat.mask + 1, &sk, &sv);
     if (e != cudaSuccess) return e;
@@ -495,7 +495,7 @@ cudaError_t run_nat_hairpin_xdp(Launcher &L, const DevCtx &c, const DevBatch &b)
 }
 
 cudaError_t run_pipeline_up(Launcher &L, const DevCtx &c, const DevBatch &b) {
-    LAUNCH(k_pipe_classify, b.n, 5, c, b, L.s.key_a, L.s.val_a);
+    LAUNCH((k_pipe_classify<true, true>), b.n, 5, c, b, L.s.key_a, L.s.val_a);
     u64 space = (u64)(c.qos_in.mask + 1) + (c.sub_nat.mask + 1);
     const u32 *sk, *sv;
     cudaError_t e = group_by_key(L, b.n, space, &sk, &sv);

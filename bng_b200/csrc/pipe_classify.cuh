@@ -14,6 +14,9 @@
 // gather-heavy kernel like this one.
 #pragma once
 
+// AS: run antispoof_ingress first; QOS: look up the qos_ingress bucket.  <false,false> is the
+// standalone nat44_egress classify (ordering key = subscriber_nat slot).
+template <bool AS, bool QOS>
 __global__ void __launch_bounds__(BLOCK, 5)
     k_pipe_classify(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b, u32 *skey, u32 *sval) {
     __shared__ SmallTabs st;
@@ -56,24 +59,27 @@ __global__ void __launch_bounds__(BLOCK, 5)
         key[1] = (u64)sport | ((u64)dport << 16) | ((u64)proto << 32);
         const u32 hi = tbl_hash<2>(key) & c.sessions.mask;
         u64 bw0 = K_EMPTY, sw0 = K_EMPTY, qw0 = K_EMPTY, kw0 = K_EMPTY, kw1 = 0;
-        if (len >= 14) bw0 = *(const u64 *)tbl_slot(c.bindings, bi);
+        if (AS && len >= 14) bw0 = *(const u64 *)tbl_slot(c.bindings, bi);
         if (ip4) {
             sw0 = *(const u64 *)tbl_slot(c.sub_nat, si);
-            qw0 = *(const u64 *)tbl_slot(c.qos_in, qi);
+            if (QOS) qw0 = *(const u64 *)tbl_slot(c.qos_in, qi);
             const ulonglong2 kk = *(const ulonglong2 *)tbl_slot(c.sessions, hi);
             kw0 = kk.x;
             kw1 = kk.y;
         }
 
         // ---- phase 2: antispoof_ingress ----
-        const u8 *bind = len >= 14 ? tbl_finish<1>(c.bindings, &mk, bi, bw0, true) : nullptr;
-        __syncwarp();
-        int v = antispoof_eval(c, bs, h, len, i, b.now, bind, as_cfg, n_allowed);
-        __syncwarp();
+        int v = TC_OK;
+        if (AS) {
+            const u8 *bind = len >= 14 ? tbl_finish<1>(c.bindings, &mk, bi, bw0, true) : nullptr;
+            __syncwarp();
+            v = antispoof_eval(c, bs, h, len, i + b.base, b.now, bind, as_cfg, n_allowed);
+            __syncwarp();
+        }
         const bool alive = act && v != TC_SHOT && ip4;
 
         // ---- phase 3: table lookups of the NAT / QoS stages ----
-        const u8 *qsl = alive ? tbl_finish<1>(c.qos_in, &sk, qi, qw0, true) : nullptr;
+        const u8 *qsl = (QOS && alive) ? tbl_finish<1>(c.qos_in, &sk, qi, qw0, true) : nullptr;
         __syncwarp();
         const bool priv = alive && ihl5 && is_private_ip(saddr);
         const u8 *sub = priv ? tbl_finish<1>(c.sub_nat, &sk, si, sw0, true) : nullptr;
@@ -85,7 +91,7 @@ __global__ void __launch_bounds__(BLOCK, 5)
             int ax = alg_find(st, ((u32)bswap16(dport) << 16) | proto);
             if (ax >= 0) { // ALG traffic goes to userspace untranslated (:615-642)
                 bstats_add(bs, ST_NAT_ALG, 1);
-                nat_log(c, i, b.now, 7, *(const u32 *)(sub + 32), saddr, 0, sport, 0, daddr, dport, (u8)proto, st.alg_type[ax]);
+                nat_log(c, i + b.base, b.now, 7, *(const u32 *)(sub + 32), saddr, 0, sport, 0, daddr, dport, (u8)proto, st.alg_type[ax]);
                 go = false;
             }
         }
@@ -132,7 +138,7 @@ __global__ void __launch_bounds__(BLOCK, 5)
 
         // ---- IPv4 options: fields are not at fixed offsets, take the generic path (rare) ----
         if (alive && !ihl5) {
-            NatOut o = nat_egress_one<false>(c, bs, p, len, i, b.now);
+            NatOut o = nat_egress_one<false>(c, bs, p, len, i + b.base, b.now);
             v = o.verdict;
             miss = o.order_key != NO_KEY;
             sub_idx = o.order_key;
@@ -151,7 +157,7 @@ __global__ void __launch_bounds__(BLOCK, 5)
                     okey = (u32)((qsl - c.qos_in.slots) / c.qos_in.slot_bytes);
                 }
             } else if (miss) {
-                okey = (c.qos_in.mask + 1) + sub_idx;
+                okey = (QOS ? (c.qos_in.mask + 1) : 0u) + sub_idx;
             }
             if (miss) oval |= MISS_FLAG;
         }
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(BLOCK, 5)
             sval[i] = oval;
         }
     }
-    warp_stat_flush(bs, ST_AS_ALLOWED, n_allowed);
+    if (AS) warp_stat_flush(bs, ST_AS_ALLOWED, n_allowed);
     warp_stat_flush(bs, ST_NAT_SNAT, n_snat);
     bstats_flush(bs, c.stats);
 }

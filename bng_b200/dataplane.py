@@ -75,6 +75,7 @@ def load_library() -> C.CDLL:
         "bng_map_lookup": ([vp, i32, vp, vp], i32),
         "bng_map_delete": ([vp, i32, vp], i32),
         "bng_map_dump": ([vp, i32, vp, vp, u64], C.c_int64),
+        "bng_map_clear": ([vp, i32], i32),
         "bng_prog_id": ([vp, C.c_char_p], i32),
         "bng_prog_run": ([vp, i32, C.POINTER(Batch)], i32),
         "bng_sync": ([vp], i32),
@@ -101,7 +102,8 @@ def load_library() -> C.CDLL:
 
 EXPORTED_SYMBOLS = (
     "bng_open", "bng_close", "bng_last_error", "bng_abi_version", "bng_map_id", "bng_map_get_info",
-    "bng_map_update", "bng_map_update_batch", "bng_map_lookup", "bng_map_delete", "bng_map_dump", "bng_prog_id",
+    "bng_map_update", "bng_map_update_batch", "bng_map_lookup", "bng_map_delete", "bng_map_clear", "bng_map_dump",
+    "bng_prog_id",
     "bng_prog_run", "bng_sync", "bng_stream", "bng_events_drain", "bng_event_size", "bng_shard_of_mac",
     "bng_stats_device_ptr", "bng_launch_count", "bng_lru_overflow", "bng_events_lost", "bng_prof_enable",
     "bng_prof_read", "bng_host_alloc", "bng_host_free",
@@ -208,6 +210,9 @@ class Dataplane:
     def delete(self, name: str, key) -> int:
         k = np.ascontiguousarray(as_bytes(np.asarray(key))).reshape(-1)
         return self.lib.bng_map_delete(self.h, self.map_id(name), k.ctypes.data)
+
+    def clear(self, name: str) -> int:
+        return self.lib.bng_map_clear(self.h, self.map_id(name))
 
     def dump(self, name: str):
         """(keys u8[n,ks], values u8[n,vs]) sorted by key bytes."""

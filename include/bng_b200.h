@@ -105,6 +105,7 @@ int bng_map_update(bng_ctx *ctx, int map, const void *key, const void *value, ui
 int bng_map_update_batch(bng_ctx *ctx, int map, const void *keys, const void *values, uint64_t n, uint64_t flags);
 int bng_map_lookup(bng_ctx *ctx, int map, const void *key, void *value_out);
 int bng_map_delete(bng_ctx *ctx, int map, const void *key);
+int bng_map_clear(bng_ctx *ctx, int map); /* drop every entry of a hash map (= close + re-create the eBPF map) */
 /* copies up to cap (key,value) pairs out; returns the number written or a negative errno */
 int64_t bng_map_dump(bng_ctx *ctx, int map, void *keys_out, void *values_out, uint64_t cap);
 

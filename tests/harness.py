@@ -123,7 +123,8 @@ class OracleBackend:
 
 
 class GpuBackend:
-    def __init__(self, dp=None, **opts):
+    def __init__(self, dp=None, pinned=False, **opts):
+        self.pinned = pinned
         if dp is None:
             from bng_b200 import Dataplane
             opts.setdefault("max_subscribers", 1 << 14)
@@ -148,7 +149,23 @@ class GpuBackend:
         return self.dp.lookup(m, k)
 
     def run(self, prog, arena, lens, now, off16, stride, prio):
-        return self.dp.run(prog, arena, lens, now, off16=off16, stride=stride, priority=prio)
+        if not getattr(self, "pinned", False):
+            return self.dp.run(prog, arena, lens, now, off16=off16, stride=stride, priority=prio)
+        # pinned host buffers: exercises the zero-copy gather/scatter path of BNG_MEM_HOST
+        import torch
+        from bng_b200 import MEM_HOST
+        ta = torch.from_numpy(arena.copy()).pin_memory()
+        tl = torch.from_numpy(lens.view(np.int32).copy()).pin_memory()
+        to = None if off16 is None else torch.from_numpy(off16.view(np.int32).copy()).pin_memory()
+        tp = None if prio is None else torch.from_numpy(prio.view(np.int32).copy()).pin_memory()
+        tv = torch.zeros(len(lens), dtype=torch.uint8).pin_memory()
+        self.dp.run(prog, ta, tl, now, off16=to, stride=stride, priority=tp, verdict=tv, mem=MEM_HOST,
+                    arena_bytes=arena.nbytes)
+        arena[:] = ta.numpy()
+        lens[:] = tl.numpy().view(np.uint32)
+        if prio is not None:
+            prio[:] = tp.numpy().view(np.uint32)
+        return tv.numpy().copy()
 
     def stats(self, m):
         return self.dp.stats(m)

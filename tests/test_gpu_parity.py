@@ -1,8 +1,9 @@
 """GPU parity: the CUDA dataplane, driven through the C ABI, against the CPU
-oracle(s) and the committed golden vectors, bit for bit."""
+oracle(s) and the committed golden vectors, bit for bit.  Every script runs
+twice: with pageable host buffers (whole-arena staging copies) and with pinned
+host buffers (zero-copy header gather/scatter pipeline)."""
 import os
 
-import numpy as np
 import pytest
 
 import harness
@@ -16,22 +17,23 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def gpu_results():
     cache = {}
 
-    def get(script):
-        if script not in cache:
-            be = harness.GpuBackend()
+    def get(script, pinned):
+        if (script, pinned) not in cache:
+            be = harness.GpuBackend(pinned=pinned)
             try:
-                cache[script] = harness.run_script(be, scenarios.ALL_SCRIPTS[script]())
+                cache[(script, pinned)] = harness.run_script(be, scenarios.ALL_SCRIPTS[script]())
             finally:
                 be.close()
-        return cache[script]
+        return cache[(script, pinned)]
 
     return get
 
 
+@pytest.mark.parametrize("pinned", [False, True], ids=["pageable", "pinned"])
 @pytest.mark.parametrize("script", sorted(scenarios.ALL_SCRIPTS))
-def test_gpu_matches_golden(script, gpu_results):
+def test_gpu_matches_golden(script, pinned, gpu_results):
     gold = harness.load_golden(os.path.join(GOLD, script + ".npz"))
-    harness.compare(gold, gpu_results(script), f"{script}: golden vs gpu")
+    harness.compare(gold, gpu_results(script, pinned), f"{script}: golden vs gpu ({'pinned' if pinned else 'pageable'})")
 
 
 @pytest.mark.parametrize("script", sorted(scenarios.ALL_SCRIPTS))
@@ -40,4 +42,4 @@ def test_gpu_matches_live_oracle(script, ora_kind, gpu_results):
         pytest.fail("no oracle library present on this box")
     be = harness.OracleBackend(ora_kind)
     res = harness.run_script(be, scenarios.ALL_SCRIPTS[script]())
-    harness.compare(res, gpu_results(script), f"{script}: {ora_kind} oracle vs gpu")
+    harness.compare(res, gpu_results(script, False), f"{script}: {ora_kind} oracle vs gpu")
