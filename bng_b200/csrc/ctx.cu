@@ -789,9 +789,17 @@ static int run_host_zero_copy(bng_ctx *c, int prog, bng_batch *bb, u8 *arena_dev
         if (bb->priority)
             CU(c, cudaMemcpyAsync(c->zc_prio[buf], bb->priority + base, (size_t)cn * 4, cudaMemcpyHostToDevice, c->s_in));
         u8 *chunk_arena = bb->off16 ? arena_dev : arena_dev + (size_t)base * bb->stride;
-        CU(c, run_gather_frames(c->s_in, c->L.num_sms, chunk_arena, bb->off16 ? c->zc_off[buf] : nullptr, c->zc_len[buf],
-                                bb->stride, cn, hb, c->zc_hdr[buf], c->zc_len0[buf]));
-        c->L.launches++;
+        // frames that ARE their header slot (fixed stride == header bytes, e.g. 64-byte frames or a
+        // header-split receive ring) move with the copy engines; anything else is gathered by SMs
+        const bool contiguous = !bb->off16 && bb->stride == hb;
+        if (contiguous) {
+            CU(c, cudaMemcpyAsync(c->zc_hdr[buf], (u8 *)bb->pkts + (size_t)base * hb, (size_t)cn * hb, cudaMemcpyHostToDevice,
+                                  c->s_in));
+        } else {
+            CU(c, run_gather_frames(c->s_in, c->L.num_sms, chunk_arena, bb->off16 ? c->zc_off[buf] : nullptr, c->zc_len[buf],
+                                    bb->stride, cn, hb, c->zc_hdr[buf], c->zc_len0[buf]));
+            c->L.launches++;
+        }
         CU(c, cudaEventRecord(c->ev_in[buf], c->s_in));
         // ---- compute ----
         CU(c, cudaStreamWaitEvent(sc, c->ev_in[buf], 0));
@@ -810,9 +818,14 @@ static int run_host_zero_copy(bng_ctx *c, int prog, bng_batch *bb, u8 *arena_dev
         CU(c, cudaEventRecord(c->ev_comp[buf], sc));
         // ---- out ----
         CU(c, cudaStreamWaitEvent(c->s_out, c->ev_comp[buf], 0));
-        CU(c, run_scatter_frames(c->s_out, c->L.num_sms, chunk_arena, bb->off16 ? c->zc_off[buf] : nullptr, c->zc_len0[buf],
-                                 bb->stride, cn, hb, c->zc_hdr[buf], first_chunk));
-        c->L.launches++;
+        if (contiguous) {
+            CU(c, cudaMemcpyAsync((u8 *)bb->pkts + (size_t)base * hb, c->zc_hdr[buf], (size_t)cn * hb, cudaMemcpyDeviceToHost,
+                                  c->s_out));
+        } else {
+            CU(c, run_scatter_frames(c->s_out, c->L.num_sms, chunk_arena, bb->off16 ? c->zc_off[buf] : nullptr,
+                                     c->zc_len0[buf], bb->stride, cn, hb, c->zc_hdr[buf], first_chunk));
+            c->L.launches++;
+        }
         CU(c, cudaMemcpyAsync(bb->verdict + base, c->zc_verdict[buf], cn, cudaMemcpyDeviceToHost, c->s_out));
         if (prog == P_DHCP)
             CU(c, cudaMemcpyAsync(bb->len + base, c->zc_len[buf], (size_t)cn * 4, cudaMemcpyDeviceToHost, c->s_out));

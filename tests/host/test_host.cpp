@@ -1,0 +1,373 @@
+// Tests of the C++ host mirror (bng_b200/host/bng_host.hpp), written after the
+// reference's own Go tests of the same types:
+//   pkg/ebpf/loader_test.go (conversions :16-130, FNV-1a :221-249, nil-map errors :383-446, Close :989-1003)
+//   test/ebpf/maps_test.go  (struct sizes :68-130, circuit-id key :235-269)
+//   pkg/nat/manager_test.go (port blocks :164-247), pkg/nat/manager_additional_test.go (flags/log2 :395-477)
+//   pkg/qos/manager_test.go (bookkeeping :80-222), pkg/antispoof/manager_test.go
+// `test_host cpu` runs everything that needs no device (the reference's "never call Start/Load" mode);
+// `test_host gpu` additionally loads the dataplane and round-trips through the C ABI.
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "../../bng_b200/host/bng_host.hpp"
+
+using namespace bng;
+
+static int g_fail = 0, g_checks = 0;
+#define CHECK(cond)                                                              \
+    do {                                                                         \
+        g_checks++;                                                              \
+        if (!(cond)) {                                                           \
+            g_fail++;                                                            \
+            fprintf(stderr, "FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond);      \
+        }                                                                        \
+    } while (0)
+#define CHECK_EQ(a, b)                                                                                        \
+    do {                                                                                                      \
+        g_checks++;                                                                                           \
+        auto va = (a);                                                                                        \
+        auto vb = (b);                                                                                        \
+        if (!(va == vb)) {                                                                                    \
+            g_fail++;                                                                                         \
+            fprintf(stderr, "FAIL %s:%d: %s == %s (%llu vs %llu)\n", __FILE__, __LINE__, #a, #b,              \
+                    (unsigned long long)va, (unsigned long long)vb);                                          \
+        }                                                                                                     \
+    } while (0)
+#define CHECK_ERR(e, text) CHECK((e).what() == std::string(text))
+
+static std::vector<uint8_t> bytes(const char *s) { return std::vector<uint8_t>(s, s + strlen(s)); }
+
+static void test_conversions() {
+    CHECK_EQ(ebpf::IPToUint32(IPv4(10, 0, 1, 1)), 0x0A000101u);
+    CHECK_EQ(ebpf::IPToUint32(IPv4(192, 168, 1, 100)), 0xC0A80164u);
+    CHECK_EQ(ebpf::IPToUint32(IPv4(255, 255, 255, 255)), 0xFFFFFFFFu);
+    CHECK_EQ(ebpf::IPToUint32(IP{}), 0u);
+    IP mapped(16, 0);
+    mapped[10] = mapped[11] = 0xff;
+    mapped[12] = 10, mapped[13] = 0, mapped[14] = 1, mapped[15] = 1;
+    CHECK_EQ(ebpf::IPToUint32(mapped), 0x0A000101u);
+    IP v6(16, 0x20);
+    CHECK_EQ(ebpf::IPToUint32(v6), 0u);
+    CHECK(ebpf::Uint32ToIP(0x0A000101) == IPv4(10, 0, 1, 1));
+    CHECK_EQ(ebpf::MACToUint64(MAC{0xaa, 0xbb, 0xcc, 0xdd, 0xee, 0xff}), 0xAABBCCDDEEFFull);
+    CHECK_EQ(ebpf::MACToUint64(MAC{0, 0, 0, 0, 0, 1}), 1ull);
+    CHECK_EQ(ebpf::MACToUint64(MAC{1, 2, 3}), 0ull);
+    CHECK(ebpf::Uint64ToMAC(0xAABBCCDDEEFFull) == (MAC{0xaa, 0xbb, 0xcc, 0xdd, 0xee, 0xff}));
+    CHECK_EQ(ebpf::HashCircuitID({}), 0xcbf29ce484222325ull);
+    CHECK_EQ(ebpf::HashCircuitID(bytes("a")), 0xaf63dc4c8601ec8cull);
+    CHECK_EQ(ebpf::HashCircuitID(bytes("foobar")), 0x85944171f73967e8ull);
+    CHECK(ebpf::HashCircuitID(bytes("eth 0/1/1:100")) != ebpf::HashCircuitID(bytes("eth 0/1/1:101")));
+    auto k = ebpf::MakeCircuitIDKey(bytes("short"));
+    CHECK(memcmp(k.b, "short", 5) == 0 && k.b[5] == 0 && k.b[31] == 0);
+    std::vector<uint8_t> lng(40, 'x');
+    k = ebpf::MakeCircuitIDKey(lng);
+    CHECK(k.b[31] == 'x');
+    uint64_t e = ebpf::LeaseExpiryFromDuration(std::chrono::seconds(3600));
+    CHECK(e > 1700000000ull);
+    CHECK_EQ(sizeof(ebpf::ServerConfig), 16u);
+    CHECK_EQ(sizeof(ebpf::DHCPStats), 80u);
+    CHECK_EQ(sizeof(ebpf::VLANKey), 4u);
+    CHECK_EQ(sizeof(ebpf::CircuitIDKey), 32u);
+    CHECK_EQ(sizeof(ebpf::PoolAssignment), 25u);
+    CHECK_EQ(sizeof(ebpf::IPPool), 28u);
+}
+
+static void test_loader_unloaded() {
+    auto bad = ebpf::Loader::NewLoader("");
+    CHECK(!bad.ok());
+    CHECK_ERR(bad.err, "interface name is required");
+    auto lr = ebpf::Loader::NewLoader("eth0");
+    CHECK(lr.ok());
+    auto l = *lr.value;
+    ebpf::PoolAssignment a;
+    CHECK_ERR(l->AddSubscriber(1, a), "subscriber_pools map not loaded");
+    CHECK_ERR(l->RemoveSubscriber(1), "subscriber_pools map not loaded");
+    CHECK_ERR(l->GetSubscriber(1).err, "subscriber_pools map not loaded");
+    CHECK_ERR(l->AddVLANSubscriber(1, 2, a), "vlan_subscriber_pools map not loaded");
+    CHECK_ERR(l->GetVLANSubscriber(1, 2).err, "vlan_subscriber_pools map not loaded");
+    CHECK(!l->HasVLANSupport());
+    ebpf::IPPool p;
+    CHECK_ERR(l->AddPool(1, p), "ip_pools map not loaded");
+    CHECK_ERR(l->GetPool(1).err, "ip_pools map not loaded");
+    CHECK_ERR(l->GetStats().err, "stats_map not loaded");
+    CHECK_ERR(l->ResetStats(), "stats_map not loaded");
+    CHECK_ERR(l->SetServerConfig(MAC(6, 1), IPv4(10, 0, 0, 1), 2), "server_config map not loaded");
+    CHECK_ERR(l->GetServerConfig().err, "server_config map not loaded");
+    CHECK_ERR(l->AddCircuitIDMapping(bytes("x"), 1), "circuit_id_map not loaded");
+    CHECK_ERR(l->GetCircuitIDMapping(bytes("x")).err, "circuit_id_map not loaded");
+    CHECK_ERR(l->CheckCircuitIDCollision(bytes("x"), 1).err, "circuit_id_map not loaded");
+    CHECK_ERR(l->AddCircuitIDSubscriber(bytes("x"), a), "circuit_id_subscribers map not loaded");
+    CHECK_ERR(l->GetCircuitIDSubscriber(bytes("x")).err, "circuit_id_subscribers map not loaded");
+    CHECK(!l->HasCircuitIDSubscriberSupport());
+    CHECK(!l->Close());
+    CHECK(!l->Close()); // idempotent
+}
+
+static void test_nat_allocator() {
+    CHECK(!nat::Manager::NewManager({}).ok());
+    nat::ManagerConfig cfg;
+    cfg.Interface = "eth0";
+    cfg.EnableEIM = cfg.EnableEIF = cfg.EnableHairpin = cfg.EnableFTPALG = true;
+    auto m = *nat::Manager::NewManager(cfg).value;
+    CHECK_EQ(m->buildFlags(), 0x0Fu);
+    CHECK_ERR(m->AddPublicIP(IP(16, 1)), "IPv4 address required");
+    CHECK(!m->AddPublicIP(IPv4(203, 0, 113, 1)));
+    CHECK(!m->AddPublicIPRange(IPv4(203, 0, 113, 2), IPv4(203, 0, 113, 3)));
+    CHECK_ERR(m->AddPublicIPRange(IPv4(203, 0, 113, 9), IPv4(203, 0, 113, 3)), "start IP must be less than or equal to end IP");
+    auto pool = m->GetPoolStats();
+    CHECK_EQ(pool.size(), 3u);
+    CHECK_EQ(pool[0].TotalPorts, 64512);
+    CHECK_EQ(pool[0].MaxSubscribers, 63); // (65535-1024+1)/1024
+    auto a1 = m->AllocateNAT(IPv4(100, 64, 0, 1));
+    CHECK(a1.ok());
+    CHECK_EQ(a1->PortStart, 1024);
+    CHECK_EQ(a1->PortEnd, 2047);
+    CHECK_EQ(a1->SubscriberID, 1u);
+    CHECK(a1->PublicIP == IPv4(203, 0, 113, 1));
+    auto a2 = m->AllocateNAT(IPv4(100, 64, 0, 2));
+    CHECK_EQ(a2->PortStart, 2048);
+    CHECK_EQ(a2->PortEnd, 3071);
+    CHECK_EQ(a2->SubscriberID, 2u);
+    auto again = m->AllocateNAT(IPv4(100, 64, 0, 1));
+    CHECK_EQ(again->PortStart, 1024);
+    CHECK_EQ(m->GetAllocationCount(), 2);
+    for (int i = 3; i <= 63; i++) CHECK(m->AllocateNAT(ebpf::Uint32ToIP(0x64400000u + i)).ok());
+    auto a64 = m->AllocateNAT(IPv4(100, 64, 0, 64)); // first IP is full: next pool entry, first block
+    CHECK(a64->PublicIP == IPv4(203, 0, 113, 2));
+    CHECK_EQ(a64->PortStart, 1024);
+    CHECK_EQ(a64->PoolIndex, 1);
+    CHECK(!m->DeallocateNAT(IPv4(100, 64, 0, 2)));
+    CHECK(!m->DeallocateNAT(IPv4(100, 64, 0, 2))); // not allocated: nil
+    CHECK(!m->GetAllocation(IPv4(100, 64, 0, 2)).has_value());
+    CHECK_EQ(m->GetPoolStats()[0].Subscribers, 62);
+    auto re = m->AllocateNAT(IPv4(100, 64, 9, 9)); // Subscribers-- makes the next block overlap a live one (kept)
+    CHECK_EQ(re->PortStart, (uint16_t)(1024 + 62 * 1024));
+    CHECK_EQ(re->SubscriberID, 65u);
+    nat::ManagerConfig small;
+    small.Interface = "eth0";
+    small.PortsPerSubscriber = 32256;
+    auto s = *nat::Manager::NewManager(small).value;
+    s->AddPublicIP(IPv4(198, 51, 100, 1));
+    CHECK(s->AllocateNAT(IPv4(10, 0, 0, 1)).ok());
+    CHECK(s->AllocateNAT(IPv4(10, 0, 0, 2)).ok());
+    CHECK_ERR(s->AllocateNAT(IPv4(10, 0, 0, 3)).err, "NAT pool exhausted: no available public IPs");
+    CHECK_EQ(nat::log2(1), 0);
+    CHECK_EQ(nat::log2(1024), 10);
+    CHECK_EQ(nat::log2(1500), 10);
+    CHECK_EQ(nat::log2(65536), 16);
+    CHECK_ERR(m->ConfigureALG(21, 6, nat::ALGTypeFTP, true), "ALG map not loaded");
+    CHECK_ERR(m->GetStats().err, "stats map not loaded");
+    CHECK_ERR(m->GetEIMMapping(IPv4(10, 0, 0, 1), 80, 6).err, "EIM table not loaded");
+    CHECK_ERR(m->LookupSession(IPv4(10, 0, 0, 1), IPv4(8, 8, 8, 8), 1, 2, 6).err, "sessions map not loaded");
+    CHECK_EQ((uint32_t)nat::NATLogPortExhaustion, 5u);
+    CHECK_EQ((uint32_t)nat::NATFlagPortContiguity, 0x40u);
+}
+
+static void test_qos_bookkeeping() {
+    CHECK(!qos::Manager::NewManager({}).ok());
+    qos::ManagerConfig cfg;
+    cfg.Interface = "eth0";
+    auto nopol = *qos::Manager::NewManager(cfg).value;
+    CHECK_ERR(nopol->SetSubscriberPolicy(IPv4(10, 0, 0, 1), "guest"), "policy manager not configured");
+    auto m = *qos::Manager::NewManager(cfg, qos::DefaultPolicies()).value;
+    CHECK_ERR(m->SetSubscriberPolicy(IPv4(10, 0, 0, 1), "nope"), "policy not found: nope");
+    CHECK(!m->SetSubscriberPolicy(IPv4(10, 0, 0, 1), "residential-100mbps"));
+    CHECK(!m->SetSubscriberPolicy(IPv4(10, 0, 0, 2), "unlimited"));
+    CHECK_EQ(m->GetSubscriberCount(), 2);
+    qos::SubscriberQoS q;
+    CHECK_ERR(m->SetSubscriberQoS(q), "subscriber IP required");
+    q.Addr = IP(16, 1);
+    CHECK_ERR(m->SetSubscriberQoS(q), "IPv4 address required");
+    CHECK(!m->RemoveSubscriberQoS(IPv4(10, 0, 0, 2)));
+    CHECK_EQ(m->GetSubscriberCount(), 1);
+    CHECK_ERR(m->GetStats().err, "stats map not loaded");
+    // burst defaulting (pkg/qos/manager.go:181-209)
+    q.Addr = IPv4(10, 0, 0, 3);
+    q.DownloadBPS = 100000000;
+    q.UploadBPS = 20000000;
+    CHECK_EQ(qos::Manager::egressBucket(q).BurstBytes, 10u * 1024 * 1024); // 12.5 MB capped at 10 MiB
+    CHECK_EQ(qos::Manager::ingressBucket(q).BurstBytes, 2500000u);
+    q.DownloadBPS = 100000;
+    CHECK_EQ(qos::Manager::egressBucket(q).BurstBytes, 65536u);
+    q.BurstBytes = 2000000;
+    CHECK_EQ(qos::Manager::egressBucket(q).BurstBytes, 2000000u);
+    CHECK_EQ(qos::Manager::ingressBucket(q).BurstBytes, 2500000u); // upload ignores BurstBytes
+    CHECK_EQ(qos::Manager::egressBucket(q).Tokens, 2000000ull);
+    CHECK_EQ(qos::Manager::egressBucket(q).LastUpdate, 0ull);
+}
+
+static void test_antispoof_bookkeeping() {
+    CHECK(!antispoof::Manager::NewManager({}).ok());
+    antispoof::ManagerConfig cfg;
+    cfg.Interface = "eth0";
+    cfg.DefaultMode = antispoof::ModeStrict;
+    auto m = *antispoof::Manager::NewManager(cfg).value;
+    CHECK_ERR(m->AddBinding(MAC{1, 2, 3}, IPv4(10, 0, 0, 1)), "invalid MAC address");
+    CHECK(!m->AddBinding(MAC{2, 0, 0, 0, 0, 1}, IPv4(10, 0, 0, 1)));
+    CHECK(!m->AddBinding(MAC{2, 0, 0, 0, 0, 2}, IPv4(10, 0, 0, 2)));
+    CHECK_EQ(m->GetBindingCount(), 2);
+    CHECK(!m->RemoveBinding(MAC{2, 0, 0, 0, 0, 2}));
+    CHECK_EQ(m->GetBindingCount(), 1);
+    CHECK_ERR(m->AddAllowedRange(IPv4(10, 0, 0, 0), 8), "ranges map not loaded");
+    CHECK_ERR(m->GetStats().err, "stats map not loaded");
+    CHECK(!m->SetMode(antispoof::ModeLoose));
+    CHECK_EQ(sizeof(antispoof::SubscriberBinding), 24u);
+}
+
+// ---- with a device: everything round-trips through the C ABI ----
+static void test_gpu_roundtrips() {
+    bng_open_opts o;
+    memset(&o, 0, sizeof(o));
+    o.struct_size = sizeof(o);
+    o.device = -1;
+    o.max_subscribers = 4096;
+    o.max_nat_sessions = 8192;
+    o.max_eim_mappings = 8192;
+    o.max_batch = 4096;
+    auto be = Backend::Open(&o);
+    CHECK(be->ctx != nullptr);
+    if (!be->ctx) {
+        fprintf(stderr, "bng_open: %s\n", be->open_error.c_str());
+        return;
+    }
+    be->wire_order_keys = true; // store addresses as the programs read them off the wire
+    auto l = *ebpf::Loader::NewLoader("eth0", be).value;
+    CHECK(!l->Load());
+    CHECK(l->HasVLANSupport() && l->HasCircuitIDSubscriberSupport());
+    ebpf::PoolAssignment a;
+    a.PoolID = 7;
+    a.AllocatedIP = 0x0100000A;
+    a.LeaseExpiry = 1ull << 40;
+    a.ClientClass = 2;
+    CHECK(!l->AddSubscriber(0x020000000001ull, a));
+    auto g = l->GetSubscriber(0x020000000001ull);
+    CHECK(g.ok() && g->PoolID == 7 && g->LeaseExpiry == (1ull << 40) && g->ClientClass == 2);
+    CHECK(!l->GetSubscriber(0x020000000002ull).ok());
+    CHECK(!l->RemoveSubscriber(0x020000000001ull));
+    CHECK((bool)l->RemoveSubscriber(0x020000000001ull)); // second delete: error, as Map.Delete does
+    CHECK(!l->AddVLANSubscriber(100, 7, a));
+    CHECK(l->GetVLANSubscriber(100, 7).ok() && !l->GetVLANSubscriber(100, 8).ok());
+    ebpf::IPPool p;
+    p.PrefixLen = 24;
+    p.LeaseTime = 3600;
+    CHECK(!l->AddPool(7, p));
+    CHECK(l->GetPool(7).ok() && l->GetPool(7)->LeaseTime == 3600);
+    CHECK(!l->SetServerConfig(MAC{2, 0xaa, 0xbb, 0xcc, 0xdd, 1}, IPv4(10, 0, 0, 1), 3));
+    auto sc = l->GetServerConfig();
+    CHECK(sc.ok() && sc->ServerMAC[1] == 0xaa && sc->InterfaceIndex == 3 && sc->ServerIP == 0x0100000Au);
+    CHECK(!l->AddCircuitIDMapping(bytes("eth 0/1/1:100"), 42));
+    CHECK(*l->GetCircuitIDMapping(bytes("eth 0/1/1:100")).value == 42ull);
+    CHECK(*l->CheckCircuitIDCollision(bytes("eth 0/1/1:100"), 42).value == false);
+    CHECK(*l->CheckCircuitIDCollision(bytes("eth 0/1/1:100"), 43).value == true);
+    CHECK(*l->CheckCircuitIDCollision(bytes("other"), 43).value == false);
+    CHECK(!l->AddCircuitIDSubscriber(bytes("eth 0/1/1:100"), a));
+    CHECK(l->GetCircuitIDSubscriber(bytes("eth 0/1/1:100")).ok());
+    auto st = l->GetStats();
+    CHECK(st.ok() && st->TotalRequests == 0);
+
+    antispoof::ManagerConfig ac;
+    ac.Interface = "eth0";
+    ac.DefaultMode = antispoof::ModeStrict;
+    ac.Backend_ = be;
+    auto am = *antispoof::Manager::NewManager(ac).value;
+    CHECK(!am->Start());
+    antispoof::Config cfgv;
+    uint32_t zero = 0;
+    CHECK_EQ(bng_map_lookup(be->ctx, be->Map("antispoof_config"), &zero, &cfgv), 0);
+    CHECK(cfgv.DefaultMode == 1 && cfgv.LogViolations == 1);
+    MAC mac{2, 0, 0, 0, 0, 9};
+    CHECK(!am->AddBinding(mac, IPv4(100, 64, 0, 9)));
+    IP v6(16, 0);
+    v6[0] = 0x20, v6[15] = 9;
+    CHECK(!am->AddBindingV6(mac, v6));
+    antispoof::SubscriberBinding sb;
+    uint64_t mk = ebpf::MACToUint64(mac);
+    CHECK_EQ(bng_map_lookup(be->ctx, be->Map("subscriber_bindings"), &mk, &sb), 0);
+    CHECK(sb.IPv4Valid == 1 && sb.IPv6Valid == 1 && sb.IPv6Addr[15] == 9 && sb.Mode == 1);
+    CHECK_EQ(sb.IPv4Addr, 0x09004064u); // wire order 100.64.0.9 read little-endian
+    CHECK(!am->AddAllowedRange(IPv4(100, 64, 0, 0), 10));
+
+    qos::ManagerConfig qc;
+    qc.Interface = "eth0";
+    qc.Backend_ = be;
+    auto qm = *qos::Manager::NewManager(qc, qos::DefaultPolicies()).value;
+    CHECK(!qm->Start());
+    CHECK(!qm->SetSubscriberPolicy(IPv4(100, 64, 0, 9), "residential-100mbps"));
+    qos::TokenBucket tb;
+    uint32_t ipk = 0x09004064u;
+    CHECK_EQ(bng_map_lookup(be->ctx, be->Map("qos_egress"), &ipk, &tb), 0);
+    CHECK(tb.RateBPS == 100000000ull && tb.BurstBytes == 2000000u && tb.Tokens == 2000000ull && tb.Priority == 4);
+    CHECK_EQ(bng_map_lookup(be->ctx, be->Map("qos_ingress"), &ipk, &tb), 0);
+    CHECK(tb.RateBPS == 20000000ull && tb.BurstBytes == 2500000u);
+
+    nat::ManagerConfig nc;
+    nc.Interface = "eth0";
+    nc.EnableEIM = nc.EnableEIF = nc.EnableHairpin = nc.EnableFTPALG = true;
+    nc.Backend_ = be;
+    auto nm = *nat::Manager::NewManager(nc).value;
+    CHECK(!nm->Start());
+    CHECK(!nm->AddPublicIP(IPv4(203, 0, 113, 1)));
+    auto al = nm->AllocateNAT(IPv4(100, 64, 0, 9));
+    CHECK(al.ok());
+    nat::SubscriberNAT sn;
+    CHECK_EQ(bng_map_lookup(be->ctx, be->Map("subscriber_nat"), &ipk, &sn), 0);
+    CHECK(sn.Block.PortStart == 1024 && sn.Block.PortEnd == 2047 && sn.Block.NextPort == 1024 && sn.Block.SubscriberID == 1 &&
+          sn.Block.BlockSizeLog2 == 10);
+    nat::NATConfig ncfg;
+    CHECK_EQ(bng_map_lookup(be->ctx, be->Map("nat_config_map"), &zero, &ncfg), 0);
+    CHECK(ncfg.Flags == 0x0F && ncfg.PortRangeStart == 1024 && ncfg.PortRangeEnd == 65535 && ncfg.DefaultPortsPerSub == 1024);
+    nat::ALGConfig alg;
+    uint32_t ak = (21u << 16) | 6;
+    CHECK_EQ(bng_map_lookup(be->ctx, be->Map("alg_ports"), &ak, &alg), 0);
+    CHECK(alg.Port == 21 && alg.ALGType == nat::ALGTypeFTP);
+
+    // one frame through the pipeline: the managers' entries must match a real frame (wire-order keys)
+    alignas(16) uint8_t f[64] = {0};
+    const uint8_t hdr[] = {0x02, 0xff, 0xff, 0xff, 0xff, 0xfe, 2, 0, 0, 0, 0, 9, 0x08, 0x00, 0x45, 0, 0, 50, 0, 1, 0x40, 0, 64, 6,
+                           0x12, 0x34, 100, 64, 0, 9, 8, 8, 8, 8, 0x9c, 0x40, 0x01, 0xbb};
+    memcpy(f, hdr, sizeof(hdr));
+    f[47] = 0x10;
+    f[50] = 0xab, f[51] = 0xcd;
+    uint32_t len = 64;
+    uint8_t verdict = 9;
+    bng_batch b;
+    memset(&b, 0, sizeof(b));
+    b.pkts = f;
+    b.len = &len;
+    b.verdict = &verdict;
+    b.n = 1;
+    b.stride = 64;
+    b.now_ns = 1000000000ull;
+    b.mem = BNG_MEM_HOST;
+    CHECK_EQ(bng_prog_run(be->ctx, bng_prog_id(be->ctx, "pipeline_up"), &b), 0);
+    CHECK_EQ((int)verdict, 0);
+    CHECK(f[26] == 203 && f[27] == 0 && f[28] == 113 && f[29] == 1); // source rewritten to the public address
+    auto as = am->GetStats();
+    CHECK(as.ok() && as->PacketsAllowed == 1 && as->PacketsDropped == 0);
+    auto qs = qm->GetStats();
+    CHECK(qs.ok() && qs->PacketsPassed == 1 && qs->BytesPassed == 64);
+    auto ns = nm->GetStats();
+    CHECK(ns.ok() && ns->PacketsSNAT == 1 && ns->SessionsCreated == 1 && ns->EIMMisses == 1);
+    auto ses = nm->LookupSession(IPv4(100, 64, 0, 9), IPv4(8, 8, 8, 8), 0x409c, 0xbb01, 6);
+    CHECK(ses.ok() && ses->PacketsOut == 1 && ses->BytesOut == 64 && ses->Protocol == 6 && ses->OrigPort == 0x409c);
+    auto eim = nm->GetEIMMapping(IPv4(100, 64, 0, 9), 0x409c, 6);
+    CHECK(eim.ok() && eim->ExternalPort == 1024 && eim->RefCount == 1);
+    auto log = nm->DrainLog();
+    CHECK(log.size() == 1 && log[0].EventType == nat::NATLogSessionCreate && log[0].SubscriberID == 1);
+    CHECK(!nm->DeallocateNAT(IPv4(100, 64, 0, 9)));
+    CHECK(bng_map_lookup(be->ctx, be->Map("subscriber_nat"), &ipk, &sn) != 0);
+    CHECK(!l->Close());
+}
+
+int main(int argc, char **argv) {
+    std::string mode = argc > 1 ? argv[1] : "cpu";
+    test_conversions();
+    test_loader_unloaded();
+    test_nat_allocator();
+    test_qos_bookkeeping();
+    test_antispoof_bookkeeping();
+    if (mode == "gpu") test_gpu_roundtrips();
+    printf("%s: %d checks, %d failed\n", mode.c_str(), g_checks, g_fail);
+    return g_fail ? 1 : 0;
+}
