@@ -5,6 +5,7 @@
 #include <errno.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -750,7 +751,18 @@ static int dispatch(bng_ctx *c, int prog, const DevBatch &b) {
 //   s_out  : header scatter back into the host arena (+ verdict / length D2H)
 // so PCIe reads, PCIe writes and compute of successive chunks overlap, and only the bytes a
 // program can touch ever cross the bus.
-#define ZC_CHUNK (1u << 19)
+static u32 zc_chunk_frames() { // frames per pipeline chunk; BNG_ZC_CHUNK_LOG2 overrides for tuning
+    static u32 v = 0;
+    if (!v) {
+        const char *e = getenv("BNG_ZC_CHUNK_LOG2");
+        int lg = e ? atoi(e) : 19;
+        if (lg < 10) lg = 10;
+        if (lg > 22) lg = 22;
+        v = 1u << lg;
+    }
+    return v;
+}
+#define ZC_CHUNK (zc_chunk_frames())
 static int run_host_zero_copy(bng_ctx *c, int prog, bng_batch *bb, u8 *arena_dev) {
     const u32 hb = prog == P_DHCP ? 448u : 64u;
     const u32 first_chunk = prog == P_DHCP ? 0u : 1u; // TC programs never write the Ethernet addresses
