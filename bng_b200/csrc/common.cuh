@@ -257,8 +257,13 @@ __device__ __forceinline__ u8 *tbl_find(const Tbl &t, const u64 *k) {
 // it.  A claimed slot is left in the K_BUSY state with key words 1.. written:
 // the caller fills the value and then calls tbl_publish().  Returns nullptr
 // when the table is full (max_entries reached or no free slot).
+// `pending` (optional): the caller batches its live-entry accounting — the claim is checked against
+// count + *pending and counted in *pending, and the caller adds *pending to t.count once (one global
+// atomic per warp instead of one per insert, which on a million-insert batch is the difference
+// between a same-address atomic storm and none).  The max_entries check is then approximate by at
+// most the inserts in flight, which only matters for the LRU maps at the very edge of capacity.
 template <int KW>
-__device__ __forceinline__ u8 *tbl_find_or_claim(const Tbl &t, const u64 *k, bool *created) {
+__device__ __forceinline__ u8 *tbl_find_or_claim(const Tbl &t, const u64 *k, bool *created, u32 *pending = nullptr) {
     *created = false;
     if (k[0] >= K_BUSY) return nullptr;
     u32 i = (u32)tbl_hash<KW>(k) & t.mask;
@@ -281,7 +286,9 @@ __device__ __forceinline__ u8 *tbl_find_or_claim(const Tbl &t, const u64 *k, boo
             u32 target = tomb >= 0 ? (u32)tomb : i;
             u64 expect = tomb >= 0 ? K_TOMB : K_EMPTY;
             u8 *ts = tbl_slot(t, target);
-            if (atomicAdd(t.count, 1u) >= t.max_entries) {
+            if (pending) {
+                if (*(volatile u32 *)t.count + *pending >= t.max_entries) return nullptr;
+            } else if (atomicAdd(t.count, 1u) >= t.max_entries) {
                 atomicSub(t.count, 1u);
                 return nullptr;
             }
@@ -290,10 +297,11 @@ __device__ __forceinline__ u8 *tbl_find_or_claim(const Tbl &t, const u64 *k, boo
 #pragma unroll
                 for (int j = 1; j < KW; j++) ((u64 *)ts)[j] = k[j];
                 *created = true;
+                if (pending) ++*pending;
                 return ts;
             }
             // lost the race for that slot: undo the reservation and look again
-            atomicSub(t.count, 1u);
+            if (!pending) atomicSub(t.count, 1u);
             if (tomb >= 0) {
                 tomb = -1;
                 i = (u32)tbl_hash<KW>(k) & t.mask;

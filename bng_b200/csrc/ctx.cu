@@ -973,6 +973,8 @@ int bng_events_drain(bng_ctx *c, int map, void *buf, uint64_t cap_records, uint6
         u64 per = ((u64)m->ev_payload + 8 + 7) & ~7ull;
         u64 used = (m->ev_pending.size() / m->ev_payload) * per;
         for (u32 i = 0; i < cnt; i++) {
+            const u32 *tag = (const u32 *)(base + (size_t)order[i] * rb + rb - 8);
+            if (tag[0] == 0xFFFFFFFFu) continue; // reserved by the resolve kernel but never written
             if (m->type == T_RINGBUF) {
                 if (used + per > (u64)m->max_entries - 1) continue; // bpf_ringbuf_reserve() == NULL
                 used += per;

@@ -32,7 +32,22 @@
 #define MISS_FLAG 0x80000000u
 
 // device-side counters (Scratch::counters)
-enum { CNT_M = 0, CNT_NSEG = 1, CNT_DEFERRED = 2 };
+enum { CNT_M = 0, CNT_NSEG = 1, CNT_DEFERRED = 2, CNT_MAXKEY = 3 };
+
+// The grouped (key, value) arrays live in one of two ping-pong buffers depending on how many radix
+// passes actually ran: passes whose digit is zero for every key of the batch (largest key < 2^(8p))
+// are skipped on the device, so the consumers pick the buffer from the device-side maximum.
+struct Grouped {
+    const u32 *ka, *va, *kb, *vb; // pass 0 writes a -> b, pass 1 b -> a, ...
+    int passes;
+};
+__device__ __forceinline__ bool rs_pass_needed(const u32 *cnt, int shift) { return shift == 0 || (cnt[CNT_MAXKEY] >> shift) != 0; }
+__device__ __forceinline__ void grouped_select(const Grouped &g, const u32 *cnt, const u32 *&k, const u32 *&v) {
+    int done = 1;
+    while (done < g.passes && rs_pass_needed(cnt, 8 * done)) done++;
+    k = (done & 1) ? g.kb : g.ka;
+    v = (done & 1) ? g.vb : g.va;
+}
 
 // ---------------------------------------------------------------------------
 // antispoof_ingress
@@ -134,7 +149,7 @@ __global__ void __launch_bounds__(BLOCK) k_nat_hairpin_xdp(const __grid_constant
 // read *cnt[CNT_M] elements.  Every block owns one contiguous range of the
 // input, so (digit, block) order of the scanned histogram is index order.
 // ---------------------------------------------------------------------------
-#define RS_BLOCKS_PER_SM 4
+#define RS_BLOCKS_PER_SM 6
 
 __device__ __forceinline__ void rs_range(u32 total, u32 &lo, u32 &hi) {
     u32 per = (total + gridDim.x - 1) / gridDim.x;
@@ -144,18 +159,31 @@ __device__ __forceinline__ void rs_range(u32 total, u32 &lo, u32 &hi) {
     hi = r < total ? (u32)r : total;
 }
 
-__global__ void __launch_bounds__(BLOCK) k_rs_hist(const u32 *keys, u32 n_host, const u32 *cnt, int first, int shift, u32 *H, u32 *T) {
+__global__ void __launch_bounds__(BLOCK) k_rs_hist(const u32 *keys, u32 n_host, u32 *cnt, int first, int shift, u32 *H, u32 *T) {
     __shared__ u32 h[256];
+    __shared__ u32 smax;
+    if (!rs_pass_needed(cnt, shift)) return; // every key has a zero digit here: the pass would be the identity
     h[threadIdx.x] = 0;
+    if (threadIdx.x == 0) smax = 0;
     __syncthreads();
+    u32 mymax = 0;
     u32 total = first ? n_host : cnt[CNT_M];
     u32 lo, hi;
     rs_range(total, lo, hi);
     for (u32 i = lo + threadIdx.x; i < hi; i += BLOCK) {
         u32 k = keys[i];
-        if (k != NO_KEY) atomicAdd(&h[(k >> shift) & 0xff], 1u);
+        if (k != NO_KEY) {
+            atomicAdd(&h[(k >> shift) & 0xff], 1u);
+            mymax = k > mymax ? k : mymax;
+        }
     }
     __syncthreads();
+    if (first) {
+        mymax = __reduce_max_sync(0xffffffffu, mymax);
+        if ((threadIdx.x & 31) == 0 && mymax) atomicMax(&smax, mymax);
+        __syncthreads();
+        if (threadIdx.x == 0 && smax) atomicMax(&cnt[CNT_MAXKEY], smax);
+    }
     u32 v = h[threadIdx.x];
     H[threadIdx.x * gridDim.x + blockIdx.x] = v;
     if (v) atomicAdd(&T[threadIdx.x], v); // per-digit totals over all blocks
@@ -163,9 +191,10 @@ __global__ void __launch_bounds__(BLOCK) k_rs_hist(const u32 *keys, u32 n_host, 
 
 // Exclusive scan of the 256 x nblocks histogram in (digit, block) order.  One block per digit:
 // base = total of the smaller digits (from T), then a block-wide scan of the digit's row.
-__global__ void __launch_bounds__(1024) k_rs_scan(u32 *H, const u32 *T, u32 nblocks, u32 *cnt, int first) {
+__global__ void __launch_bounds__(1024) k_rs_scan(u32 *H, const u32 *T, u32 nblocks, u32 *cnt, int first, int shift) {
     __shared__ u32 wsum[32];
     __shared__ u32 s_base;
+    if (!rs_pass_needed(cnt, shift)) return;
     const u32 d = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     u32 t = (threadIdx.x < 256 && threadIdx.x < d) ? T[threadIdx.x] : 0; // digits below d
     t = __reduce_add_sync(0xffffffffu, t);
@@ -201,53 +230,83 @@ __global__ void __launch_bounds__(1024) k_rs_scan(u32 *H, const u32 *T, u32 nblo
     if (first && d == 255 && threadIdx.x == 1023) cnt[CNT_M] = s_base + wsum[31] + inc; // = number of valid keys
 }
 
+// Stable scatter of one radix pass.  A tile is RS_ROWS x 256 elements (row-major = index order);
+// ranks inside a warp come from __match_any_sync, per-(row, warp) digit counts go to shared memory
+// and thread d turns them into running offsets of digit d — three block barriers per 1024 elements.
+#define RS_ROWS 4
 __global__ void __launch_bounds__(BLOCK) k_rs_scatter(const u32 *keys, const u32 *vals, u32 *okeys, u32 *ovals, u32 n_host,
                                                       const u32 *cnt, int first, int shift, const u32 *H) {
     __shared__ u32 offs[256];
-    __shared__ u32 wcnt[BLOCK / 32][256];
+    __shared__ u32 wcnt[RS_ROWS * (BLOCK / 32)][256];
+    if (!rs_pass_needed(cnt, shift)) return;
     offs[threadIdx.x] = H[threadIdx.x * gridDim.x + blockIdx.x];
     u32 total = first ? n_host : cnt[CNT_M];
     u32 lo, hi;
     rs_range(total, lo, hi);
     const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (u32 base = lo; base < hi; base += BLOCK) {
-        u32 i = base + threadIdx.x;
-        u32 k = NO_KEY, v = 0;
-        if (i < hi) {
-            k = keys[i];
-            v = vals[i];
-        }
-        bool valid = k != NO_KEY;
-        u32 d = valid ? ((k >> shift) & 0xff) : (256 + lane); // invalid lanes match nobody
+    u32 nk[RS_ROWS], nv[RS_ROWS]; // next tile, fetched while the current one goes through shared memory
 #pragma unroll
-        for (int r = 0; r < BLOCK / 32; r++) wcnt[r][threadIdx.x] = 0;
+    for (int r = 0; r < RS_ROWS; r++) {
+        u32 i = lo + r * BLOCK + threadIdx.x;
+        nk[r] = NO_KEY;
+        nv[r] = 0;
+        if (i < hi) {
+            nk[r] = keys[i];
+            nv[r] = vals[i];
+        }
+    }
+    for (u32 base = lo; base < hi; base += RS_ROWS * BLOCK) {
+        u32 k[RS_ROWS], v[RS_ROWS], d[RS_ROWS], rank[RS_ROWS];
+#pragma unroll
+        for (int r = 0; r < RS_ROWS; r++) {
+            k[r] = nk[r];
+            v[r] = nv[r];
+            d[r] = k[r] != NO_KEY ? ((k[r] >> shift) & 0xff) : (256 + lane); // invalid lanes match nobody
+            u32 i = base + RS_ROWS * BLOCK + r * BLOCK + threadIdx.x;
+            nk[r] = NO_KEY;
+            nv[r] = 0;
+            if (i < hi) {
+                nk[r] = keys[i];
+                nv[r] = vals[i];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < RS_ROWS * (BLOCK / 32); j++) wcnt[j][threadIdx.x] = 0;
         __syncthreads();
-        u32 peers = __match_any_sync(0xffffffffu, d);
-        u32 rank = __popc(peers & ((1u << lane) - 1));
-        if (valid && rank == 0) wcnt[w][d] = __popc(peers);
+#pragma unroll
+        for (int r = 0; r < RS_ROWS; r++) {
+            u32 peers = __match_any_sync(0xffffffffu, d[r]);
+            rank[r] = __popc(peers & ((1u << lane) - 1));
+            if (k[r] != NO_KEY && rank[r] == 0) wcnt[r * (BLOCK / 32) + w][d[r]] = __popc(peers);
+        }
         __syncthreads();
-        { // thread d: running offsets of digit d across the warps of this tile, in warp (= index) order
+        { // thread d: running offsets of digit d over the (row, warp) cells of this tile, in index order
             u32 run = offs[threadIdx.x];
 #pragma unroll
-            for (int r = 0; r < BLOCK / 32; r++) {
-                u32 t = wcnt[r][threadIdx.x];
-                wcnt[r][threadIdx.x] = run;
+            for (int j = 0; j < RS_ROWS * (BLOCK / 32); j++) {
+                u32 t = wcnt[j][threadIdx.x];
+                wcnt[j][threadIdx.x] = run;
                 run += t;
             }
             offs[threadIdx.x] = run;
         }
         __syncthreads();
-        if (valid) {
-            u32 pos = wcnt[w][d] + rank;
-            okeys[pos] = k;
-            ovals[pos] = v;
+#pragma unroll
+        for (int r = 0; r < RS_ROWS; r++) {
+            if (k[r] != NO_KEY) {
+                u32 pos = wcnt[r * (BLOCK / 32) + w][d[r]] + rank[r];
+                okeys[pos] = k[r];
+                ovals[pos] = v[r];
+            }
         }
         __syncthreads();
     }
 }
 
 // group heads: positions where the sorted key changes (any order; groups are independent)
-__global__ void __launch_bounds__(BLOCK) k_heads(const u32 *skey, u32 *seg, u32 *cnt) {
+__global__ void __launch_bounds__(BLOCK) k_heads(const __grid_constant__ Grouped g, u32 *seg, u32 *cnt) {
+    const u32 *skey, *sval_unused;
+    grouped_select(g, cnt, skey, sval_unused);
     u32 m = cnt[CNT_M];
     for (u32 j = blockIdx.x * BLOCK + threadIdx.x; j < m; j += gridDim.x * BLOCK) {
         if (j == 0 || skey[j - 1] != skey[j]) seg[atomicAdd(&cnt[CNT_NSEG], 1u)] = j;
@@ -262,14 +321,20 @@ __global__ void __launch_bounds__(BLOCK) k_heads(const u32 *skey, u32 *seg, u32 
 // ---------------------------------------------------------------------------
 template <bool NAT, bool QOS, bool EGRESS>
 __global__ void __launch_bounds__(BLOCK) k_resolve(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b,
-                                                   const u32 *skey, const u32 *sval, const u32 *seg, const u32 *cnt) {
+                                                   const __grid_constant__ Grouped g, const u32 *seg, const u32 *cnt) {
     __shared__ BlockStats bs;
     bstats_init(bs);
+    const u32 *skey, *sval;
+    grouped_select(g, cnt, skey, sval);
     const Tbl &qt = EGRESS ? c.qos_eg : c.qos_in;
     const u32 lane = threadIdx.x & 31;
     const u32 warp = (blockIdx.x * BLOCK + threadIdx.x) >> 5, nwarps = (gridDim.x * BLOCK) >> 5;
     const u32 m = cnt[CNT_M], nseg = cnt[CNT_NSEG];
     u64 pp = 0, pb = 0, dp = 0, db = 0; // per-lane partial QoS counters
+    NatPend pend;
+    pend.ses = pend.rev = pend.eim = 0;
+    pend.log_rec = nullptr;
+    pend.logged = false;
     for (u32 s = warp; s < nseg; s += nwarps) {
         const u32 start = seg[s];
         const u32 key = skey[start];
@@ -287,18 +352,38 @@ __global__ void __launch_bounds__(BLOCK) k_resolve(const __grid_constant__ DevCt
             const u32 len = valid ? b.len[idx] : 0;
             bool dropped = false;
             if (NAT) {
-                u32 mm = __ballot_sync(0xffffffffu, valid && (sv & MISS_FLAG));
-                while (mm) { // new flows of this subscriber, strictly in index order
-                    u32 l = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    if (lane == l) {
-                        NatOut o = nat_egress_one<true>(c, bs, frame_ptr(b, idx), len, idx + b.base, b.now);
-                        if (o.verdict == TC_SHOT) {
-                            b.verdict[idx] = TC_SHOT;
-                            dropped = true;
-                        }
+                const bool is_miss = valid && (sv & MISS_FLAG);
+                u32 mm = __ballot_sync(0xffffffffu, is_miss);
+                if (mm) {
+                    // one nat_log_rb reservation for all new flows of this chunk (every one of them
+                    // logs at most one record; a slot left unused is tagged invalid for the drain)
+                    const EvRing &r = c.natlog_ev;
+                    u32 cnt = __popc(mm), basepos = 0;
+                    if (lane == 0) basepos = atomicAdd(r.count, cnt);
+                    basepos = __shfl_sync(0xffffffffu, basepos, 0);
+                    if (lane == 0 && basepos + cnt > r.cap) { // staging ring full: the tail of the chunk has no slot
+                        u32 over = basepos >= r.cap ? cnt : basepos + cnt - r.cap;
+                        atomicSub(r.count, over);
+                        atomicAdd(&c.stats[r.lost_stat], (u64)over);
                     }
-                    __syncwarp();
+                    u32 pos = basepos + __popc(mm & ((1u << lane) - 1));
+                    pend.log_rec = (is_miss && pos < r.cap) ? r.buf + (size_t)pos * r.rec_bytes : nullptr;
+                    pend.logged = false;
+                    if (pend.log_rec) *(uint2 *)(pend.log_rec + r.rec_bytes - 8) = make_uint2(idx + b.base, c.batch_seq);
+                    while (mm) { // new flows of this subscriber, strictly in index order
+                        u32 l = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        if (lane == l) {
+                            NatOut o = nat_egress_one<true>(c, bs, frame_ptr(b, idx), len, idx + b.base, b.now, &pend);
+                            if (o.verdict == TC_SHOT) {
+                                b.verdict[idx] = TC_SHOT;
+                                dropped = true;
+                            }
+                            if (!pend.logged && pend.log_rec) // e.g. the session was created earlier in this batch
+                                *(uint2 *)(pend.log_rec + r.rec_bytes - 8) = make_uint2(0xFFFFFFFFu, c.batch_seq);
+                        }
+                        __syncwarp();
+                    }
                 }
             }
             if (has_bucket) {
@@ -345,6 +430,15 @@ __global__ void __launch_bounds__(BLOCK) k_resolve(const __grid_constant__ DevCt
         if (has_bucket && lane == 0) {
             *(u64 *)(slot + 16) = tb.tokens;
             *(u64 *)(slot + 24) = tb.last_update;
+        }
+    }
+    if (NAT) { // live-entry counts of the flow tables: one global atomic per warp and table
+        u32 a = __reduce_add_sync(0xffffffffu, pend.ses), r2 = __reduce_add_sync(0xffffffffu, pend.rev),
+            e = __reduce_add_sync(0xffffffffu, pend.eim);
+        if (lane == 0) {
+            if (a) atomicAdd(c.sessions.count, a);
+            if (r2) atomicAdd(c.reverse.count, r2);
+            if (e) atomicAdd(c.eim.count, e);
         }
     }
     if (QOS) {
@@ -425,7 +519,7 @@ void prof_collect(Launcher &L) {
 // Groups the (key, value) pairs in (key_a, val_a)[0..n) by key, stably, skipping NO_KEY.
 // On return *sk / *sv name the buffers holding the grouped pairs; counters[CNT_M] holds their
 // number and seg[0..counters[CNT_NSEG]) the group heads.
-static cudaError_t group_by_key(Launcher &L, u32 n, u64 key_space, const u32 **sk, const u32 **sv) {
+static cudaError_t group_by_key(Launcher &L, u32 n, u64 key_space, Grouped *out) {
     Scratch &s = L.s;
     int passes = (bits_for(key_space) + 7) / 8;
     int rsb = L.num_sms * RS_BLOCKS_PER_SM;
@@ -439,7 +533,7 @@ static cudaError_t group_by_key(Launcher &L, u32 n, u64 key_space, const u32 **s
     for (int p = 0; p < passes; p++) {
         int first = p == 0;
         k_rs_hist<<<rsb, BLOCK, 0, L.stream>>>(ik, n, s.counters, first, 8 * p, H, T + 256 * p);
-        k_rs_scan<<<256, 1024, 0, L.stream>>>(H, T + 256 * p, (u32)rsb, s.counters, first);
+        k_rs_scan<<<256, 1024, 0, L.stream>>>(H, T + 256 * p, (u32)rsb, s.counters, first, 8 * p);
         k_rs_scatter<<<rsb, BLOCK, 0, L.stream>>>(ik, iv, ok, ov, n, s.counters, first, 8 * p, H);
         L.launches += 3;
         u32 *t = ik;
@@ -449,11 +543,16 @@ static cudaError_t group_by_key(Launcher &L, u32 n, u64 key_space, const u32 **s
         iv = ov;
         ov = t;
     }
-    k_heads<<<grid_for(L, n, 8), BLOCK, 0, L.stream>>>(ik, s.qslot, s.counters);
+    Grouped g;
+    g.ka = s.key_a;
+    g.va = s.val_a;
+    g.kb = s.key_b;
+    g.vb = s.val_b;
+    g.passes = passes;
+    *out = g;
+    k_heads<<<grid_for(L, n, 8), BLOCK, 0, L.stream>>>(g, s.qslot, s.counters);
     L.launches++;
     prof_end(L);
-    *sk = ik;
-    *sv = iv;
     return cudaGetLastError();
 }
 
@@ -465,22 +564,22 @@ cudaError_t run_antispoof(Launcher &L, const DevCtx &c, const DevBatch &b) {
 cudaError_t run_qos(Launcher &L, const DevCtx &c, const DevBatch &b, bool egress) {
     LAUNCH(k_qos_classify, b.n, 8, c, b, egress ? 1 : 0, L.s.key_a, L.s.val_a);
     const Tbl &t = egress ? c.qos_eg : c.qos_in;
-    const u32 *sk, *sv;
-    cudaError_t e = group_by_key(L, b.n, (u64)t.mask + 1, &sk, &sv);
+    Grouped g;
+    cudaError_t e = group_by_key(L, b.n, (u64)t.mask + 1, &g);
     if (e != cudaSuccess) return e;
     if (egress)
-        LAUNCH((k_resolve<false, true, true>), b.n, 4, c, b, sk, sv, L.s.qslot, L.s.counters);
+        LAUNCH((k_resolve<false, true, true>), b.n, 4, c, b, g, L.s.qslot, L.s.counters);
     else
-        LAUNCH((k_resolve<false, true, false>), b.n, 4, c, b, sk, sv, L.s.qslot, L.s.counters);
+        LAUNCH((k_resolve<false, true, false>), b.n, 4, c, b, g, L.s.qslot, L.s.counters);
     return cudaGetLastError();
 }
 
 cudaError_t run_nat_egress(Launcher &L, const DevCtx &c, const DevBatch &b) {
     LAUNCH((k_pipe_classify<false, false>), b.n, 5, c, b, L.s.key_a, L.s.val_a);
-    const u32 *sk, *sv;
-    cudaError_t e = group_by_key(L, b.n, (u64)c.sub_nat.mask + 1, &sk, &sv);
+    Grouped g;
+    cudaError_t e = group_by_key(L, b.n, (u64)c.sub_nat.mask + 1, &g);
     if (e != cudaSuccess) return e;
-    LAUNCH((k_resolve<true, false, false>), b.n, 4, c, b, sk, sv, L.s.qslot, L.s.counters);
+    LAUNCH((k_resolve<true, false, false>), b.n, 8, c, b, g, L.s.qslot, L.s.counters);
     return cudaGetLastError();
 }
 
@@ -497,9 +596,9 @@ cudaError_t run_nat_hairpin_xdp(Launcher &L, const DevCtx &c, const DevBatch &b)
 cudaError_t run_pipeline_up(Launcher &L, const DevCtx &c, const DevBatch &b) {
     LAUNCH((k_pipe_classify<true, true>), b.n, 5, c, b, L.s.key_a, L.s.val_a);
     u64 space = (u64)(c.qos_in.mask + 1) + (c.sub_nat.mask + 1);
-    const u32 *sk, *sv;
-    cudaError_t e = group_by_key(L, b.n, space, &sk, &sv);
+    Grouped g;
+    cudaError_t e = group_by_key(L, b.n, space, &g);
     if (e != cudaSuccess) return e;
-    LAUNCH((k_resolve<true, true, false>), b.n, 4, c, b, sk, sv, L.s.qslot, L.s.counters);
+    LAUNCH((k_resolve<true, true, false>), b.n, 8, c, b, g, L.s.qslot, L.s.counters);
     return cudaGetLastError();
 }

@@ -194,10 +194,24 @@ __device__ __forceinline__ bool is_private_ip(u32 ip_le) { // bpf/nat44.c:340-36
     return false;
 }
 
+// Batched accounting of the ordered NAT phase (one per lane, reduced per warp by k_resolve):
+// live-entry deltas of the three flow tables, and the log record reserved for this frame.
+struct NatPend {
+    u32 ses, rev, eim; // inserts not yet added to the tables' counts
+    u8 *log_rec;       // staged nat_log_rb record reserved for this frame (nullptr: ring full)
+    bool logged;
+};
+
 __device__ __forceinline__ void nat_log(const DevCtx &c, u32 idx, u64 now, u32 type, u32 sub_id, u32 priv_ip,
                                         u32 pub_ip, u16 priv_port, u16 pub_port, u32 dst_ip, u16 dst_port, u8 proto,
-                                        u8 flags) { // log_nat_event(), :531-562
-    u8 *r = ev_reserve(c, c.natlog_ev, idx);
+                                        u8 flags, NatPend *pd = nullptr) { // log_nat_event(), :531-562
+    u8 *r;
+    if (pd) { // the resolve kernel reserved the record up front (one atomic per 32 frames)
+        r = pd->log_rec;
+        pd->logged = true;
+    } else {
+        r = ev_reserve(c, c.natlog_ev, idx);
+    }
     if (!r) return;
     ((u64 *)r)[0] = now;
     ((u32 *)r)[2] = type;
@@ -272,7 +286,8 @@ struct NatOut {
 //     subscriber's worker in frame-index order; counters that classify
 //     already bumped for this frame (hairpin) are not bumped again.
 template <bool RESOLVE>
-__device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs, u8 *p, u32 len, u32 idx, u64 now) {
+__device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs, u8 *p, u32 len, u32 idx, u64 now,
+                                                 NatPend *pd = nullptr) {
     NatOut o;
     o.verdict = TC_OK;
     o.order_key = NO_KEY;
@@ -357,7 +372,7 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
                     bstats_add(bs, ST_NAT_EXHAUST, 1);
                 } else {
                     bool created;
-                    m = tbl_find_or_claim<1>(c.eim, &ek, &created);
+                    m = tbl_find_or_claim<1>(c.eim, &ek, &created, pd ? &pd->eim : nullptr);
                     if (m && created) {
                         *(u32 *)(m + 8) = pub_ip;
                         *(u32 *)(m + 12) = ext; // external_port (host order) + zero pad
@@ -386,7 +401,7 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
             if (ap == 0) {
                 bstats_add(bs, ST_NAT_EXHAUST, 1);
                 bstats_add(bs, ST_NAT_DROPPED, 1);
-                nat_log(c, idx, now, 5, sub_id, saddr, pub_ip, sport, 0, daddr, dport, (u8)proto, 0);
+                nat_log(c, idx, now, 5, sub_id, saddr, pub_ip, sport, 0, daddr, dport, (u8)proto, 0, pd);
                 o.verdict = TC_SHOT;
                 return o;
             }
@@ -394,7 +409,7 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
             nat_port = bswap16(ap);
         }
         bool created;
-        u8 *ns = tbl_find_or_claim<2>(c.sessions, key, &created); // BPF_ANY (:730)
+        u8 *ns = tbl_find_or_claim<2>(c.sessions, key, &created, pd ? &pd->ses : nullptr); // BPF_ANY (:730)
         if (ns) {
             *(u32 *)(ns + SES_NAT_IP) = nat_ip;
             *(u32 *)(ns + SES_NAT_PORT) = (u32)nat_port | ((u32)sport << 16); // nat_port, orig_port
@@ -416,7 +431,7 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
         u64 rk[2];
         rk[0] = (u64)daddr | ((u64)nat_ip << 32);
         rk[1] = (u64)dport | ((u64)nat_port << 16) | ((u64)proto << 32);
-        u8 *rs = tbl_find_or_claim<2>(c.reverse, rk, &created); // BPF_ANY (:740)
+        u8 *rs = tbl_find_or_claim<2>(c.reverse, rk, &created, pd ? &pd->rev : nullptr); // BPF_ANY (:740)
         if (rs) {
             *(u64 *)(rs + 16) = key[0];
             *(u64 *)(rs + 24) = key[1];
@@ -427,7 +442,7 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
         atomicAdd((u64 *)(sub + 40), 1ull);
         atomicAdd((u64 *)(sub + 48), 1ull);
         bstats_add(bs, ST_NAT_CREATED, 1);
-        nat_log(c, idx, now, 1, sub_id, saddr, nat_ip, sport, nat_port, daddr, dport, (u8)proto, is_hairpin);
+        nat_log(c, idx, now, 1, sub_id, saddr, nat_ip, sport, nat_port, daddr, dport, (u8)proto, is_hairpin, pd);
     }
     nat_snat_rewrite(p, l4, proto, saddr, nat_ip, nat_port);
     bstats_add(bs, ST_NAT_SNAT, 1);
