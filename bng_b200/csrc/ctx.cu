@@ -764,7 +764,7 @@ static u32 zc_chunk_frames() { // frames per pipeline chunk; BNG_ZC_CHUNK_LOG2 o
 }
 #define ZC_CHUNK (zc_chunk_frames())
 static int run_host_zero_copy(bng_ctx *c, int prog, bng_batch *bb, u8 *arena_dev) {
-    const u32 hb = prog == P_DHCP ? 448u : 64u;
+    const u32 hb = prog == P_DHCP ? 448u : 64u; // bytes of a frame a program can touch
     const u32 first_chunk = prog == P_DHCP ? 0u : 1u; // TC programs never write the Ethernet addresses
     if (!c->s_in) {
         CU(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));

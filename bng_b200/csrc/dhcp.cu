@@ -278,7 +278,10 @@ __device__ __forceinline__ int dhcp_one(const DevCtx &c, BlockStats &bs, u8 *p, 
 // mbarrier), runs the program on the shared-memory copy, and bulk-stores it back.  HBM sees two
 // streaming passes per frame instead of scattered 1-16 byte accesses.
 #define DH_TILE 128
-#define DH_SLOT 448 // bytes staged per frame: covers the longest reply (22 + 60 + 8 + 240 + 64 options)
+// Bytes staged per frame, also the slot stride in shared memory.  400 = 16 x 25: a multiple of 16 (bulk
+// copies) whose word stride (100) spreads same-offset accesses of the 32 lanes over 8 banks; 384 or 448
+// would put them on 1 or 2.  Frames whose options end beyond it (QinQ + IPv4 options) run in place.
+#define DH_SLOT 400
 
 __global__ void __launch_bounds__(DH_TILE) k_dhcp_fastpath(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b) {
     extern __shared__ __align__(128) u8 stage[]; // DH_TILE * DH_SLOT
@@ -322,12 +325,22 @@ __global__ void __launch_bounds__(DH_TILE) k_dhcp_fastpath(const __grid_constant
         }
         phase ^= 1;
         // ---- the program, on the staged copy ----
+        bool direct = false; // the program would reach past the staged bytes: run it on the frame itself
+        if (act && len > DH_SLOT) {
+            u32 et = rd16(mine, 12), l3 = 14;
+            if (et == 0x0081u || et == 0xA888u) {
+                l3 = 18;
+                if (rd16(mine, 16) == 0x0081u) l3 = 22;
+            }
+            direct = l3 + (u32)(mine[l3] & 0x0f) * 4 + 8 + 240 + 64 > DH_SLOT;
+        }
         if (act) {
             const u32 l0 = len;
-            int v = dhcp_one(c, bs, mine, len, b.now);
+            int v = dhcp_one(c, bs, direct ? g : mine, len, b.now);
             b.verdict[i] = (u8)v;
             if (len != l0) b.len[i] = len;
         }
+        if (direct) nbytes = 0;
         // ---- stage out (every staged frame: a passed frame may have been rewritten, :769) ----
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (nbytes) {
@@ -349,7 +362,7 @@ cudaError_t run_dhcp_fastpath(Launcher &L, const DevCtx &c, const DevBatch &b) {
         attr_set = true;
     }
     long want = ((long)b.n + DH_TILE - 1) / DH_TILE;
-    long cap = (long)L.num_sms * 3; // 3 x 56 KB of staging per SM
+    long cap = (long)L.num_sms * 4; // 4 x 50 KB of staging per SM
     int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
     prof_begin(L, "k_dhcp_fastpath");
     k_dhcp_fastpath<<<grid, DH_TILE, smem, L.stream>>>(c, b);
