@@ -73,9 +73,12 @@ enum {
     SES_NAT_IP = 16,    // u32
     SES_NAT_PORT = 20,  // u16
     SES_ORIG_PORT = 22, // u16
-    SES_ORIG_IP = 24,   // u32
-    SES_STATE = 28,     // u8 state, protocol@29, flags@30, is_hairpin@31
-    SES_LAST_SEEN = 32, // u64
+    // last_seen shares the 32-byte sector of the key and the translation: a hit reads it for free and
+    // stores it only when it differs from this batch's now (a plain store next to the counters' atomics
+    // cost 40 % of the classify kernel: profiles/r01_results.md)
+    SES_LAST_SEEN = 24, // u64
+    SES_ORIG_IP = 32,   // u32
+    SES_STATE = 36,     // u8 state, protocol@37, flags@38, is_hairpin@39
     SES_PKTS_OUT = 40,
     SES_BYTES_OUT = 48,
     SES_PKTS_IN = 56,
@@ -102,6 +105,13 @@ __host__ __device__ __forceinline__ u32 ses_abi_to_slot(u32 a) {
     if (a < 76) return SES_STATE + (a - 72);
     return 92 + (a - 76);
 }
+#ifdef __CUDACC__
+// session->last_seen = now.  Every frame of a batch stores the same value, so only the first frame of a
+// flow needs to; a stale read merely repeats the store.
+__device__ __forceinline__ void ses_touch(u8 *ses, u64 now) {
+    if (*(const volatile u64 *)(ses + SES_LAST_SEEN) != now) *(u64 *)(ses + SES_LAST_SEEN) = now;
+}
+#endif
 
 struct LpmTbl { // BPF_MAP_TYPE_LPM_TRIE with a 4-byte address: {prefixlen, addr bytes, value}
     u32 *ents;  // 3 x u32 per entry: prefixlen, addr (memory order), value
@@ -453,6 +463,37 @@ __device__ __forceinline__ void hdr_load(Hdr64 &h, const u8 *p, u32 len) {
 }
 __device__ __forceinline__ void hdr_store_chunk(const Hdr64 &h, u8 *p, int c) {
     *(uint4 *)(p + c * 16) = make_uint4(h.w[4 * c], h.w[4 * c + 1], h.w[4 * c + 2], h.w[4 * c + 3]);
+}
+
+// Frame bytes stream through L2 exactly once per batch; tagging them evict_first leaves more of the
+// 126 MB L2 to the flow table, whose lines are re-used several times per batch.
+__device__ __forceinline__ u64 l2_policy_evict_first() {
+    u64 p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint4 ldg128_stream(const void *p, u64 pol) {
+    uint4 v;
+    asm("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void stg128_stream(void *p, uint4 v, u64 pol) {
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void hdr_load_stream(Hdr64 &h, const u8 *p, u32 len, u64 pol) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if ((u32)c * 16 < len) v = ldg128_stream(p + c * 16, pol);
+        h.w[4 * c + 0] = v.x;
+        h.w[4 * c + 1] = v.y;
+        h.w[4 * c + 2] = v.z;
+        h.w[4 * c + 3] = v.w;
+    }
+}
+__device__ __forceinline__ void hdr_store_chunk_stream(const Hdr64 &h, u8 *p, int c, u64 pol) {
+    stg128_stream(p + c * 16, make_uint4(h.w[4 * c], h.w[4 * c + 1], h.w[4 * c + 2], h.w[4 * c + 3]), pol);
 }
 
 // MAC bytes [off, off+6) as the reference's big-endian u64 key

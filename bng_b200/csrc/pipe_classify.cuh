@@ -28,6 +28,9 @@ __global__ void __launch_bounds__(BLOCK, 5)
     const u32 as_cfg = st.as_cfg, nflags = st.nat_flags;
     const u32 lane = threadIdx.x & 31;
     u32 n_allowed = 0, n_snat = 0;
+#if BNG_L2_STREAM
+    const u64 pol = l2_policy_evict_first();
+#endif
     // warp-uniform trip count: every lane stays in the loop, inactive lanes are predicated off
     for (u32 base = blockIdx.x * BLOCK + (threadIdx.x & ~31u); base < b.n; base += gridDim.x * BLOCK) {
         const u32 i = base + lane;
@@ -35,7 +38,11 @@ __global__ void __launch_bounds__(BLOCK, 5)
         const u32 len = act ? b.len[i] : 0;
         u8 *p = act ? frame_ptr(b, i) : b.pkts;
         Hdr64 h;
+#if BNG_L2_STREAM
+        hdr_load_stream(h, p, len, pol);
+#else
         hdr_load(h, p, len);
+#endif
 
         // ---- phase 1: keys, and the first probe of every table this frame may need ----
         const bool ip4 = len >= 34 && h.b16(12) == ETH_P_IP_LE;
@@ -105,11 +112,17 @@ __global__ void __launch_bounds__(BLOCK, 5)
         bool miss = go && !ses;
         u32 sub_idx = miss ? (u32)((sub - c.sub_nat.slots) / c.sub_nat.slot_bytes) : 0;
         if (ses) {
-            const u32 nat_ip = *(const u32 *)(ses + SES_NAT_IP);
-            const u16 nat_port = *(const u16 *)(ses + SES_NAT_PORT);
-            *(u64 *)(ses + SES_LAST_SEEN) = b.now;
+            // one 16-byte load in the key's own sector: nat_ip, nat_port|orig_port, last_seen
+            const uint4 tr = *(const uint4 *)(ses + SES_NAT_IP);
+            const u32 nat_ip = tr.x;
+            const u16 nat_port = (u16)tr.y;
+            if (((u64)tr.z | ((u64)tr.w << 32)) != b.now) *(u64 *)(ses + SES_LAST_SEEN) = b.now;
+#if BNG_EXP != 2
             atomicAdd((u64 *)(ses + SES_PKTS_OUT), 1ull);
+#endif
+#if BNG_EXP != 1 && BNG_EXP != 2
             atomicAdd((u64 *)(ses + SES_BYTES_OUT), (u64)len);
+#endif
             h.s32(26, nat_ip);
             h.s16(24, csum_upd32(h.b16(24), saddr, nat_ip));
             if (proto == 6) {
@@ -129,9 +142,15 @@ __global__ void __launch_bounds__(BLOCK, 5)
                 h.s16(38, nat_port);
                 h.s16(36, csum_upd16(h.b16(36), sport, nat_port));
             }
+#if BNG_L2_STREAM
+            hdr_store_chunk_stream(h, p, 1, pol);
+            hdr_store_chunk_stream(h, p, 2, pol);
+            if (proto == 6) hdr_store_chunk_stream(h, p, 3, pol);
+#else
             hdr_store_chunk(h, p, 1);
             hdr_store_chunk(h, p, 2);
             if (proto == 6) hdr_store_chunk(h, p, 3);
+#endif
             n_snat++;
         }
         __syncwarp();

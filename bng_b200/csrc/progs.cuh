@@ -348,7 +348,7 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
     if (ses) { // :674-680
         nat_ip = *(const u32 *)(ses + SES_NAT_IP);
         nat_port = *(const u16 *)(ses + SES_NAT_PORT);
-        *(u64 *)(ses + SES_LAST_SEEN) = now;
+        ses_touch(ses, now);
         atomicAdd((u64 *)(ses + SES_PKTS_OUT), 1ull);
         atomicAdd((u64 *)(ses + SES_BYTES_OUT), (u64)len);
     } else {
@@ -497,7 +497,7 @@ __device__ __forceinline__ int nat_ingress_one(const DevCtx &c, BlockStats &bs, 
             bstats_add(bs, ST_NAT_PASSED, 1);
         return TC_OK;
     }
-    *(u64 *)(ses + SES_LAST_SEEN) = now;
+    ses_touch(ses, now);
     atomicAdd((u64 *)(ses + SES_PKTS_IN), 1ull);
     atomicAdd((u64 *)(ses + SES_BYTES_IN), (u64)len);
     if (proto == 6) { // :885-895; CLOSING(3) is absorbing, NEW(0)->ESTABLISHED(1) on ack

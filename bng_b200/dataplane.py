@@ -15,7 +15,7 @@ import numpy as np
 from .layouts import as_bytes
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbng_b200.so")
+LIB_PATH = os.environ.get("BNG_B200_LIB") or os.path.join(HERE, "libbng_b200.so")  # override: A/B builds
 
 MEM_DEVICE, MEM_HOST = 0, 1
 ANY, NOEXIST, EXIST = 0, 1, 2

@@ -9,6 +9,7 @@ collective is needed.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -210,9 +211,11 @@ def dhcp(n: int, rank=0, world=1, n_subs=1 << 20, seed=0xB2000005, frame_len=362
     return w
 
 
+_FPS = int(os.environ.get("BNG_FLOWS_PER_SUB", "64"))  # experiment knob: flow-table footprint vs L2 size
+
 BUILDERS = {
-    "pipeline_imix": lambda n, r, wd: pipeline(n, r, wd, imix=True),
-    "pipeline_64": lambda n, r, wd: pipeline(n, r, wd, imix=False),
+    "pipeline_imix": lambda n, r, wd: pipeline(n, r, wd, flows_per_sub=_FPS, imix=True),
+    "pipeline_64": lambda n, r, wd: pipeline(n, r, wd, flows_per_sub=_FPS, imix=False),
     "antispoof_64": antispoof,
     "nat_steady_64": lambda n, r, wd: nat(n, r, wd, cold=False),
     "nat_cold_64": lambda n, r, wd: nat(n, r, wd, cold=True),
