@@ -244,6 +244,9 @@ def run_gpu(a):
             a16[gidx.reshape(-1)] = hdr_d.view(-1, 16)
         len_d.copy_(len0_d)
         torch.cuda.synchronize()
+        reset_state()
+
+    def reset_state():
         for ring in ("spoof_events", "nat_log_rb"):  # the event consumer keeps the staging rings empty (untimed)
             dp.drain(ring)
         if wl.name == "nat_cold_64":  # every step starts from empty flow tables and fresh port blocks
@@ -350,6 +353,8 @@ def run_gpu(a):
         tot = 0.0
         for s in range(1 + e2e_steps):
             restore_fn()
+            reset_state()
+            dp.sync()
             if world > 1:
                 dist.barrier()
             t0 = time.perf_counter()

@@ -79,10 +79,13 @@ enum {
     SES_LAST_SEEN = 24, // u64
     SES_ORIG_IP = 32,   // u32
     SES_STATE = 36,     // u8 state, protocol@37, flags@38, is_hairpin@39
-    SES_PKTS_OUT = 40,
-    SES_BYTES_OUT = 48,
-    SES_PKTS_IN = 56,
-    SES_BYTES_IN = 64,
+    // The two counters of a direction advance with ONE 64-bit atomic: the low words of packets and
+    // bytes share a u64 (packets in bits 0-31, bytes in bits 32-63), their high words a second u64 that
+    // is touched only when a low word wraps (ses_count()).
+    SES_OUT_LO = 40, // u64: packets_out[31:0] | bytes_out[31:0] << 32
+    SES_OUT_HI = 48, // u64: packets_out[63:32] | bytes_out[63:32] << 32
+    SES_IN_LO = 56,
+    SES_IN_HI = 64,
     SES_CREATED = 72,
     SES_DEST_IP = 80,   // u32
     SES_DEST_PORT = 84, // u16, _pad1@86, implicit padding@88, tail padding@92
@@ -98,10 +101,14 @@ __host__ __device__ __forceinline__ u32 ses_abi_to_slot(u32 a) {
     if (a < 24) return 88 + (a - 20);
     if (a < 32) return SES_LAST_SEEN + (a - 24);
     if (a < 40) return SES_CREATED + (a - 32);
-    if (a < 48) return SES_PKTS_OUT + (a - 40);
-    if (a < 56) return SES_PKTS_IN + (a - 48);
-    if (a < 64) return SES_BYTES_OUT + (a - 56);
-    if (a < 72) return SES_BYTES_IN + (a - 64);
+    if (a < 44) return SES_OUT_LO + (a - 40); // packets_out
+    if (a < 48) return SES_OUT_HI + (a - 44);
+    if (a < 52) return SES_IN_LO + (a - 48); // packets_in
+    if (a < 56) return SES_IN_HI + (a - 52);
+    if (a < 60) return SES_OUT_LO + 4 + (a - 56); // bytes_out
+    if (a < 64) return SES_OUT_HI + 4 + (a - 60);
+    if (a < 68) return SES_IN_LO + 4 + (a - 64); // bytes_in
+    if (a < 72) return SES_IN_HI + 4 + (a - 68);
     if (a < 76) return SES_STATE + (a - 72);
     return 92 + (a - 76);
 }
@@ -110,6 +117,25 @@ __host__ __device__ __forceinline__ u32 ses_abi_to_slot(u32 a) {
 // flow needs to; a stale read merely repeats the store.
 __device__ __forceinline__ void ses_touch(u8 *ses, u64 now) {
     if (*(const volatile u64 *)(ses + SES_LAST_SEEN) != now) *(u64 *)(ses + SES_LAST_SEEN) = now;
+}
+// Rare half of ses_count(): a low word wrapped.  c: the packet word carried into the byte word (undo
+// it there, count it in the high packet word); w: the byte word wrapped upwards.
+static __device__ __noinline__ void ses_count_carry(u8 *ses, u32 lo_off, u32 c, u32 w) {
+    u64 add = w ? (1ull << 32) : 0;
+    if (c) {
+        add += 1;
+        u64 old = atomicAdd((unsigned long long *)(ses + lo_off), 0xFFFFFFFF00000000ull); // byte word -= 1
+        if ((old >> 32) == 0) add -= 1ull << 32;                                         // ... which wrapped downwards
+    }
+    if (add) atomicAdd((unsigned long long *)(ses + lo_off + 8), add);
+}
+// packets += 1, bytes += len on the counter pair at lo_off (SES_OUT_LO / SES_IN_LO): exact u64
+// arithmetic, every wrap of a low word is seen by exactly one caller through the value the atomic returns.
+__device__ __forceinline__ void ses_count(u8 *ses, u32 lo_off, u32 len) {
+    const u64 old = atomicAdd((unsigned long long *)(ses + lo_off), 1ull | ((u64)len << 32));
+    const u32 c = (u32)old == 0xFFFFFFFFu;
+    const u32 w = (u32)(((old >> 32) + len + c) >> 32);
+    if (c | w) ses_count_carry(ses, lo_off, c, w);
 }
 #endif
 

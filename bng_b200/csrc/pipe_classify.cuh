@@ -117,12 +117,7 @@ __global__ void __launch_bounds__(BLOCK, 5)
             const u32 nat_ip = tr.x;
             const u16 nat_port = (u16)tr.y;
             if (((u64)tr.z | ((u64)tr.w << 32)) != b.now) *(u64 *)(ses + SES_LAST_SEEN) = b.now;
-#if BNG_EXP != 2
-            atomicAdd((u64 *)(ses + SES_PKTS_OUT), 1ull);
-#endif
-#if BNG_EXP != 1 && BNG_EXP != 2
-            atomicAdd((u64 *)(ses + SES_BYTES_OUT), (u64)len);
-#endif
+            ses_count(ses, SES_OUT_LO, len);
             h.s32(26, nat_ip);
             h.s16(24, csum_upd32(h.b16(24), saddr, nat_ip));
             if (proto == 6) {

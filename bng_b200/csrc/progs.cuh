@@ -349,8 +349,7 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
         nat_ip = *(const u32 *)(ses + SES_NAT_IP);
         nat_port = *(const u16 *)(ses + SES_NAT_PORT);
         ses_touch(ses, now);
-        atomicAdd((u64 *)(ses + SES_PKTS_OUT), 1ull);
-        atomicAdd((u64 *)(ses + SES_BYTES_OUT), (u64)len);
+        ses_count(ses, SES_OUT_LO, len);
     } else {
         if (!RESOLVE) {
             o.order_key = (u32)((sub - c.sub_nat.slots) / c.sub_nat.slot_bytes);
@@ -416,10 +415,10 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
             *(u32 *)(ns + SES_ORIG_IP) = saddr;
             *(u32 *)(ns + SES_STATE) = (proto << 8) | ((u32)is_hairpin << 24); // state NEW, protocol, flags 0, hairpin
             *(u64 *)(ns + SES_LAST_SEEN) = now;
-            *(u64 *)(ns + SES_PKTS_OUT) = 1;
-            *(u64 *)(ns + SES_BYTES_OUT) = (u64)len;
-            *(u64 *)(ns + SES_PKTS_IN) = 0;
-            *(u64 *)(ns + SES_BYTES_IN) = 0;
+            *(u64 *)(ns + SES_OUT_LO) = 1ull | ((u64)len << 32); // packets_out = 1, bytes_out = len
+            *(u64 *)(ns + SES_OUT_HI) = 0;
+            *(u64 *)(ns + SES_IN_LO) = 0;
+            *(u64 *)(ns + SES_IN_HI) = 0;
             *(u64 *)(ns + SES_CREATED) = now;
             *(u32 *)(ns + SES_DEST_IP) = daddr;
             *(u32 *)(ns + SES_DEST_PORT) = (u32)dport; // dest_port, _pad1 = 0
@@ -498,8 +497,7 @@ __device__ __forceinline__ int nat_ingress_one(const DevCtx &c, BlockStats &bs, 
         return TC_OK;
     }
     ses_touch(ses, now);
-    atomicAdd((u64 *)(ses + SES_PKTS_IN), 1ull);
-    atomicAdd((u64 *)(ses + SES_BYTES_IN), (u64)len);
+    ses_count(ses, SES_IN_LO, len);
     if (proto == 6) { // :885-895; CLOSING(3) is absorbing, NEW(0)->ESTABLISHED(1) on ack
         u32 tf = p[l4 + 13];
         bool finrst = (tf & 0x05) != 0, ack = (tf & 0x10) != 0;

@@ -318,6 +318,58 @@ def nat_exhaust_script(flags=0x0F, name="nat_exhaust") -> Script:
     return sc
 
 
+def nat_wrap_script() -> Script:
+    """Long-lived sessions whose 64-bit packet / byte counters are about to cross 2^32 (and 2^33):
+    struct nat_session counters are plain __u64 in the reference (bpf/nat44.c:131-136); a dataplane
+    that keeps the low words apart from the high words has to carry exactly."""
+    sc = Script("nat_wrap")
+    n_subs, per = 4, 3
+    pubs = nat_maps(sc, n_subs, 64, 0x0F)
+    sub = np.repeat(np.arange(n_subs), per)
+    nf = len(sub)
+    sport = (40000 + np.arange(nf)).astype(np.uint32)
+    nport = (1024 + 64 * sub + np.tile(np.arange(per), n_subs)).astype(np.uint32)
+    proto = np.where(np.arange(nf) % 3 == 2, 17, 6).astype(np.uint32)
+    dst = np.full(nf, 0x08080808, np.uint32)
+    k = np.zeros(nf, L.nat_key)
+    k["src_ip"], k["dst_ip"] = S.ip_bytes(S.sub_ip(sub)), S.ip_bytes(dst)
+    k["src_port"], k["dst_port"] = S.port_bytes(sport), S.port_bytes(np.full(nf, 443))
+    k["protocol"] = proto
+    v = np.zeros(nf, L.nat_session)
+    v["nat_ip"], v["nat_port"] = S.ip_bytes(np.full(nf, pubs[0], np.uint32)), S.port_bytes(nport)
+    v["orig_ip"], v["orig_port"] = k["src_ip"], k["src_port"]
+    v["dest_ip"], v["dest_port"] = k["dst_ip"], k["dst_port"]
+    v["protocol"], v["state"] = proto, 1
+    v["created"] = v["last_seen"] = 10**9
+    M = 1 << 32
+    # per flow: (packets, bytes) start values for both directions; 64-byte frames, 20 / 9 hits per flow
+    starts = [(M - 1, M - 65), (M - 1, M - 64), (M - 4, (1 << 33) - 300), (2 * M - 20, M - 1), (M - 1, 0), (M - 1, M - 1),
+              (M - 19, 3 * M - 64 * 20), (5, 7 * M - 1), (M - 2, M - 129), (0, 0), ((1 << 40) - 1, (1 << 48) - 1), (M - 20, M - 1280)]
+    for d in ("out", "in"):
+        v[f"packets_{d}"] = [s[0] for s in starts]
+        v[f"bytes_{d}"] = [s[1] for s in starts]
+    sc.update("nat_sessions", k, v)
+    rk = np.zeros(nf, L.nat_key)
+    rk["src_ip"], rk["dst_ip"] = k["dst_ip"], v["nat_ip"]
+    rk["src_port"], rk["dst_port"] = k["dst_port"], v["nat_port"]
+    rk["protocol"] = proto
+    sc.update("nat_reverse", rk, k)
+    lens1 = np.full(nf, 64, np.uint32)
+    eg1 = S.ipv4_headers(S.sub_mac_key(sub), np.uint64(GW_MAC), S.sub_ip(sub), dst, proto, sport, 443, lens1, l4_check=0x2222,
+                         tcp_flags=0x10)
+    in1 = S.ipv4_headers(np.uint64(GW_MAC), S.sub_mac_key(sub), dst, np.full(nf, pubs[0], np.uint32), proto, 443, nport, lens1,
+                         l4_check=0x3333, tcp_flags=0x10)
+    sc.run("nat44_egress", fixed(eg1), lens1, 2 * 10**9)  # one frame per flow: the single-step carries
+    sc.run("nat44_ingress", fixed(in1), lens1, 2 * 10**9)
+    rep = np.tile(np.arange(nf), 19)
+    lens = np.full(len(rep), 64, np.uint32)
+    sc.run("nat44_egress", fixed(eg1[rep]), lens, 3 * 10**9)
+    sc.run("nat44_ingress", fixed(in1[rep[: nf * 8]]), lens[: nf * 8], 3 * 10**9)
+    for i in range(nf):
+        sc.lookup("nat_sessions", k[i])
+    return sc
+
+
 # ---------------------------------------------------------------------------
 # dhcp_fastpath_prog
 # ---------------------------------------------------------------------------
@@ -485,6 +537,7 @@ ALL_SCRIPTS = {
     "nat_noeim": lambda: nat_script(seed=0x46, flags=0x0E, name="nat_noeim"),
     "nat_sip": lambda: nat_script(seed=0x47, flags=0x1D, pps=32, name="nat_sip"),
     "nat_stale": nat_stale_script,
+    "nat_wrap": nat_wrap_script,
     "nat_exhaust": nat_exhaust_script,
     "nat_exhaust_parity": lambda: nat_exhaust_script(flags=0x2F, name="nat_exhaust_parity"),
     "nat_exhaust_noeim": lambda: nat_exhaust_script(flags=0x2E, name="nat_exhaust_noeim"),
