@@ -69,6 +69,8 @@ struct Tbl {
 // layout of struct nat_session (bpf/nat44.c:123-141) is restored by
 // ses_abi_to_slot() whenever a value crosses the ABI.
 #define VL_SESSION 1u
+#define VL_QOS 2u         // value verbatim at voff, plus a copy of rate_bps at QOS_RATE_COPY
+#define QOS_RATE_COPY 8u  // qos slot: key u64 @0, rate_bps copy @8, struct token_bucket @16
 enum {
     SES_NAT_IP = 16,    // u32
     SES_NAT_PORT = 20,  // u16
@@ -215,7 +217,10 @@ struct DevBatch {
     u64 now;
     u32 base; // index of frame 0 within the caller's batch (event records carry base + i)
     u32 pad;
+    u64 arena_len; // bytes addressable from pkts (0 = unknown: no access may run past a frame's 16-byte chunks)
 };
+// may the 64 bytes at p be read with 32-byte accesses?
+#define FRAME_WIDE_OK(b, p) ((((uintptr_t)(p)) & 31) == 0 && (u64)((p) - (b).pkts) + 64 <= (b).arena_len)
 
 // ---------------------------------------------------------------------------
 // small helpers
@@ -491,35 +496,42 @@ __device__ __forceinline__ void hdr_store_chunk(const Hdr64 &h, u8 *p, int c) {
     *(uint4 *)(p + c * 16) = make_uint4(h.w[4 * c], h.w[4 * c + 1], h.w[4 * c + 2], h.w[4 * c + 3]);
 }
 
-// Frame bytes stream through L2 exactly once per batch; tagging them evict_first leaves more of the
-// 126 MB L2 to the flow table, whose lines are re-used several times per batch.
-__device__ __forceinline__ u64 l2_policy_evict_first() {
-    u64 p;
-    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256).  One instruction moves a whole 32-byte sector per
+// lane; the per-frame kernels are bound by the number of divergent memory instructions they issue
+// (l1tex wavefronts), so a sector is never fetched piecemeal.  p must be 32-byte aligned.
+struct __align__(16) U256 {
+    u32 w[8];
+};
+__device__ __forceinline__ U256 ldg256(const void *p) {
+    U256 r;
+    asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+                 : "l"(p)
+                 : "memory");
+    return r;
 }
-__device__ __forceinline__ uint4 ldg128_stream(const void *p, u64 pol) {
-    uint4 v;
-    asm("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ void stg128_stream(void *p, uint4 v, u64 pol) {
-    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
+__device__ __forceinline__ void stg256(void *p, const u32 *w) {
+    asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
+                 "r"(w[5]), "r"(w[6]), "r"(w[7])
                  : "memory");
 }
-__device__ __forceinline__ void hdr_load_stream(Hdr64 &h, const u8 *p, u32 len, u64 pol) {
+// Frame header load: two 256-bit loads when the whole warp's frames allow it (32-byte aligned and 64
+// bytes inside the arena), 16-byte chunks otherwise.  `wide` must be warp-uniform.
+__device__ __forceinline__ void hdr_load_wide(Hdr64 &h, const u8 *p, u32 len, bool wide) {
+    if (wide) {
+        U256 a, b;
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if ((u32)c * 16 < len) v = ldg128_stream(p + c * 16, pol);
-        h.w[4 * c + 0] = v.x;
-        h.w[4 * c + 1] = v.y;
-        h.w[4 * c + 2] = v.z;
-        h.w[4 * c + 3] = v.w;
+        for (int k = 0; k < 8; k++) a.w[k] = b.w[k] = 0;
+        if (len > 0) a = ldg256(p);
+        if (len > 32) b = ldg256(p + 32);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            h.w[k] = a.w[k];
+            h.w[8 + k] = b.w[k];
+        }
+    } else {
+        hdr_load(h, p, len);
     }
-}
-__device__ __forceinline__ void hdr_store_chunk_stream(const Hdr64 &h, u8 *p, int c, u64 pol) {
-    stg128_stream(p + c * 16, make_uint4(h.w[4 * c], h.w[4 * c + 1], h.w[4 * c + 2], h.w[4 * c + 3]), pol);
 }
 
 // MAC bytes [off, off+6) as the reference's big-endian u64 key

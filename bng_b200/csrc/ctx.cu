@@ -355,8 +355,8 @@ bng_ctx *bng_open(const bng_open_opts *o) {
     DevCtx &d = c->dev;
 
     OPEN_R(make_table(c, &d.bindings, 8, 24, 8, max_subs));
-    OPEN_R(make_table(c, &d.qos_eg, 4, 32, 16, max_subs));
-    OPEN_R(make_table(c, &d.qos_in, 4, 32, 16, max_subs));
+    OPEN_R(make_table(c, &d.qos_eg, 4, 32, 16, max_subs, VL_QOS));
+    OPEN_R(make_table(c, &d.qos_in, 4, 32, 16, max_subs, VL_QOS));
     OPEN_R(make_table(c, &d.sub_nat, 4, 64, 8, max_subs));
     OPEN_R(make_table(c, &d.sessions, 16, 80, 16, max_sess, VL_SESSION, 128));
     OPEN_R(make_table(c, &d.reverse, 16, 16, 16, max_sess));
@@ -825,6 +825,7 @@ static int run_host_zero_copy(bng_ctx *c, int prog, bng_batch *bb, u8 *arena_dev
         b.stride = hb;
         b.now = bb->now_ns;
         b.base = base;
+        b.arena_len = (u64)cn * hb;
         int r = dispatch(c, prog, b);
         if (r) return r;
         CU(c, cudaEventRecord(c->ev_comp[buf], sc));
@@ -865,6 +866,9 @@ int bng_prog_run(bng_ctx *c, int prog, bng_batch *bb) {
     b.n = bb->n;
     b.stride = bb->stride;
     b.now = bb->now_ns;
+    // bytes the kernels may touch from pkts: a fixed-stride arena holds n * stride; with an offset table
+    // the caller's arena_bytes (16-byte units, possibly rounded up) says, and 0 means unknown
+    b.arena_len = bb->off16 ? (bb->arena_bytes ? (u64)bb->arena_bytes * 16 - 15 : 0) : (u64)bb->n * bb->stride;
     if (bb->mem == BNG_MEM_DEVICE) {
         b.pkts = (u8 *)bb->pkts;
         b.off16 = bb->off16;

@@ -61,10 +61,22 @@ __global__ void __launch_bounds__(BLOCK) k_antispoof(const __grid_constant__ Dev
         u32 len = b.len[i];
         const u8 *p = frame_ptr(b, i);
         Hdr64 h;
-        hdr_load(h, p, len);
+        hdr_load_wide(h, p, len, __all_sync(__activemask(), FRAME_WIDE_OK(b, p)));
         u64 mk = mac_key(h, 6);
-        const u8 *bind = len >= 14 ? tbl_find<1, false>(c.bindings, &mk) : nullptr;
-        b.verdict[i] = (u8)antispoof_eval(c, bs, h, len, i + b.base, b.now, bind, cfg, n_allowed);
+        // first probe = the whole 32-byte slot (key + binding); later probes only on a collision
+        const u8 *slot0 = tbl_slot(c.bindings, tbl_hash<1>(&mk) & c.bindings.mask);
+        BindVal bv;
+        bv.has = false;
+        if (len >= 14) {
+            bv.s = ldg256(slot0);
+            const u64 w0 = (u64)bv.s.w[0] | ((u64)bv.s.w[1] << 32);
+            if (w0 == mk) {
+                bv.has = true;
+            } else if (w0 != K_EMPTY) {
+                bv = bind_load(tbl_find<1, false>(c.bindings, &mk));
+            }
+        }
+        b.verdict[i] = (u8)antispoof_eval(c, bs, h, len, i + b.base, b.now, bv, cfg, n_allowed);
     }
     warp_stat_flush(bs, ST_AS_ALLOWED, n_allowed);
     bstats_flush(bs, c.stats);
@@ -82,7 +94,7 @@ __global__ void __launch_bounds__(BLOCK)
         u32 len = b.len[i];
         const u8 *p = frame_ptr(b, i);
         Hdr64 h;
-        hdr_load(h, p, len < 34 ? len : 34);
+        hdr_load_wide(h, p, len < 34 ? len : 34, __all_sync(__activemask(), FRAME_WIDE_OK(b, p)));
         u32 prio;
         bool prio_set;
         u32 key = qos_classify_one(c, bs, t, h, len, egress != 0, &prio, &prio_set);
@@ -159,7 +171,8 @@ __device__ __forceinline__ void rs_range(u32 total, u32 &lo, u32 &hi) {
     hi = r < total ? (u32)r : total;
 }
 
-__global__ void __launch_bounds__(BLOCK) k_rs_hist(const u32 *keys, u32 n_host, u32 *cnt, int first, int shift, u32 *H, u32 *T) {
+__global__ void __launch_bounds__(BLOCK) k_rs_hist(const u32 *keys, u32 n_host, u32 *cnt, int first, int shift, u32 *H, u32 *T,
+                                                   u32 *anyv) {
     __shared__ u32 h[256];
     __shared__ u32 smax;
     if (!rs_pass_needed(cnt, shift)) return; // every key has a zero digit here: the pass would be the identity
@@ -179,6 +192,8 @@ __global__ void __launch_bounds__(BLOCK) k_rs_hist(const u32 *keys, u32 n_host, 
     }
     __syncthreads();
     if (first) {
+        int any = __syncthreads_or(mymax != 0 || h[0] != 0); // a block of NO_KEYs only has nothing to scatter
+        if (threadIdx.x == 0) anyv[blockIdx.x] = (u32)any;
         mymax = __reduce_max_sync(0xffffffffu, mymax);
         if ((threadIdx.x & 31) == 0 && mymax) atomicMax(&smax, mymax);
         __syncthreads();
@@ -230,24 +245,36 @@ __global__ void __launch_bounds__(1024) k_rs_scan(u32 *H, const u32 *T, u32 nblo
     if (first && d == 255 && threadIdx.x == 1023) cnt[CNT_M] = s_base + wsum[31] + inc; // = number of valid keys
 }
 
-// Stable scatter of one radix pass.  A tile is RS_ROWS x 256 elements (row-major = index order);
-// ranks inside a warp come from __match_any_sync, per-(row, warp) digit counts go to shared memory
-// and thread d turns them into running offsets of digit d — three block barriers per 1024 elements.
-#define RS_ROWS 4
+// Stable scatter of one radix pass.  A tile is 8 warps x RS_ROWS x 32 elements; warp w owns the
+// contiguous elements [w * RS_ROWS * 32, (w + 1) * RS_ROWS * 32) of the tile and walks them row by row,
+// so index order is (warp, row, lane).  Ranks inside a row come from __match_any_sync, ranks across
+// the rows of a warp from a warp-private running histogram in shared memory; thread d then turns the
+// 8 per-warp totals of digit d into tile-local offsets.  The tile is reordered by digit in shared
+// memory and written out from there, so that a warp's store covers runs of consecutive addresses
+// (one run per digit) instead of 32 scattered words.
+#define RS_ROWS 8
+#define RS_TILE (RS_ROWS * BLOCK)
+#define RS_WARPS (BLOCK / 32)
 __global__ void __launch_bounds__(BLOCK) k_rs_scatter(const u32 *keys, const u32 *vals, u32 *okeys, u32 *ovals, u32 n_host,
-                                                      const u32 *cnt, int first, int shift, const u32 *H) {
-    __shared__ u32 offs[256];
-    __shared__ u32 wcnt[RS_ROWS * (BLOCK / 32)][256];
+                                                      const u32 *cnt, int first, int shift, const u32 *H, const u32 *anyv) {
+    __shared__ u16 wh[RS_WARPS][256]; // per-warp digit counts, then the warp's offset inside the digit's run
+    __shared__ u32 stage_k[RS_TILE], stage_v[RS_TILE];
+    __shared__ u32 tstart[256]; // tile-local start of digit d
+    __shared__ u32 gdelta[256]; // global position of a staged element = gdelta[digit] + its tile-local position
+    __shared__ u32 wsum[RS_WARPS];
+    __shared__ u32 tile_n;
     if (!rs_pass_needed(cnt, shift)) return;
-    offs[threadIdx.x] = H[threadIdx.x * gridDim.x + blockIdx.x];
+    if (first && !anyv[blockIdx.x]) return; // nothing but NO_KEY in this block's range
+    u32 goff = H[threadIdx.x * gridDim.x + blockIdx.x]; // thread d owns the running global offset of digit d
     u32 total = first ? n_host : cnt[CNT_M];
     u32 lo, hi;
     rs_range(total, lo, hi);
     const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const u32 toff = w * (RS_ROWS * 32) + lane; // + r * 32
     u32 nk[RS_ROWS], nv[RS_ROWS]; // next tile, fetched while the current one goes through shared memory
 #pragma unroll
     for (int r = 0; r < RS_ROWS; r++) {
-        u32 i = lo + r * BLOCK + threadIdx.x;
+        u32 i = lo + toff + r * 32;
         nk[r] = NO_KEY;
         nv[r] = 0;
         if (i < hi) {
@@ -255,14 +282,13 @@ __global__ void __launch_bounds__(BLOCK) k_rs_scatter(const u32 *keys, const u32
             nv[r] = vals[i];
         }
     }
-    for (u32 base = lo; base < hi; base += RS_ROWS * BLOCK) {
-        u32 k[RS_ROWS], v[RS_ROWS], d[RS_ROWS], rank[RS_ROWS];
+    for (u32 base = lo; base < hi; base += RS_TILE) {
+        u32 k[RS_ROWS], v[RS_ROWS], rank[RS_ROWS];
 #pragma unroll
         for (int r = 0; r < RS_ROWS; r++) {
             k[r] = nk[r];
             v[r] = nv[r];
-            d[r] = k[r] != NO_KEY ? ((k[r] >> shift) & 0xff) : (256 + lane); // invalid lanes match nobody
-            u32 i = base + RS_ROWS * BLOCK + r * BLOCK + threadIdx.x;
+            u32 i = base + RS_TILE + toff + r * 32;
             nk[r] = NO_KEY;
             nv[r] = 0;
             if (i < hi) {
@@ -271,33 +297,64 @@ __global__ void __launch_bounds__(BLOCK) k_rs_scatter(const u32 *keys, const u32
             }
         }
 #pragma unroll
-        for (int j = 0; j < RS_ROWS * (BLOCK / 32); j++) wcnt[j][threadIdx.x] = 0;
-        __syncthreads();
+        for (int j = 0; j < 256 / 32; j++) wh[w][j * 32 + lane] = 0;
+        __syncwarp();
 #pragma unroll
         for (int r = 0; r < RS_ROWS; r++) {
-            u32 peers = __match_any_sync(0xffffffffu, d[r]);
-            rank[r] = __popc(peers & ((1u << lane) - 1));
-            if (k[r] != NO_KEY && rank[r] == 0) wcnt[r * (BLOCK / 32) + w][d[r]] = __popc(peers);
+            const bool ok = k[r] != NO_KEY;
+            u32 d = ok ? ((k[r] >> shift) & 0xff) : (256 + lane); // invalid lanes match nobody
+            u32 peers = __match_any_sync(0xffffffffu, d);
+            u32 before = ok ? wh[w][d] : 0; // elements of digit d in the earlier rows of this warp
+            u32 rk = __popc(peers & ((1u << lane) - 1));
+            __syncwarp();
+            if (ok && rk == 0) wh[w][d] = (u16)(before + __popc(peers));
+            __syncwarp();
+            rank[r] = before + rk;
         }
         __syncthreads();
-        { // thread d: running offsets of digit d over the (row, warp) cells of this tile, in index order
-            u32 run = offs[threadIdx.x];
+        { // thread d: exclusive offsets of digit d over the warps; then the block-wide exclusive scan of
+          // the per-digit totals gives each digit's start inside the tile
+            u32 run = 0;
 #pragma unroll
-            for (int j = 0; j < RS_ROWS * (BLOCK / 32); j++) {
-                u32 t = wcnt[j][threadIdx.x];
-                wcnt[j][threadIdx.x] = run;
+            for (int j = 0; j < RS_WARPS; j++) {
+                u32 t = wh[j][threadIdx.x];
+                wh[j][threadIdx.x] = (u16)run;
                 run += t;
             }
-            offs[threadIdx.x] = run;
+            u32 inc = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                u32 x = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= (u32)o) inc += x;
+            }
+            if (lane == 31) wsum[w] = inc;
+            __syncthreads();
+            u32 pre = 0;
+#pragma unroll
+            for (int j = 0; j < RS_WARPS; j++) pre += j < (int)w ? wsum[j] : 0;
+            u32 ts = pre + inc - run;
+            tstart[threadIdx.x] = ts;
+            gdelta[threadIdx.x] = goff - ts;
+            goff += run;
+            if (threadIdx.x == BLOCK - 1) tile_n = ts + run;
         }
         __syncthreads();
 #pragma unroll
         for (int r = 0; r < RS_ROWS; r++) {
             if (k[r] != NO_KEY) {
-                u32 pos = wcnt[r * (BLOCK / 32) + w][d[r]] + rank[r];
-                okeys[pos] = k[r];
-                ovals[pos] = v[r];
+                u32 d = (k[r] >> shift) & 0xff;
+                u32 lp = tstart[d] + wh[w][d] + rank[r];
+                stage_k[lp] = k[r];
+                stage_v[lp] = v[r];
             }
+        }
+        __syncthreads();
+        const u32 tn = tile_n;
+        for (u32 j = threadIdx.x; j < tn; j += BLOCK) {
+            u32 kk = stage_k[j];
+            u32 g = gdelta[(kk >> shift) & 0xff] + j;
+            okeys[g] = kk;
+            ovals[g] = stage_v[j];
         }
         __syncthreads();
     }
@@ -468,7 +525,7 @@ static int bits_for(u64 max_key_exclusive) {
 
 size_t sort_temp_bytes(u32 n) { // histogram matrix: 256 digits x blocks
     (void)n;
-    return (size_t)(256 * 1024 + 4 * 256) * sizeof(u32);
+    return (size_t)(256 * 1024 + 4 * 256 + 1024) * sizeof(u32); // H, per-pass digit totals, per-block "any key" flags
 }
 
 void prof_begin(Launcher &L, const char *name) {
@@ -524,7 +581,7 @@ static cudaError_t group_by_key(Launcher &L, u32 n, u64 key_space, Grouped *out)
     int passes = (bits_for(key_space) + 7) / 8;
     int rsb = L.num_sms * RS_BLOCKS_PER_SM;
     if (rsb > 1024) rsb = 1024;
-    u32 *H = (u32 *)s.cub_tmp, *T = H + 256 * 1024;
+    u32 *H = (u32 *)s.cub_tmp, *T = H + 256 * 1024, *ANYV = T + 4 * 256;
     cudaError_t e = cudaMemsetAsync(s.counters, 0, 64, L.stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(T, 0, 4 * 256 * sizeof(u32), L.stream);
     if (e != cudaSuccess) return e;
@@ -532,9 +589,9 @@ static cudaError_t group_by_key(Launcher &L, u32 n, u64 key_space, Grouped *out)
     prof_begin(L, "group_by_key");
     for (int p = 0; p < passes; p++) {
         int first = p == 0;
-        k_rs_hist<<<rsb, BLOCK, 0, L.stream>>>(ik, n, s.counters, first, 8 * p, H, T + 256 * p);
+        k_rs_hist<<<rsb, BLOCK, 0, L.stream>>>(ik, n, s.counters, first, 8 * p, H, T + 256 * p, ANYV);
         k_rs_scan<<<256, 1024, 0, L.stream>>>(H, T + 256 * p, (u32)rsb, s.counters, first, 8 * p);
-        k_rs_scatter<<<rsb, BLOCK, 0, L.stream>>>(ik, iv, ok, ov, n, s.counters, first, 8 * p, H);
+        k_rs_scatter<<<rsb, BLOCK, 0, L.stream>>>(ik, iv, ok, ov, n, s.counters, first, 8 * p, H, ANYV);
         L.launches += 3;
         u32 *t = ik;
         ik = ok;
@@ -575,7 +632,7 @@ cudaError_t run_qos(Launcher &L, const DevCtx &c, const DevBatch &b, bool egress
 }
 
 cudaError_t run_nat_egress(Launcher &L, const DevCtx &c, const DevBatch &b) {
-    LAUNCH((k_pipe_classify<false, false>), b.n, 5, c, b, L.s.key_a, L.s.val_a);
+    LAUNCH((k_pipe_classify<false, false>), b.n, CLASSIFY_BPS(false), c, b, L.s.key_a, L.s.val_a);
     Grouped g;
     cudaError_t e = group_by_key(L, b.n, (u64)c.sub_nat.mask + 1, &g);
     if (e != cudaSuccess) return e;
@@ -594,7 +651,7 @@ cudaError_t run_nat_hairpin_xdp(Launcher &L, const DevCtx &c, const DevBatch &b)
 }
 
 cudaError_t run_pipeline_up(Launcher &L, const DevCtx &c, const DevBatch &b) {
-    LAUNCH((k_pipe_classify<true, true>), b.n, 5, c, b, L.s.key_a, L.s.val_a);
+    LAUNCH((k_pipe_classify<true, true>), b.n, CLASSIFY_BPS(true), c, b, L.s.key_a, L.s.val_a);
     u64 space = (u64)(c.qos_in.mask + 1) + (c.sub_nat.mask + 1);
     Grouped g;
     cudaError_t e = group_by_key(L, b.n, space, &g);

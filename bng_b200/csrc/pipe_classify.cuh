@@ -14,10 +14,15 @@
 // gather-heavy kernel like this one.
 #pragma once
 
+// Resident blocks per SM each instantiation is compiled for: the three-stage pipeline keeps two 256-bit
+// table probes and the 64-byte header live at once and spills at 48 registers (5 blocks), so it runs 4
+// blocks of 64 registers; the NAT-only instantiation fits 48.
+#define CLASSIFY_BPS(AS) ((AS) ? 4 : 5)
+
 // AS: run antispoof_ingress first; QOS: look up the qos_ingress bucket.  <false,false> is the
 // standalone nat44_egress classify (ordering key = subscriber_nat slot).
 template <bool AS, bool QOS>
-__global__ void __launch_bounds__(BLOCK, 5)
+__global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
     k_pipe_classify(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b, u32 *skey, u32 *sval) {
     __shared__ SmallTabs st;
     __shared__ BlockStats bs;
@@ -28,21 +33,15 @@ __global__ void __launch_bounds__(BLOCK, 5)
     const u32 as_cfg = st.as_cfg, nflags = st.nat_flags;
     const u32 lane = threadIdx.x & 31;
     u32 n_allowed = 0, n_snat = 0;
-#if BNG_L2_STREAM
-    const u64 pol = l2_policy_evict_first();
-#endif
     // warp-uniform trip count: every lane stays in the loop, inactive lanes are predicated off
     for (u32 base = blockIdx.x * BLOCK + (threadIdx.x & ~31u); base < b.n; base += gridDim.x * BLOCK) {
         const u32 i = base + lane;
         const bool act = i < b.n;
         const u32 len = act ? b.len[i] : 0;
         u8 *p = act ? frame_ptr(b, i) : b.pkts;
+        const bool wide = __all_sync(0xffffffffu, !act || FRAME_WIDE_OK(b, p));
         Hdr64 h;
-#if BNG_L2_STREAM
-        hdr_load_stream(h, p, len, pol);
-#else
-        hdr_load(h, p, len);
-#endif
+        hdr_load_wide(h, p, len, wide);
 
         // ---- phase 1: keys, and the first probe of every table this frame may need ----
         const bool ip4 = len >= 34 && h.b16(12) == ETH_P_IP_LE;
@@ -65,22 +64,34 @@ __global__ void __launch_bounds__(BLOCK, 5)
         key[0] = (u64)saddr | ((u64)daddr << 32);
         key[1] = (u64)sport | ((u64)dport << 16) | ((u64)proto << 32);
         const u32 hi = tbl_hash<2>(key) & c.sessions.mask;
-        u64 bw0 = K_EMPTY, sw0 = K_EMPTY, qw0 = K_EMPTY, kw0 = K_EMPTY, kw1 = 0;
-        if (AS && len >= 14) bw0 = *(const u64 *)tbl_slot(c.bindings, bi);
+        // whole 32-byte sectors per probe: the binding slot, and the flow slot's key + translation
+        u64 sw0 = K_EMPTY, qw0 = K_EMPTY, qrate0 = 0;
+        BindVal bv;
+        U256 s0;
+        bv.s.w[0] = bv.s.w[1] = s0.w[0] = s0.w[1] = 0xFFFFFFFFu; // K_EMPTY
+        s0.w[2] = s0.w[3] = 0;
+        const u8 *bslot0 = tbl_slot(c.bindings, bi);
+        u8 *sslot0 = tbl_slot(c.sessions, hi);
+        if (AS && len >= 14) bv.s = ldg256(bslot0);
         if (ip4) {
             sw0 = *(const u64 *)tbl_slot(c.sub_nat, si);
-            if (QOS) qw0 = *(const u64 *)tbl_slot(c.qos_in, qi);
-            const ulonglong2 kk = *(const ulonglong2 *)tbl_slot(c.sessions, hi);
-            kw0 = kk.x;
-            kw1 = kk.y;
+            if (QOS) { // key and the mirrored rate_bps in one 16-byte load
+                const ulonglong2 q = *(const ulonglong2 *)tbl_slot(c.qos_in, qi);
+                qw0 = q.x;
+                qrate0 = q.y;
+            }
+            s0 = ldg256(sslot0);
         }
+        const u64 kw0 = (u64)s0.w[0] | ((u64)s0.w[1] << 32), kw1 = (u64)s0.w[2] | ((u64)s0.w[3] << 32);
 
         // ---- phase 2: antispoof_ingress ----
         int v = TC_OK;
         if (AS) {
-            const u8 *bind = len >= 14 ? tbl_finish<1>(c.bindings, &mk, bi, bw0, true) : nullptr;
+            const u8 *bind = len >= 14 ? tbl_finish<1>(c.bindings, &mk, bi, (u64)bv.s.w[0] | ((u64)bv.s.w[1] << 32), true) : nullptr;
             __syncwarp();
-            v = antispoof_eval(c, bs, h, len, i + b.base, b.now, bind, as_cfg, n_allowed);
+            bv.has = bind != nullptr;
+            if (bind && bind != bslot0) bv.s = ldg256(bind); // found on a later probe
+            v = antispoof_eval(c, bs, h, len, i + b.base, b.now, bv, as_cfg, n_allowed);
             __syncwarp();
         }
         const bool alive = act && v != TC_SHOT && ip4;
@@ -112,8 +123,9 @@ __global__ void __launch_bounds__(BLOCK, 5)
         bool miss = go && !ses;
         u32 sub_idx = miss ? (u32)((sub - c.sub_nat.slots) / c.sub_nat.slot_bytes) : 0;
         if (ses) {
-            // one 16-byte load in the key's own sector: nat_ip, nat_port|orig_port, last_seen
-            const uint4 tr = *(const uint4 *)(ses + SES_NAT_IP);
+            // the key's own sector also carries nat_ip, nat_port|orig_port, last_seen
+            uint4 tr = make_uint4(s0.w[4], s0.w[5], s0.w[6], s0.w[7]);
+            if (ses != sslot0) tr = *(const uint4 *)(ses + SES_NAT_IP); // found on a later probe
             const u32 nat_ip = tr.x;
             const u16 nat_port = (u16)tr.y;
             if (((u64)tr.z | ((u64)tr.w << 32)) != b.now) *(u64 *)(ses + SES_LAST_SEEN) = b.now;
@@ -137,15 +149,17 @@ __global__ void __launch_bounds__(BLOCK, 5)
                 h.s16(38, nat_port);
                 h.s16(36, csum_upd16(h.b16(36), sport, nat_port));
             }
-#if BNG_L2_STREAM
-            hdr_store_chunk_stream(h, p, 1, pol);
-            hdr_store_chunk_stream(h, p, 2, pol);
-            if (proto == 6) hdr_store_chunk_stream(h, p, 3, pol);
-#else
-            hdr_store_chunk(h, p, 1);
-            hdr_store_chunk(h, p, 2);
-            if (proto == 6) hdr_store_chunk(h, p, 3);
-#endif
+            if (wide) { // whole sectors: bytes 0-31 (the Ethernet header goes back unchanged), then 32-63 or 32-47
+                stg256(p, &h.w[0]);
+                if (proto == 6)
+                    stg256(p + 32, &h.w[8]);
+                else
+                    hdr_store_chunk(h, p, 2);
+            } else {
+                hdr_store_chunk(h, p, 1);
+                hdr_store_chunk(h, p, 2);
+                if (proto == 6) hdr_store_chunk(h, p, 3);
+            }
             n_snat++;
         }
         __syncwarp();
@@ -163,7 +177,7 @@ __global__ void __launch_bounds__(BLOCK, 5)
         u32 okey = NO_KEY, oval = i;
         if (alive && v != TC_SHOT) {
             if (qsl) {
-                const u64 rate = *(const u64 *)(qsl + 32);
+                const u64 rate = qsl == tbl_slot(c.qos_in, qi) ? qrate0 : *(const u64 *)(qsl + QOS_RATE_COPY);
                 if (!miss && rate == 0) { // unlimited bucket and nothing left to order
                     bstats_add(bs, ST_QOS_PASS_PKTS, 1);
                     bstats_add(bs, ST_QOS_PASS_BYTES, len);

@@ -45,14 +45,26 @@ __device__ __forceinline__ void spoof_log(const DevCtx &c, BlockStats &bs, u32 i
 // `bind` is the subscriber_bindings slot of the frame's source MAC (or null),
 // `cfg` = default_mode | log_violations << 8; packets_allowed is counted in the
 // caller's register counter n_allowed (flushed once per thread).
+// A subscriber_bindings slot (32 B: key, then struct subscriber_binding) as one 256-bit load.
+struct BindVal {
+    bool has;
+    U256 s; // w[0..1] key, w[2] ipv4_addr, w[3..6] ipv6_addr, w[7] ipv4_valid | ipv6_valid << 8 | mode << 16
+};
+__device__ __forceinline__ BindVal bind_load(const u8 *slot) {
+    BindVal b;
+    b.has = slot != nullptr;
+    if (slot) b.s = ldg256(slot);
+    return b;
+}
 __device__ __forceinline__ int antispoof_eval(const DevCtx &c, BlockStats &bs, const Hdr64 &h, u32 len, u32 idx, u64 now,
-                                              const u8 *bind, u32 cfg, u32 &n_allowed) {
+                                              const BindVal &bv, u32 cfg, u32 &n_allowed) {
+    const bool bind = bv.has;
     if (len < 14) return TC_OK; // :195-196, no stats
     u32 default_mode = cfg & 0xff, log_viol = (cfg >> 8) & 0xff;
     u32 b_ipv4 = 0, b_flags = 0; // flags word: ipv4_valid | ipv6_valid<<8 | mode<<16
     if (bind) {
-        b_ipv4 = *(const u32 *)(bind + 8);
-        b_flags = *(const u32 *)(bind + 28);
+        b_ipv4 = bv.s.w[2];
+        b_flags = bv.s.w[7];
     }
     u32 mode = bind ? ((b_flags >> 16) & 0xff) : default_mode;
     if (mode == 0) { // ANTISPOOF_DISABLED :213-216
@@ -89,7 +101,7 @@ __device__ __forceinline__ int antispoof_eval(const DevCtx &c, BlockStats &bs, c
             allowed = true;
 #pragma unroll
             for (int k = 0; k < 4; k++) // ip6->saddr at frame bytes 22..37, binding ipv6_addr at value+4
-                allowed = allowed && (h.b32(22 + 4 * k) == *(const u32 *)(bind + 12 + 4 * k));
+                allowed = allowed && (h.b32(22 + 4 * k) == bv.s.w[3 + k]);
         } else if (mode == 2) {
             allowed = true;
         }
@@ -162,7 +174,7 @@ __device__ __forceinline__ u32 qos_classify_one(const DevCtx &c, BlockStats &bs,
     u64 k = egress ? h.b32(30) : h.b32(26);
     const u8 *slot = tbl_find<1, false>(t, &k);
     if (!slot) return NO_KEY; // no policy: TC_ACT_OK without statistics
-    u64 rate = *(const u64 *)(slot + 32);
+    u64 rate = *(const u64 *)(slot + QOS_RATE_COPY); // mirror of rate_bps in the key's sector
     if (rate == 0) { // unlimited: pass, bucket untouched (:77-78)
         bstats_add(bs, ST_QOS_PASS_PKTS, 1);
         bstats_add(bs, ST_QOS_PASS_BYTES, len);

@@ -25,6 +25,9 @@ __device__ __forceinline__ void val_to_slot(const Tbl &t, u8 *slot, const u8 *ab
         for (u32 i = 0; i < t.value_size; i++) slot[ses_abi_to_slot(i)] = abi[i];
     } else {
         copy_bytes(slot + t.voff, abi, t.value_size);
+        // token buckets: rate_bps (value offset 16) is mirrored next to the key, so that the per-frame
+        // probe learns "unlimited or not" from the key's own 16 bytes.  Device code never changes the rate.
+        if (t.vlayout == VL_QOS) *(u64 *)(slot + QOS_RATE_COPY) = *(const u64 *)(slot + t.voff + 16);
     }
 }
 __device__ __forceinline__ void val_from_slot(const Tbl &t, u8 *abi, const u8 *slot) {
