@@ -269,14 +269,18 @@ __device__ __forceinline__ u64 ld_vol64(const u8 *p) { return *(volatile const u
 // Find the slot holding key k (KW 64-bit words), or nullptr.  VOL selects
 // L1-bypassing loads of the state word, needed in kernels that insert
 // concurrently.
-template <int KW, bool VOL>
+// SKIP_BUSY: a slot another thread is filling right now is stepped over instead of waited for.  Legal
+// wherever a key can only be inserted by the thread that looks it up (the ordered phase: every flow
+// key belongs to one subscriber, every subscriber to one worker) — and necessary there, because the
+// workers of 32 subscribers share a warp and a lane must never wait for another lane of its own warp.
+template <int KW, bool VOL, bool SKIP_BUSY = false>
 __device__ __forceinline__ u8 *tbl_find(const Tbl &t, const u64 *k) {
     if (k[0] >= K_BUSY) return nullptr;
     u32 i = (u32)tbl_hash<KW>(k) & t.mask;
     for (u32 probe = 0; probe <= t.mask; probe++) {
         u8 *s = tbl_slot(t, i);
         u64 w0 = VOL ? ld_vol64(s) : *(const u64 *)s;
-        if (VOL) {
+        if (VOL && !SKIP_BUSY) {
             while (w0 == K_BUSY) {
                 __nanosleep(32);
                 w0 = ld_vol64(s);
@@ -303,7 +307,7 @@ __device__ __forceinline__ u8 *tbl_find(const Tbl &t, const u64 *k) {
 // atomic per warp instead of one per insert, which on a million-insert batch is the difference
 // between a same-address atomic storm and none).  The max_entries check is then approximate by at
 // most the inserts in flight, which only matters for the LRU maps at the very edge of capacity.
-template <int KW>
+template <int KW, bool SKIP_BUSY = false>
 __device__ __forceinline__ u8 *tbl_find_or_claim(const Tbl &t, const u64 *k, bool *created, u32 *pending = nullptr) {
     *created = false;
     if (k[0] >= K_BUSY) return nullptr;
@@ -312,7 +316,7 @@ __device__ __forceinline__ u8 *tbl_find_or_claim(const Tbl &t, const u64 *k, boo
     for (u32 probe = 0; probe <= t.mask;) {
         u8 *s = tbl_slot(t, i);
         u64 w0 = ld_vol64(s);
-        while (w0 == K_BUSY) {
+        while (!SKIP_BUSY && w0 == K_BUSY) {
             __nanosleep(32);
             w0 = ld_vol64(s);
         }
@@ -356,8 +360,14 @@ __device__ __forceinline__ u8 *tbl_find_or_claim(const Tbl &t, const u64 *k, boo
     return nullptr;
 }
 
+// FENCE orders the value stores before the key for readers in other warps.  The ordered phase publishes
+// without it: a flow key is only ever looked up by the worker that inserted it (other workers step over
+// the slot whatever its state), lanes of one warp are ordered by __syncwarp(), and the kernel boundary
+// orders everything for whoever comes next — three device-wide fences per new flow were 40 % of a
+// cold-start batch.
+template <bool FENCE = true>
 __device__ __forceinline__ void tbl_publish(u8 *slot, u64 k0) {
-    __threadfence();
+    if (FENCE) __threadfence();
     *(volatile u64 *)slot = k0;
 }
 

@@ -377,7 +377,10 @@ __global__ void __launch_bounds__(BLOCK) k_heads(const __grid_constant__ Grouped
 //   QOS:  token_bucket_check() for every surviving frame of the group.
 // ---------------------------------------------------------------------------
 template <bool NAT, bool QOS, bool EGRESS>
-__global__ void __launch_bounds__(BLOCK) k_resolve(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b,
+// The NAT-only walk is a chain of dependent table accesses per new flow: what hides its latency is the
+// number of resident warps, so it is compiled for 8 blocks per SM (32 registers, a few spills); with
+// the token-bucket walk in the same kernel the spills cost more than the occupancy gives.
+__global__ void __launch_bounds__(BLOCK, (NAT && !QOS) ? 8 : 4) k_resolve(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b,
                                                    const __grid_constant__ Grouped g, const u32 *seg, const u32 *cnt) {
     __shared__ BlockStats bs;
     bstats_init(bs);

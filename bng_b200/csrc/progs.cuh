@@ -250,7 +250,7 @@ __device__ __forceinline__ u16 nat_alloc_port(const DevCtx &c, u8 *sub, bool par
         if (next > port_end) next = port_start;
         if (parity && ((port & 1) != (orig_port & 1))) continue;
         u64 ek = (u64)internal_ip | ((u64)port << 32) | ((u64)proto << 48);
-        if (tbl_find<1, true>(c.eim, &ek)) continue;
+        if (tbl_find<1, true, true>(c.eim, &ek)) continue;
         found = port;
         break;
     }
@@ -309,7 +309,7 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
     u32 saddr = rd32(p, 26);
     if (!is_private_ip(saddr)) return o;
     u64 sk = saddr;
-    u8 *sub = tbl_find<1, RESOLVE>(c.sub_nat, &sk);
+    u8 *sub = tbl_find<1, RESOLVE, RESOLVE>(c.sub_nat, &sk);
     if (!sub) {
         if (!RESOLVE) bstats_add(bs, ST_NAT_PASSED, 1);
         return o;
@@ -354,7 +354,7 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
     u64 key[2];
     key[0] = (u64)saddr | ((u64)daddr << 32);
     key[1] = (u64)sport | ((u64)dport << 16) | ((u64)proto << 32);
-    u8 *ses = tbl_find<2, RESOLVE>(c.sessions, key);
+    u8 *ses = tbl_find<2, RESOLVE, RESOLVE>(c.sessions, key);
     u32 nat_ip;
     u16 nat_port;
     if (ses) { // :674-680
@@ -372,7 +372,7 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
         bool have = false;
         if (cfg_flags & NATF_EIM) { // get_eim_mapping(), :469-528
             u64 ek = (u64)saddr | ((u64)sport << 32) | ((u64)proto << 48);
-            u8 *m = tbl_find<1, true>(c.eim, &ek);
+            u8 *m = tbl_find<1, true, true>(c.eim, &ek);
             if (m) {
                 *(u64 *)(m + 24) = now;
                 *(u32 *)(m + 32) += 1;
@@ -383,7 +383,7 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
                     bstats_add(bs, ST_NAT_EXHAUST, 1);
                 } else {
                     bool created;
-                    m = tbl_find_or_claim<1>(c.eim, &ek, &created, pd ? &pd->eim : nullptr);
+                    m = tbl_find_or_claim<1, true>(c.eim, &ek, &created, pd ? &pd->eim : nullptr);
                     if (m && created) {
                         *(u32 *)(m + 8) = pub_ip;
                         *(u32 *)(m + 12) = ext; // external_port (host order) + zero pad
@@ -391,7 +391,7 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
                         *(u64 *)(m + 24) = now;
                         *(u32 *)(m + 32) = 1;
                         *(u32 *)(m + 36) = 0;
-                        tbl_publish(m, ek);
+                        tbl_publish<false>(m, ek);
                         bstats_add(bs, ST_NAT_EIM_MISS, 1);
                     } else if (m) { // "someone else created it" branch (:521-527)
                         *(u32 *)(m + 32) += 1;
@@ -420,7 +420,7 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
             nat_port = bswap16(ap);
         }
         bool created;
-        u8 *ns = tbl_find_or_claim<2>(c.sessions, key, &created, pd ? &pd->ses : nullptr); // BPF_ANY (:730)
+        u8 *ns = tbl_find_or_claim<2, true>(c.sessions, key, &created, pd ? &pd->ses : nullptr); // BPF_ANY (:730)
         if (ns) {
             *(u32 *)(ns + SES_NAT_IP) = nat_ip;
             *(u32 *)(ns + SES_NAT_PORT) = (u32)nat_port | ((u32)sport << 16); // nat_port, orig_port
@@ -435,18 +435,18 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
             *(u32 *)(ns + SES_DEST_IP) = daddr;
             *(u32 *)(ns + SES_DEST_PORT) = (u32)dport; // dest_port, _pad1 = 0
             *(u64 *)(ns + 88) = 0;                      // the struct's padding bytes
-            if (created) tbl_publish(ns, key[0]);
+            if (created) tbl_publish<false>(ns, key[0]);
         } else {
             bstats_add(bs, ST_LRU_OVERFLOW, 1);
         }
         u64 rk[2];
         rk[0] = (u64)daddr | ((u64)nat_ip << 32);
         rk[1] = (u64)dport | ((u64)nat_port << 16) | ((u64)proto << 32);
-        u8 *rs = tbl_find_or_claim<2>(c.reverse, rk, &created, pd ? &pd->rev : nullptr); // BPF_ANY (:740)
+        u8 *rs = tbl_find_or_claim<2, true>(c.reverse, rk, &created, pd ? &pd->rev : nullptr); // BPF_ANY (:740)
         if (rs) {
             *(u64 *)(rs + 16) = key[0];
             *(u64 *)(rs + 24) = key[1];
-            if (created) tbl_publish(rs, rk[0]);
+            if (created) tbl_publish<false>(rs, rk[0]);
         } else {
             bstats_add(bs, ST_LRU_OVERFLOW, 1);
         }
