@@ -154,6 +154,28 @@ class GpuBackend:
         # pinned host buffers: exercises the zero-copy gather/scatter path of BNG_MEM_HOST
         import torch
         from bng_b200 import MEM_HOST
+        if self.pinned == "abi":  # the arena comes from bng_host_alloc() (huge-page backed, registered)
+            import ctypes
+            from bng_b200.dataplane import load_library
+            lib = load_library()
+            p = lib.bng_host_alloc(arena.nbytes + 64)
+            assert p, "bng_host_alloc failed"
+            try:
+                view = np.ctypeslib.as_array((ctypes.c_uint8 * arena.nbytes).from_address(p))
+                view[:] = arena
+                tl = torch.from_numpy(lens.view(np.int32).copy()).pin_memory()
+                to = None if off16 is None else torch.from_numpy(off16.view(np.int32).copy()).pin_memory()
+                tp = None if prio is None else torch.from_numpy(prio.view(np.int32).copy()).pin_memory()
+                tv = torch.zeros(len(lens), dtype=torch.uint8).pin_memory()
+                self.dp.run(prog, int(p), tl, now, off16=to, stride=stride, priority=tp, verdict=tv, mem=MEM_HOST,
+                            arena_bytes=arena.nbytes)
+                arena[:] = view
+            finally:
+                lib.bng_host_free(p)
+            lens[:] = tl.numpy().view(np.uint32)
+            if prio is not None:
+                prio[:] = tp.numpy().view(np.uint32)
+            return tv.numpy().copy()
         ta = torch.from_numpy(arena.copy()).pin_memory()
         tl = torch.from_numpy(lens.view(np.int32).copy()).pin_memory()
         to = None if off16 is None else torch.from_numpy(off16.view(np.int32).copy()).pin_memory()

@@ -36,6 +36,13 @@ def test_gpu_matches_golden(script, pinned, gpu_results):
     harness.compare(gold, gpu_results(script, pinned), f"{script}: golden vs gpu ({'pinned' if pinned else 'pageable'})")
 
 
+@pytest.mark.parametrize("script", ["pipeline", "nat", "dhcp"])
+def test_gpu_matches_golden_abi_host_arena(script, gpu_results):
+    """Frames in memory obtained from bng_host_alloc() (huge-page backed, cudaHostRegister'ed)."""
+    gold = harness.load_golden(os.path.join(GOLD, script + ".npz"))
+    harness.compare(gold, gpu_results(script, "abi"), f"{script}: golden vs gpu (bng_host_alloc arena)")
+
+
 @pytest.mark.parametrize("script", sorted(scenarios.ALL_SCRIPTS))
 def test_gpu_matches_live_oracle(script, ora_kind, gpu_results):
     if ora_kind == "none":
