@@ -57,26 +57,28 @@ __global__ void __launch_bounds__(BLOCK) k_antispoof(const __grid_constant__ Dev
     bstats_init(bs);
     u32 cfg = *(const u16 *)c.as_config;
     u32 n_allowed = 0;
-    for (u32 i = blockIdx.x * BLOCK + threadIdx.x; i < b.n; i += gridDim.x * BLOCK) {
-        u32 len = b.len[i];
-        const u8 *p = frame_ptr(b, i);
+    const u32 lane = threadIdx.x & 31;
+    // warp-uniform trip count: the warp decides together whether its frames allow 256-bit loads
+    for (u32 base = blockIdx.x * BLOCK + (threadIdx.x & ~31u); base < b.n; base += gridDim.x * BLOCK) {
+        const u32 i = base + lane;
+        const bool act = i < b.n;
+        const u32 len = act ? b.len[i] : 0;
+        const u8 *p = act ? frame_ptr(b, i) : b.pkts;
         Hdr64 h;
-        hdr_load_wide(h, p, len, __all_sync(__activemask(), FRAME_WIDE_OK(b, p)));
+        hdr_load_wide(h, p, len, __all_sync(0xffffffffu, !act || FRAME_WIDE_OK(b, p)));
         u64 mk = mac_key(h, 6);
         // first probe = the whole 32-byte slot (key + binding); later probes only on a collision
-        const u8 *slot0 = tbl_slot(c.bindings, tbl_hash<1>(&mk) & c.bindings.mask);
         BindVal bv;
         bv.has = false;
         if (len >= 14) {
-            bv.s = ldg256(slot0);
+            bv.s = ldg256(tbl_slot(c.bindings, tbl_hash<1>(&mk) & c.bindings.mask));
             const u64 w0 = (u64)bv.s.w[0] | ((u64)bv.s.w[1] << 32);
-            if (w0 == mk) {
+            if (w0 == mk)
                 bv.has = true;
-            } else if (w0 != K_EMPTY) {
+            else if (w0 != K_EMPTY)
                 bv = bind_load(tbl_find<1, false>(c.bindings, &mk));
-            }
         }
-        b.verdict[i] = (u8)antispoof_eval(c, bs, h, len, i + b.base, b.now, bv, cfg, n_allowed);
+        if (act) b.verdict[i] = (u8)antispoof_eval(c, bs, h, len, i + b.base, b.now, bv, cfg, n_allowed);
     }
     warp_stat_flush(bs, ST_AS_ALLOWED, n_allowed);
     bstats_flush(bs, c.stats);
@@ -161,7 +163,9 @@ __global__ void __launch_bounds__(BLOCK) k_nat_hairpin_xdp(const __grid_constant
 // read *cnt[CNT_M] elements.  Every block owns one contiguous range of the
 // input, so (digit, block) order of the scanned histogram is index order.
 // ---------------------------------------------------------------------------
-#define RS_BLOCKS_PER_SM 6
+#ifndef RS_BLOCKS_PER_SM
+#define RS_BLOCKS_PER_SM 3 // what the scatter's 71 registers x 256 threads lets an SM hold: one wave, whole tiles
+#endif
 
 __device__ __forceinline__ void rs_range(u32 total, u32 &lo, u32 &hi) {
     u32 per = (total + gridDim.x - 1) / gridDim.x;
@@ -365,8 +369,20 @@ __global__ void __launch_bounds__(BLOCK) k_heads(const __grid_constant__ Grouped
     const u32 *skey, *sval_unused;
     grouped_select(g, cnt, skey, sval_unused);
     u32 m = cnt[CNT_M];
-    for (u32 j = blockIdx.x * BLOCK + threadIdx.x; j < m; j += gridDim.x * BLOCK) {
-        if (j == 0 || skey[j - 1] != skey[j]) seg[atomicAdd(&cnt[CNT_NSEG], 1u)] = j;
+    for (u32 j = 4 * (blockIdx.x * BLOCK + threadIdx.x); j < m; j += 4 * gridDim.x * BLOCK) { // 4 keys per thread
+        u32 k[4], prev = j ? skey[j - 1] : ~skey[0];
+        if (j + 3 < m) {
+            const uint4 v = *(const uint4 *)(skey + j);
+            k[0] = v.x, k[1] = v.y, k[2] = v.z, k[3] = v.w;
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; t++) k[t] = j + t < m ? skey[j + t] : 0;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            if (j + t < m && k[t] != prev) seg[atomicAdd(&cnt[CNT_NSEG], 1u)] = j + t;
+            prev = k[t];
+        }
     }
 }
 
@@ -377,6 +393,9 @@ __global__ void __launch_bounds__(BLOCK) k_heads(const __grid_constant__ Grouped
 //   QOS:  token_bucket_check() for every surviving frame of the group.
 // ---------------------------------------------------------------------------
 template <bool NAT, bool QOS, bool EGRESS>
+#ifndef RESOLVE_CHUNKS
+#define RESOLVE_CHUNKS 2
+#endif
 // The NAT-only walk is a chain of dependent table accesses per new flow: what hides its latency is the
 // number of resident warps, so it is compiled for 8 blocks per SM (32 registers, a few spills); with
 // the token-bucket walk in the same kernel the spills cost more than the occupancy gives.
@@ -402,14 +421,11 @@ __global__ void __launch_bounds__(BLOCK, (NAT && !QOS) ? 8 : 4) k_resolve(const 
         u8 *slot = has_bucket ? tbl_slot(qt, key) : nullptr;
         TokenBucket tb;
         if (has_bucket) tb_load(tb, slot);
-        for (u32 q0 = start;; q0 += 32) {
-            const u32 q = q0 + lane;
-            const bool valid = q < m && skey[q] == key;
+        // one chunk = 32 consecutive frames of the group; returns false when the group ended in it
+        auto chunk = [&](const bool valid, const u32 sv, const u32 len) -> bool {
             const u32 vmask = __ballot_sync(0xffffffffu, valid);
-            if (!vmask) break;
-            const u32 sv = valid ? sval[q] : 0;
+            if (!vmask) return false;
             const u32 idx = sv & ~MISS_FLAG;
-            const u32 len = valid ? b.len[idx] : 0;
             bool dropped = false;
             if (NAT) {
                 const bool is_miss = valid && (sv & MISS_FLAG);
@@ -485,7 +501,25 @@ __global__ void __launch_bounds__(BLOCK, (NAT && !QOS) ? 8 : 4) k_resolve(const 
                     }
                 }
             }
-            if (vmask != 0xffffffffu) break; // the group ended inside this chunk
+            return vmask == 0xffffffffu; // else the group ended inside this chunk
+        };
+        // RESOLVE_CHUNKS chunks per trip: their (key, value) loads and their length gathers are issued
+        // together, which divides the number of dependent memory round trips of the walk; the chunks
+        // themselves are applied one after the other, in index order.
+        for (u32 q0 = start;; q0 += 32 * RESOLVE_CHUNKS) {
+            bool v[RESOLVE_CHUNKS], more = true;
+            u32 sv[RESOLVE_CHUNKS], ln[RESOLVE_CHUNKS];
+#pragma unroll
+            for (int t = 0; t < RESOLVE_CHUNKS; t++) {
+                const u32 q = q0 + 32 * t + lane;
+                v[t] = q < m && skey[q] == key;
+                sv[t] = v[t] ? sval[q] : 0;
+            }
+#pragma unroll
+            for (int t = 0; t < RESOLVE_CHUNKS; t++) ln[t] = v[t] ? b.len[sv[t] & ~MISS_FLAG] : 0;
+#pragma unroll
+            for (int t = 0; t < RESOLVE_CHUNKS; t++) more = more && chunk(v[t], sv[t], ln[t]);
+            if (!more) break;
         }
         if (has_bucket && lane == 0) {
             *(u64 *)(slot + 16) = tb.tokens;
