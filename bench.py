@@ -18,6 +18,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -465,13 +466,39 @@ def run_gpu(a):
         dist.destroy_process_group()
 
 
+def run_dhcp_slow(a):
+    """BASELINE.json configs[0]: 1 000 DHCP DISCOVERs through the slow path with a 256-entry lease map, CPU only.
+    The reference's pkg/dhcp is Go and cannot be built in this image; what is timed is its C++ restatement
+    (bng_b200/host/bng_dhcp_slow.hpp, one thread — the reference serialises on the pool mutex).  Plumbing: no GPU,
+    no roofline, gpu_launches 0 by construction."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_host_mirror
+    test_host_mirror.build_host_test()
+    rounds = max(1, a.steps) * 100
+    j = json.loads(subprocess.run([test_host_mirror.SLOW_BIN, str(rounds)], capture_output=True, text=True, check=True).stdout)
+    print(json.dumps({
+        "metric": "DHCP DISCOVER/s (slow path, CPU only)", "value": round(j["req_per_s"], 1), "unit": "requests/s", "n_gpus": 0,
+        "steps": rounds, "warmup": 0, "ms_per_step": round(j["seconds"] / rounds * 1e3, 4), "higher_is_better": True,
+        "scaling": "n/a", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "dhcp_slow", "requests_per_step": 1000, "clients_with_lease": 256, "pool": "10.0.0.0/22",
+                   "implementation": "C++ restatement of pkg/dhcp Server.handleDiscover + Pool.Allocate (Go toolchain absent)"},
+        "roofline": None, "gpu_launches": 0,
+        "cpu_baseline": {"value": round(j["req_per_s"], 1), "unit": "requests/s", "cores": 1, "kind": "port",
+                         "sample": f"{j['requests']} DISCOVERs in {j['seconds']:.2f} s"},
+        "e2e": {"value": round(j["req_per_s"], 1), "unit": "requests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "replies_fnv1a": j["replies_fnv1a"]}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="pipeline_imix", choices=sorted(W.BUILDERS))
+    ap.add_argument("--workload", default="pipeline_imix", choices=sorted(W.BUILDERS) + ["dhcp_slow"],
+                    help="dhcp_slow = BASELINE config #1: the DHCP slow path (CPU only, plumbing; no GPU involved)")
     ap.add_argument("--frames", type=int, default=1 << 22)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
@@ -483,7 +510,9 @@ def main():
                          "receive ring uses: far fewer IOMMU translations for the GPU's scattered header reads), or cudaHostAlloc")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
-    if a.impl == "reference":
+    if a.workload == "dhcp_slow":
+        run_dhcp_slow(a)
+    elif a.impl == "reference":
         run_reference_arm(a)
     else:
         run_gpu(a)

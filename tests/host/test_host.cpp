@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <string>
 
+#include "../../bng_b200/host/bng_dhcp_slow.hpp"
 #include "../../bng_b200/host/bng_host.hpp"
 
 using namespace bng;
@@ -216,6 +217,8 @@ static void test_antispoof_bookkeeping() {
 }
 
 // ---- with a device: everything round-trips through the C ABI ----
+static std::shared_ptr<dhcp::Pool> make_pool(const char *net, const char *gw, int rs = 0, int re = 0, uint32_t id = 1);
+
 static void test_gpu_roundtrips() {
     bng_open_opts o;
     memset(&o, 0, sizeof(o));
@@ -357,12 +360,180 @@ static void test_gpu_roundtrips() {
     CHECK(log.size() == 1 && log[0].EventType == nat::NATLogSessionCreate && log[0].SubscriberID == 1);
     CHECK(!nm->DeallocateNAT(IPv4(100, 64, 0, 9)));
     CHECK(bng_map_lookup(be->ctx, be->Map("subscriber_nat"), &ipk, &sn) != 0);
+
+    // ---- slow path -> fast path: what pkg/dhcp decides is what the GPU answers with from then on ----
+    {
+        dhcp::PoolManager pm(l.get());
+        auto pool = make_pool("10.0.0.0/22", "10.0.0.1", 0, 0, 3);
+        CHECK(!pm.AddPool(pool) && !pm.LastSyncError());
+        auto gp = l->GetPool(3); // mirrored by AddPool (pkg/dhcp/pool.go:266-282)
+        CHECK(gp.ok() && gp->Network == 0x0A000000u && gp->PrefixLen == 22 && gp->Gateway == 0x0A000001u &&
+              gp->DNSPrimary == 0x08080808u && gp->DNSSecondary == 0x08080404u && gp->LeaseTime == 3600);
+        CHECK(!l->SetServerConfig(MAC{2, 0xaa, 0, 0, 0, 1}, IPv4(10, 0, 0, 1), 2));
+        int64_t t = 1700000000;
+        dhcp::Server srv(0x0A000001u, &pm, l.get(), [&] { return t; });
+        auto d = dhcp::ClientMessage(dhcp::Discover, 42, 0xABCD0001);
+        auto offer = dhcp::Message::Parse(srv.HandleDHCP(d.data(), d.size())->data(), 300);
+        CHECK(offer.ok() && offer->yiaddr == 0x0A000002u);
+        CHECK(!l->GetSubscriber(0x02000000002Aull).ok()); // an OFFER does not populate the fast path
+        auto rq = dhcp::ClientMessage(dhcp::Request, 42, 0xABCD0002, offer->yiaddr);
+        auto ack = dhcp::Message::Parse(srv.HandleDHCP(rq.data(), rq.size())->data(), 300);
+        CHECK(ack.ok() && ack->Type() == (int)dhcp::Ack && !srv.LastFastPathError());
+        auto sub = l->GetSubscriber(0x02000000002Aull); // updateFastPathCache (server.go:1057-1075)
+        CHECK(sub.ok() && sub->PoolID == 3 && sub->AllocatedIP == 0x0A000002u && sub->VlanID == 100 && sub->ClientClass == 1 &&
+              sub->LeaseExpiry == (uint64_t)(t + 3600));
+        // the client's next DISCOVER, as a frame on the wire, is answered by dhcp_fastpath_prog on the GPU
+        std::vector<uint8_t> fr(362, 0);
+        memset(&fr[0], 0xff, 6);
+        memcpy(&fr[6], "\x02\x00\x00\x00\x00\x2a", 6);
+        fr[12] = 0x08, fr[13] = 0x00;
+        fr[14] = 0x45, fr[16] = (uint8_t)((362 - 14) >> 8), fr[17] = (uint8_t)(362 - 14), fr[22] = 64, fr[23] = 17;
+        memset(&fr[30], 0xff, 4);
+        fr[34] = 0, fr[35] = 68, fr[36] = 0, fr[37] = 67, fr[38] = (uint8_t)((362 - 34) >> 8), fr[39] = (uint8_t)(362 - 34);
+        auto next = dhcp::ClientMessage(dhcp::Discover, 42, 0xABCD0003);
+        memcpy(&fr[42], next.data(), 300);
+        uint32_t flen = 362;
+        uint8_t fv = 0xff;
+        bng_batch fb;
+        memset(&fb, 0, sizeof(fb));
+        fb.pkts = fr.data(), fb.len = &flen, fb.verdict = &fv, fb.n = 1, fb.stride = 368, fb.now_ns = 5000000000ull, fb.mem = BNG_MEM_HOST;
+        fr.resize(368);
+        fb.pkts = fr.data();
+        CHECK_EQ(bng_prog_run(be->ctx, bng_prog_id(be->ctx, "dhcp_fastpath_prog"), &fb), 0);
+        CHECK_EQ((int)fv, 3); // XDP_TX: answered without the slow path
+        CHECK_EQ((int)fr[42], 2); // BOOTREPLY
+        uint32_t yi_stored = sub->AllocatedIP; // the program copies the stored word as is
+        CHECK(memcmp(&fr[42 + 16], &yi_stored, 4) == 0);
+        auto st = l->GetStats();
+        CHECK(st.ok() && st->FastpathHits == 1);
+    }
     CHECK(!l->Close());
+}
+
+// ---- DHCP slow path (bng_dhcp_slow.hpp), after pkg/dhcp/pool_test.go and the handleDiscover flow ----
+static std::shared_ptr<dhcp::Pool> make_pool(const char *net, const char *gw, int rs, int re, uint32_t id) {
+    dhcp::PoolConfig c;
+    c.ID = id, c.Name = "test", c.Network = net, c.Gateway = gw, c.DNSServers = {"8.8.8.8", "8.8.4.4"};
+    c.LeaseTimeSec = 3600, c.ReservedStart = rs, c.ReservedEnd = re, c.VlanID = 100, c.ClientClass = 1;
+    auto p = dhcp::Pool::New(c);
+    CHECK(p.ok());
+    return *p;
+}
+
+static void test_dhcp_pool() {
+    // TestNewPool (pool_test.go:9-42): /24 = 254 usable, minus 10 + 5 reserved; the gateway .1 is inside the reserved start
+    auto p = make_pool("10.0.1.0/24", "10.0.1.1", 10, 5);
+    CHECK_EQ(p->Stats().Available, 254 - 10 - 5);
+    CHECK_EQ(p->SubnetMask, 0xFFFFFF00u);
+    { // invalid inputs (NewPool :58-77)
+        dhcp::PoolConfig c;
+        c.Network = "10.0.1.0", c.Gateway = "10.0.1.1";
+        CHECK(!dhcp::Pool::New(c).ok());
+        c.Network = "10.0.1.0/24", c.Gateway = "nope";
+        CHECK_ERR(dhcp::Pool::New(c).err, "invalid gateway IP: nope");
+        c.Gateway = "10.0.1.1", c.DNSServers = {"8.8.8"};
+        CHECK_ERR(dhcp::Pool::New(c).err, "invalid DNS server IP: 8.8.8");
+    }
+    // TestPoolAllocate (:44-83): first free address (gateway skipped), same MAC -> same address
+    auto q = make_pool("192.168.1.0/24", "192.168.1.1");
+    auto a = q->Allocate(0xAABBCCDDEEFFull);
+    CHECK(a.ok() && *a == 0xC0A80102u && q->Contains(*a));
+    auto a2 = q->Allocate(0xAABBCCDDEEFFull);
+    CHECK(a2.ok() && *a2 == *a);
+    CHECK_EQ(*q->Allocate(0xAABBCCDDEE00ull), 0xC0A80103u);
+    // TestPoolRelease (:85-118): a /28 has 14 hosts, 13 without the gateway; release appends at the END
+    auto r = make_pool("192.168.1.0/28", "192.168.1.1");
+    int initial = r->Stats().Available;
+    CHECK_EQ(initial, 13);
+    auto ip = r->Allocate(1);
+    CHECK_EQ(r->Stats().Available, initial - 1);
+    r->Release(*ip);
+    CHECK_EQ(r->Stats().Available, initial);
+    CHECK_EQ(*r->Allocate(2), 0xC0A80103u); // .2 went to the back of the list
+    // exhaustion
+    for (uint64_t m = 10; r->Allocate(m).ok(); m++) {}
+    CHECK_ERR(r->Allocate(999).err, "pool test exhausted");
+    CHECK(!r->Contains(0xC0A80110u) && r->Contains(0xC0A8010Fu));
+    // PoolManager (:191-260): first pool is the default; duplicates refused
+    dhcp::PoolManager pm;
+    CHECK(pm.ClassifyClient(1) == nullptr);
+    CHECK(!pm.AddPool(p));
+    CHECK_ERR(pm.AddPool(p), "pool 1 already exists");
+    auto p2 = make_pool("10.0.2.0/24", "10.0.2.1", 0, 0, 2);
+    CHECK(!pm.AddPool(p2));
+    CHECK(pm.ClassifyClient(1) == p);
+    CHECK(!pm.SetDefaultPool(2));
+    CHECK(pm.ClassifyClient(1) == p2);
+    CHECK_ERR(pm.SetDefaultPool(9), "pool 9 not found");
+    CHECK(!pm.RemovePool(2));
+    CHECK(pm.ClassifyClient(1) == p);
+}
+
+static void test_dhcp_slow_path() {
+    int64_t t = 1700000000;
+    dhcp::PoolManager pm;
+    auto pool = make_pool("10.0.0.0/22", "10.0.0.1");
+    CHECK(!pm.AddPool(pool));
+    const uint32_t server_ip = 0x0A000001u;
+    dhcp::Server srv(server_ip, &pm, nullptr, [&] { return t; });
+    // DISCOVER of subscriber 5 -> OFFER with the pool's first address and the pool's parameters
+    auto req = dhcp::ClientMessage(dhcp::Discover, 5, 0x11223344);
+    CHECK_EQ(req.size(), 300u);
+    auto out = srv.HandleDHCP(req.data(), req.size());
+    CHECK(out.ok() && out->size() >= 300);
+    auto offer = dhcp::Message::Parse(out->data(), out->size());
+    CHECK(offer.ok());
+    CHECK_EQ((int)offer->op, 2);
+    CHECK_EQ(offer->xid, 0x11223344u);
+    CHECK_EQ(offer->flags, 0x8000);
+    CHECK_EQ(offer->Type(), (int)dhcp::Offer);
+    CHECK_EQ(offer->yiaddr, 0x0A000002u); // .1 is the gateway
+    CHECK_EQ(offer->siaddr, server_ip);
+    CHECK(memcmp(offer->chaddr, "\x02\x00\x00\x00\x00\x05", 6) == 0);
+    CHECK((offer->options[dhcp::OptServerID] == std::vector<uint8_t>{10, 0, 0, 1}));
+    CHECK((offer->options[dhcp::OptLeaseTime] == std::vector<uint8_t>{0, 0, 0x0e, 0x10}));
+    CHECK((offer->options[dhcp::OptSubnetMask] == std::vector<uint8_t>{255, 255, 252, 0}));
+    CHECK((offer->options[dhcp::OptRouter] == std::vector<uint8_t>{10, 0, 0, 1}));
+    CHECK((offer->options[dhcp::OptDNS] == std::vector<uint8_t>{8, 8, 8, 8, 8, 8, 4, 4}));
+    CHECK_EQ(srv.offersTotal, 1u);
+    // options leave in ascending code order and the message ends 255, padded to 300 bytes
+    CHECK((*out)[240] == dhcp::OptSubnetMask && (*out)[246] == dhcp::OptRouter);
+    // the same client asks again: Pool.Allocate returns the same address, no lease exists yet
+    auto again = srv.HandleDHCP(req.data(), req.size());
+    CHECK(dhcp::Message::Parse(again->data(), again->size())->yiaddr == 0x0A000002u);
+    CHECK_EQ(srv.ActiveLeases(), 0u);
+    // REQUEST for the offered address -> ACK, lease recorded with the pool's lease time
+    auto rq = dhcp::ClientMessage(dhcp::Request, 5, 0x11223345, 0x0A000002u);
+    auto ack = dhcp::Message::Parse(srv.HandleDHCP(rq.data(), rq.size())->data(), 300);
+    CHECK(ack.ok() && ack->Type() == (int)dhcp::Ack && ack->yiaddr == 0x0A000002u);
+    CHECK_EQ(srv.ActiveLeases(), 1u);
+    // renewal with a different address -> NAK (:586-590); an address outside the pool for a new client -> NAK
+    auto bad = dhcp::ClientMessage(dhcp::Request, 5, 1, 0x0A000009u);
+    CHECK_EQ(dhcp::Message::Parse(srv.HandleDHCP(bad.data(), bad.size())->data(), 300)->Type(), (int)dhcp::Nak);
+    auto outside = dhcp::ClientMessage(dhcp::Request, 6, 1, 0xC0A80001u);
+    CHECK_EQ(dhcp::Message::Parse(srv.HandleDHCP(outside.data(), outside.size())->data(), 300)->Type(), (int)dhcp::Nak);
+    CHECK_EQ(srv.naksTotal, 2u);
+    // a live lease is reused by DISCOVER (:420-424); once expired the pool is asked again (same MAC -> same address)
+    dhcp::Lease seeded;
+    seeded.MAC = 0x020000000007ull, seeded.IP = 0x0A000155u, seeded.PoolID = 1, seeded.ExpiresAt = t + 100;
+    srv.InstallLease(seeded);
+    auto d7 = dhcp::ClientMessage(dhcp::Discover, 7, 9);
+    CHECK_EQ(dhcp::Message::Parse(srv.HandleDHCP(d7.data(), d7.size())->data(), 300)->yiaddr, 0x0A000155u);
+    t += 200;
+    CHECK_EQ(dhcp::Message::Parse(srv.HandleDHCP(d7.data(), d7.size())->data(), 300)->yiaddr, 0x0A000003u);
+    // malformed input
+    CHECK(!srv.HandleDHCP(req.data(), 100).ok());
+    // no pool at all
+    dhcp::PoolManager empty;
+    dhcp::Server none(server_ip, &empty, nullptr);
+    CHECK_ERR(none.HandleDHCP(req.data(), req.size()).err, "no pool available for client");
 }
 
 int main(int argc, char **argv) {
     std::string mode = argc > 1 ? argv[1] : "cpu";
     test_conversions();
+    test_dhcp_pool();
+    test_dhcp_slow_path();
     test_loader_unloaded();
     test_nat_allocator();
     test_qos_bookkeeping();
