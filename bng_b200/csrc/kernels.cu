@@ -129,11 +129,145 @@ __global__ void __launch_bounds__(BLOCK)
 // ---------------------------------------------------------------------------
 // nat44_ingress, nat44_hairpin_xdp
 // ---------------------------------------------------------------------------
+// Header in registers, whole-sector probes (nat_reverse slot = key + original tuple in one 256-bit load,
+// nat_sessions sector 0 = key + translation + last_seen), the TCP state CAS only when the state would
+// change, the rewrite stored back as whole sectors.  Frames with IPv4 options take nat_ingress_one().
 __global__ void __launch_bounds__(BLOCK) k_nat_ingress(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b) {
     __shared__ BlockStats bs;
     bstats_init(bs);
-    for (u32 i = blockIdx.x * BLOCK + threadIdx.x; i < b.n; i += gridDim.x * BLOCK)
-        b.verdict[i] = (u8)nat_ingress_one(c, bs, frame_ptr(b, i), b.len[i], b.now);
+    const u32 lane = threadIdx.x & 31;
+    u32 n_dnat = 0, n_passed = 0;
+    for (u32 base = blockIdx.x * BLOCK + (threadIdx.x & ~31u); base < b.n; base += gridDim.x * BLOCK) {
+        const u32 i = base + lane;
+        const bool act = i < b.n;
+        const u32 len = act ? b.len[i] : 0;
+        u8 *p = act ? frame_ptr(b, i) : b.pkts;
+        const bool wide = __all_sync(0xffffffffu, !act || FRAME_WIDE_OK(b, p));
+        Hdr64 h;
+        hdr_load_wide(h, p, len, wide);
+        if (act) b.verdict[i] = TC_OK; // nat44_ingress never drops
+        const bool ip4 = len >= 34 && h.b16(12) == ETH_P_IP_LE;
+        if (ip4 && (h.b8(14) & 0x0f) != 5) { // options: fields are not at fixed offsets (rare)
+            nat_ingress_one(c, bs, p, len, b.now);
+            continue;
+        }
+        const u32 saddr = h.b32(26), daddr = h.b32(30), proto = h.b8(23);
+        u16 sport = 0, dport = 0;
+        bool go = ip4;
+        if (proto == 6) {
+            go = go && len >= 54;
+            sport = h.b16(34), dport = h.b16(36);
+        } else if (proto == 17) {
+            go = go && len >= 42;
+            sport = h.b16(34), dport = h.b16(36);
+        } else if (proto == 1) {
+            go = go && len >= 42;
+            dport = h.b16(38); // the echo id is the "destination port" of a reply (bpf/nat44.c:845-848)
+        } else {
+            go = false;
+        }
+        u64 rk[2];
+        rk[0] = (u64)saddr | ((u64)daddr << 32);
+        rk[1] = (u64)sport | ((u64)dport << 16) | ((u64)proto << 32);
+        // ---- nat_reverse: 32-byte slot = key, then the original tuple ----
+        u64 ok[2] = {0, 0};
+        bool have = false;
+        if (go && rk[0] < K_BUSY) {
+            const u8 *s0 = tbl_slot(c.reverse, tbl_hash<2>(rk) & c.reverse.mask);
+            U256 r = ldg256(s0);
+            const u64 w0 = (u64)r.w[0] | ((u64)r.w[1] << 32), w1 = (u64)r.w[2] | ((u64)r.w[3] << 32);
+            if (w0 == rk[0] && w1 == rk[1]) {
+                have = true;
+            } else if (w0 != K_EMPTY) { // collision: the general probe loop
+                const u8 *rs = tbl_find<2, true>(c.reverse, rk);
+                if (rs) {
+                    r = ldg256(rs);
+                    have = true;
+                }
+            }
+            ok[0] = (u64)r.w[4] | ((u64)r.w[5] << 32);
+            ok[1] = (u64)r.w[6] | ((u64)r.w[7] << 32);
+        }
+        if (go && !have) n_passed++; // no mapping: to the stack untouched (:861-867)
+        // ---- nat_sessions: sector 0 (key, translation, last_seen), then orig_ip + state from sector 1 ----
+        u8 *ses = nullptr;
+        uint4 tr = make_uint4(0, 0, 0, 0);
+        uint2 os = make_uint2(0, 0); // orig_ip, state word
+        if (have && ok[0] < K_BUSY) {
+            u8 *s0 = tbl_slot(c.sessions, tbl_hash<2>(ok) & c.sessions.mask);
+            const U256 s = ldg256(s0);
+            os = *(const uint2 *)(s0 + SES_ORIG_IP); // issued with the probe: one round trip, not two
+            const u64 w0 = (u64)s.w[0] | ((u64)s.w[1] << 32), w1 = (u64)s.w[2] | ((u64)s.w[3] << 32);
+            tr = make_uint4(s.w[4], s.w[5], s.w[6], s.w[7]);
+            if (w0 == ok[0] && w1 == ok[1]) {
+                ses = s0;
+            } else if (w0 != K_EMPTY) {
+                ses = tbl_find<2, false>(c.sessions, ok);
+                if (ses) {
+                    tr = *(const uint4 *)(ses + SES_NAT_IP);
+                    os = *(const uint2 *)(ses + SES_ORIG_IP);
+                }
+            }
+        }
+        if (have && !ses) { // stale reverse entry: one frame deletes it (sessions_expired), the others miss (:871-876)
+            if (tbl_erase<2>(c.reverse, rk))
+                bstats_add(bs, ST_NAT_EXPIRED, 1);
+            else
+                n_passed++;
+        }
+        if (ses) {
+            if (((u64)tr.z | ((u64)tr.w << 32)) != b.now) *(u64 *)(ses + SES_LAST_SEEN) = b.now;
+            ses_count(ses, SES_IN_LO, len);
+            if (proto == 6) { // :885-895; CLOSING(3) is absorbing, NEW(0) -> ESTABLISHED(1) on ack
+                const u32 tf = h.b8(47);
+                const bool finrst = (tf & 0x05) != 0, ack = (tf & 0x10) != 0;
+                u32 cur = os.y;
+                while (finrst || ack) {
+                    const u32 st = cur & 0xff, nst = finrst ? 3u : (st == 0 ? 1u : st);
+                    if (nst == st) break;
+                    const u32 prev = atomicCAS((u32 *)(ses + SES_STATE), cur, (cur & ~0xffu) | nst);
+                    if (prev == cur) break;
+                    cur = prev;
+                }
+            }
+            const u32 new_ip = os.x;
+            const u16 new_port = (u16)(tr.y >> 16); // orig_port
+            h.s32(30, new_ip);
+            h.s16(24, csum_upd32(h.b16(24), daddr, new_ip));
+            if (proto == 6) {
+                h.s16(36, new_port);
+                u16 ck = csum_upd32(h.b16(50), daddr, new_ip);
+                h.s16(50, csum_upd16(ck, dport, new_port));
+            } else if (proto == 17) {
+                h.s16(36, new_port);
+                u16 ck = h.b16(40);
+                if (ck != 0) {
+                    ck = csum_upd32(ck, daddr, new_ip);
+                    ck = csum_upd16(ck, dport, new_port);
+                    if (ck == 0) ck = 0xffff;
+                    h.s16(40, ck);
+                }
+            } else {
+                h.s16(38, new_port);
+                h.s16(36, csum_upd16(h.b16(36), dport, new_port));
+            }
+            if (wide) {
+                stg256(p, &h.w[0]);
+                if (proto == 6)
+                    stg256(p + 32, &h.w[8]);
+                else
+                    hdr_store_chunk(h, p, 2);
+            } else {
+                hdr_store_chunk(h, p, 1);
+                hdr_store_chunk(h, p, 2);
+                if (proto == 6) hdr_store_chunk(h, p, 3);
+            }
+            n_dnat++;
+        }
+    }
+    __syncwarp();
+    warp_stat_flush(bs, ST_NAT_DNAT, n_dnat);
+    warp_stat_flush(bs, ST_NAT_PASSED, n_passed);
     bstats_flush(bs, c.stats);
 }
 

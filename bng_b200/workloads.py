@@ -28,6 +28,9 @@ ALGO_BYTES = {
     "pipeline_64": 405,
     "qos_64": 64 + 36 + 16 + 1,
     "dhcp": 748,
+    # downstream direction, counted the way §8d counts the upstream programs:
+    "nat_ingress_64": 64 + 64 + (16 + 16) + (16 + 80) + 24 + 1,  # frame r/w, nat_reverse, nat_sessions, write-back, verdict
+    "qos_egress_64": 64 + 36 + 16 + 1 + 4,                       # as qos_64 plus the priority mark
 }
 
 
@@ -44,6 +47,7 @@ class Workload:
     prewarm: list = field(default_factory=list)  # [(prog, headers, lens)] run once before timing
     n_subs_local: int = 0
     info: dict = field(default_factory=dict)
+    derive: object = None  # callable(list of prewarm arenas after their programs ran) -> (headers, lens)
 
     @property
     def n(self):
@@ -120,6 +124,32 @@ def nat(n: int, rank=0, world=1, n_subs=16_384, flows_per_sub=64, cold=False, se
     return w
 
 
+def nat_ingress(n: int, rank=0, world=1, n_subs=16_384, flows_per_sub=64, seed=0xB2000003) -> Workload:
+    """SURVEY.md §8(f)-1, downstream half of config #3: return traffic of the 1 M pre-created flows (DNAT: reverse
+    lookup, session lookup, TCP state, rewrite).  The replies are derived from what nat44_egress made of each
+    flow's first frame: addresses and ports swapped, so the destination is the flow's public (address, port)."""
+    w = nat(n, rank, world, n_subs, flows_per_sub, cold=False, seed=seed)
+    w.name, w.prog = "nat_ingress_64", "nat44_ingress"
+    n_flows = w.prewarm[0][1].shape[0]
+    pick = _pick(seed + 19 + rank, n, n_flows)
+
+    def derive(translated):
+        t = translated[0].reshape(-1, 64)
+        out = t.copy()
+        out[:, 0:6], out[:, 6:12] = t[:, 6:12], t[:, 0:6]
+        out[:, 26:30], out[:, 30:34] = t[:, 30:34], t[:, 26:30]
+        l4 = (t[:, 23] == 6) | (t[:, 23] == 17)
+        out[l4, 34:36], out[l4, 36:38] = t[l4, 36:38], t[l4, 34:36]
+        out[t[:, 23] == 6, 47] = 0x10  # ACK: NEW -> ESTABLISHED on the first reply, then steady
+        out[t[:, 23] == 1, 34] = 0     # echo reply
+        return out[pick], np.full(n, 64, np.uint32)
+
+    w.derive = derive
+    w.headers = np.zeros((n, 64), np.uint8)  # placeholder until derive() runs (after the prewarm)
+    w.lens = np.full(n, 64, np.uint32)
+    return w
+
+
 def pipeline(n: int, rank=0, world=1, n_subs=10_000, flows_per_sub=64, imix=True, seed=0xB2000004) -> Workload:
     """Config #4: antispoof -> NAT44 -> QoS over 10 k subscribers (binding + port block + upload bucket with
     the reference's policy tiers round-robin), 64 pre-warmed flows each, IMIX 7:4:1 or all-64 B frames,
@@ -146,14 +176,19 @@ def pipeline(n: int, rank=0, world=1, n_subs=10_000, flows_per_sub=64, imix=True
     return w
 
 
-def qos(n: int, rank=0, world=1, n_subs=10_000, seed=0xB2000006) -> Workload:
+def qos(n: int, rank=0, world=1, n_subs=10_000, seed=0xB2000006, egress=False) -> Workload:
+    """qos_ingress_prog keyed on the source address (upload) or — egress=True, SURVEY.md §8(f)-1 — qos_egress_prog
+    keyed on the destination address (download buckets, priority mark)."""
     subs = local_subscribers(n_subs, rank, world)
-    qk, qv = S.qos_buckets(n_subs, upload=True)
-    w = Workload("qos_64", "qos_ingress_prog")
-    w.maps = [("qos_ingress", qk[subs], qv[subs])]
+    qk, qv = S.qos_buckets(n_subs, upload=not egress)
+    w = Workload("qos_egress_64" if egress else "qos_64", "qos_egress_prog" if egress else "qos_ingress_prog")
+    w.maps = [("qos_egress" if egress else "qos_ingress", qk[subs], qv[subs])]
     sub = subs[_pick(seed + rank, n, len(subs))]
     lens = np.full(n, 64, np.uint32)
-    w.headers = S.ipv4_headers(S.sub_mac_key(sub), np.uint64(GW_MAC), S.sub_ip(sub), np.uint32(0x08080808), 17, 5000, 53, lens)
+    if egress:
+        w.headers = S.ipv4_headers(np.uint64(GW_MAC), S.sub_mac_key(sub), np.uint32(0x08080808), S.sub_ip(sub), 17, 53, 5000, lens)
+    else:
+        w.headers = S.ipv4_headers(S.sub_mac_key(sub), np.uint64(GW_MAC), S.sub_ip(sub), np.uint32(0x08080808), 17, 5000, 53, lens)
     w.lens, w.n_subs_local = lens, len(subs)
     return w
 
@@ -219,7 +254,9 @@ BUILDERS = {
     "antispoof_64": antispoof,
     "nat_steady_64": lambda n, r, wd: nat(n, r, wd, cold=False),
     "nat_cold_64": lambda n, r, wd: nat(n, r, wd, cold=True),
+    "nat_ingress_64": nat_ingress,
     "qos_64": qos,
+    "qos_egress_64": lambda n, r, wd: qos(n, r, wd, egress=True),
     "dhcp": dhcp,
 }
 

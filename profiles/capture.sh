@@ -27,7 +27,7 @@ SMI=$!
 python bench.py > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err
 kill $SMI
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/${R}_bench_reference.json 2> gpurun_out/${R}_bench_reference.err
-for w in pipeline_64 antispoof_64 nat_steady_64 nat_cold_64 qos_64 dhcp; do
+for w in pipeline_64 antispoof_64 nat_steady_64 nat_cold_64 nat_ingress_64 qos_64 qos_egress_64 dhcp; do
     python bench.py --workload $w --steps 10 > gpurun_out/${R}_bench_$w.json 2> gpurun_out/${R}_bench_$w.err
 done
 echo done

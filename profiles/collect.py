@@ -63,7 +63,8 @@ def main():
                 traffic[wl] = {label: b}
     json.dump(traffic, open(os.path.join(DST, "ncu_traffic.json"), "w"), indent=1)
 
-    names = ["", "_pipeline_64", "_antispoof_64", "_nat_steady_64", "_nat_cold_64", "_qos_64", "_dhcp"]
+    names = ["", "_pipeline_64", "_antispoof_64", "_nat_steady_64", "_nat_cold_64", "_nat_ingress_64", "_qos_64", "_qos_egress_64",
+             "_dhcp"]
     lines = [f"# Measured on B200 — round {R}", "",
              "One `python bench.py --workload W` line each (`profiles/%s_bench_W.json`), 2^22 frames per step unless the" % R,
              "workload holds fewer; `value` = device-resident throughput, `e2e` = through the C ABI from a pinned host arena.",
