@@ -12,6 +12,7 @@
 
 #include "../../bng_b200/host/bng_dhcp_slow.hpp"
 #include "../../bng_b200/host/bng_host.hpp"
+#include "../../bng_b200/host/bng_nat_log.hpp"
 
 using namespace bng;
 
@@ -36,6 +37,15 @@ static int g_fail = 0, g_checks = 0;
         }                                                                                                     \
     } while (0)
 #define CHECK_ERR(e, text) CHECK((e).what() == std::string(text))
+#define CHECK_STR(a, b)                                                                                    \
+    do {                                                                                                   \
+        g_checks++;                                                                                        \
+        std::string sa = (a), sb = (b);                                                                    \
+        if (sa != sb) {                                                                                    \
+            g_fail++;                                                                                      \
+            fprintf(stderr, "FAIL %s:%d: %s\n  got:  %s\n  want: %s\n", __FILE__, __LINE__, #a, sa.c_str(), sb.c_str()); \
+        }                                                                                                  \
+    } while (0)
 
 static std::vector<uint8_t> bytes(const char *s) { return std::vector<uint8_t>(s, s + strlen(s)); }
 
@@ -358,6 +368,23 @@ static void test_gpu_roundtrips() {
     CHECK(eim.ok() && eim->ExternalPort == 1024 && eim->RefCount == 1);
     auto log = nm->DrainLog();
     CHECK(log.size() == 1 && log[0].EventType == nat::NATLogSessionCreate && log[0].SubscriberID == 1);
+    { // GPU ring -> host -> compliance log line: a second new flow of the same subscriber
+        memcpy(f, hdr, sizeof(hdr));
+        f[35] = 0x41; // source port 40001
+        f[47] = 0x10, f[50] = 0xab, f[51] = 0xcd;
+        b.now_ns = 2000000000ull;
+        CHECK_EQ(bng_prog_run(be->ctx, bng_prog_id(be->ctx, "nat44_egress"), &b), 0);
+        std::ostringstream sink;
+        nat::LoggerConfig lc;
+        lc.Format = nat::LogFormat::Syslog;
+        nat::Logger lg(lc, &sink, [](int64_t *s, uint32_t *nsec) { *s = 1700000000, *nsec = 0; });
+        lg.wire_order = true;
+        CHECK_EQ(nat::PumpLog(*nm, lg), 1u);
+        lg.Flush();
+        CHECK_STR(sink.str(), std::string("2023-11-14T22:13:20Z NAT session_create: subscriber=1 private=100.64.0.9:40001 "
+                                         "public=203.0.113.1:1025 dest=8.8.8.8:443 proto=tcp duration=0ms\n"));
+        CHECK_EQ(nat::PumpLog(*nm, lg), 0u);
+    }
     CHECK(!nm->DeallocateNAT(IPv4(100, 64, 0, 9)));
     CHECK(bng_map_lookup(be->ctx, be->Map("subscriber_nat"), &ipk, &sn) != 0);
 
@@ -529,11 +556,78 @@ static void test_dhcp_slow_path() {
     CHECK_ERR(none.HandleDHCP(req.data(), req.size()).err, "no pool available for client");
 }
 
+// ---- NAT compliance log lines (bng_nat_log.hpp), formats of pkg/nat/logging.go:416-522 ----
+static void test_nat_log_formats() {
+    nat::LogEntry e;
+    memset(&e, 0, sizeof(e));
+    e.EventType = nat::NATLogSessionCreate;
+    e.SubscriberID = 7;
+    e.PrivateIP = 0x09004064u;  // bytes 64 40 00 09 = 100.64.0.9 on the wire, as the u32 the Go struct holds
+    e.PublicIP = 0x017100CBu;   // 203.0.113.1
+    e.DestIP = 0x08080808u;
+    e.PrivatePort = 0x409C;     // bytes 9c 40 = 40000
+    e.PublicPort = 0x0004;      // bytes 04 00 = 1024
+    e.DestPort = 0xBB01;        // 443
+    e.Protocol = 6;
+    auto clock = [](int64_t *s, uint32_t *ns) { *s = 1700000000, *ns = 123450000; };
+    auto line = [&](nat::LogFormat f, bool wire) {
+        std::ostringstream sink;
+        nat::LoggerConfig c;
+        c.Format = f;
+        nat::Logger l(c, &sink, clock);
+        l.wire_order = wire;
+        l.LogFromBPF(e);
+        CHECK_EQ(l.Buffered(), 1u);
+        l.Flush();
+        CHECK_EQ(l.Buffered(), 0u);
+        return sink.str();
+    };
+    // the reference's conventions: keyToIP(BigEndian) of the little-endian-loaded field, ports as loaded
+    CHECK_STR(line(nat::LogFormat::JSON, false),
+             std::string("{\"timestamp\":\"2023-11-14T22:13:20.12345Z\",\"event_type\":\"session_create\",\"subscriber_id\":7,"
+                         "\"private_ip\":\"9.0.64.100\",\"private_port\":16540,\"public_ip\":\"1.113.0.203\",\"public_port\":4,"
+                         "\"protocol\":\"tcp\",\"dest_ip\":\"8.8.8.8\",\"dest_port\":47873}\n"));
+    // ... and what was on the wire
+    CHECK_STR(line(nat::LogFormat::Syslog, true),
+             std::string("2023-11-14T22:13:20Z NAT session_create: subscriber=7 private=100.64.0.9:40000 public=203.0.113.1:1024 "
+                         "dest=8.8.8.8:443 proto=tcp duration=0ms\n"));
+    CHECK_STR(line(nat::LogFormat::CSV, true),
+             std::string("2023-11-14T22:13:20Z,session_create,7,100.64.0.9,40000,203.0.113.1,1024,8.8.8.8,443,tcp,0,0,0\n"));
+    CHECK_STR(line(nat::LogFormat::NEL, true),
+             std::string("{\"age\":0,\"body\":{\"dest_ip\":\"8.8.8.8\",\"dest_port\":443,\"event\":\"session_create\",\"private_ip\":"
+                         "\"100.64.0.9\",\"private_port\":40000,\"protocol\":\"tcp\",\"public_ip\":\"203.0.113.1\",\"public_port\":1024,"
+                         "\"subscriber\":7},\"type\":\"NAT\"}\n"));
+    CHECK_STR(std::string(nat::Logger::bpfEventTypeToString(5)), std::string("port_exhaustion"));
+    CHECK_STR(std::string(nat::Logger::bpfEventTypeToString(99)), std::string("unknown"));
+    CHECK_STR(nat::Logger::protocolToString(47), std::string("proto_47"));
+    { // omitempty: zero ports / subscriber vanish from the JSON; a full buffer flushes by itself; disabled = silent
+        nat::LogEntry z;
+        memset(&z, 0, sizeof(z));
+        z.EventType = nat::NATLogALGTrigger, z.Protocol = 17;
+        std::ostringstream sink;
+        nat::LoggerConfig c;
+        c.BufferSize = 2;
+        nat::Logger l(c, &sink, [](int64_t *s, uint32_t *ns) { *s = 0, *ns = 0; });
+        l.LogFromBPF(z);
+        CHECK(sink.str().empty());
+        l.LogFromBPF(z);
+        CHECK_EQ(l.linesWritten, 2u);
+        CHECK_STR(sink.str().substr(0, sink.str().find('\n') + 1),
+                 std::string("{\"timestamp\":\"1970-01-01T00:00:00Z\",\"event_type\":\"alg_trigger\",\"private_ip\":\"0.0.0.0\","
+                             "\"public_ip\":\"0.0.0.0\",\"protocol\":\"udp\",\"dest_ip\":\"0.0.0.0\"}\n"));
+        c.Enabled = false;
+        nat::Logger off(c, &sink);
+        off.LogFromBPF(z);
+        CHECK_EQ(off.Buffered(), 0u);
+    }
+}
+
 int main(int argc, char **argv) {
     std::string mode = argc > 1 ? argv[1] : "cpu";
     test_conversions();
     test_dhcp_pool();
     test_dhcp_slow_path();
+    test_nat_log_formats();
     test_loader_unloaded();
     test_nat_allocator();
     test_qos_bookkeeping();

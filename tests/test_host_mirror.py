@@ -20,7 +20,8 @@ def _stale(binary, deps):
 
 
 def build_host_test():
-    hdrs = [os.path.join(HOST, "bng_host.hpp"), os.path.join(HOST, "bng_dhcp_slow.hpp"), os.path.join(ROOT, "include", "bng_b200.h")]
+    hdrs = [os.path.join(HOST, h) for h in ("bng_host.hpp", "bng_dhcp_slow.hpp", "bng_nat_log.hpp")] + \
+        [os.path.join(ROOT, "include", "bng_b200.h")]
     lib = ["-L" + os.path.join(ROOT, "bng_b200"), "-lbng_b200"]
     if _stale(BIN, [SRC] + hdrs):
         subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", SRC, "-o", BIN] + lib + ["-Wl,-rpath,$ORIGIN/../../bng_b200"], check=True)
