@@ -33,29 +33,12 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
     const u32 as_cfg = st.as_cfg, nflags = st.nat_flags;
     const u32 lane = threadIdx.x & 31;
     u32 n_allowed = 0, n_snat = 0;
-    // warp-uniform trip count: every lane stays in the loop, inactive lanes are predicated off.
-    // Where the NEXT trip's frame lives (len[], off16[]) is fetched one trip ahead: it is the first link
-    // of the per-frame dependent chain and costs two registers to take off it.
-    u32 base = blockIdx.x * BLOCK + (threadIdx.x & ~31u);
-#if BNG_CLASSIFY_LOOKAHEAD
-    u32 len_n = base + lane < b.n ? b.len[base + lane] : 0;
-    u8 *p_n = base + lane < b.n ? frame_ptr(b, base + lane) : b.pkts;
-#endif
-    for (; base < b.n; base += gridDim.x * BLOCK) {
+    // warp-uniform trip count: every lane stays in the loop, inactive lanes are predicated off
+    for (u32 base = blockIdx.x * BLOCK + (threadIdx.x & ~31u); base < b.n; base += gridDim.x * BLOCK) {
         const u32 i = base + lane;
         const bool act = i < b.n;
-#if BNG_CLASSIFY_LOOKAHEAD
-        const u32 len = len_n;
-        u8 *p = p_n;
-        {
-            const u32 in = i + gridDim.x * BLOCK;
-            len_n = in < b.n ? b.len[in] : 0;
-            p_n = in < b.n ? frame_ptr(b, in) : b.pkts;
-        }
-#else
         const u32 len = act ? b.len[i] : 0;
         u8 *p = act ? frame_ptr(b, i) : b.pkts;
-#endif
         const bool wide = __all_sync(0xffffffffu, !act || FRAME_WIDE_OK(b, p));
         Hdr64 h;
         hdr_load_wide(h, p, len, wide);
