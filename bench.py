@@ -244,6 +244,11 @@ def run_gpu(a):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: whatever native libraries print there while we run (NCCL's version
+    # banner, for one) goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     numa = bind_to_gpu_numa_node(local)  # pinned host buffers must live next to the GPU's PCIe root
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -469,7 +474,8 @@ def run_gpu(a):
                                 "qos_dropped": int(stats_global[7].item())},
             "lru_overflow": int(dp.lru_overflow), "events_lost": int(dp.events_lost),
         }
-        print(json.dumps(out), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     dp.close()
     if world > 1:
         dist.destroy_process_group()
