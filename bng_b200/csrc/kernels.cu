@@ -109,24 +109,6 @@ __global__ void __launch_bounds__(BLOCK)
 }
 
 // ---------------------------------------------------------------------------
-// nat44_egress: classify (generic path: any ihl, fields read from memory)
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(BLOCK)
-    k_nat_eg_classify(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b, u32 *skey, u32 *sval) {
-    __shared__ BlockStats bs;
-    bstats_init(bs);
-    for (u32 i = blockIdx.x * BLOCK + threadIdx.x; i < b.n; i += gridDim.x * BLOCK) {
-        u32 len = b.len[i];
-        u8 *p = frame_ptr(b, i);
-        NatOut o = nat_egress_one<false>(c, bs, p, len, i, b.now);
-        b.verdict[i] = (u8)o.verdict;
-        skey[i] = o.order_key;
-        sval[i] = i | MISS_FLAG;
-    }
-    bstats_flush(bs, c.stats);
-}
-
-// ---------------------------------------------------------------------------
 // nat44_ingress, nat44_hairpin_xdp
 // ---------------------------------------------------------------------------
 // Header in registers, whole-sector probes (nat_reverse slot = key + original tuple in one 256-bit load,
