@@ -372,29 +372,38 @@ def run_gpu(a):
                 "kernels_ms": {k: round(v[1] / v[0], 4) for k, v in prof.items()}}
 
     # ---- end to end through the C ABI with pinned host buffers ----
+    # One call = one batch of n_e frames (the first n_e of the workload).  The batch is capped at --e2e-frames
+    # (2^20) because what bounds this leg is the host side: behind the box's IOMMU the GPU's scattered header
+    # reads need the arena in 2 MB pages, and a 1.6 GB arena often cannot get them all (72 vs 290 Mpps seen).
     e2e_steps = max(1, min(a.steps, a.e2e_steps))
-    arena_h = host_arena(total16 * 16 + 64, a.arena)
+    n_e = min(n, max(1, a.e2e_frames))
+    lens_e, hdrs_e = wl.lens[:n_e], wl.headers[:n_e]
+    off16_e = off16[:n_e] if off16 is not None else None
+    total16_e = total16 if n_e == n else (int(off16[n_e]) if off16 is not None else n_e * stride // 16)
+    arena_h = host_arena(total16_e * 16 + 64, a.arena)
+
     def host_like(t):
         h = host_arena(t.numel() * t.element_size(), a.arena).view(t.dtype)[: t.numel()]
         h.copy_(t)
         return h
 
-    len_h = host_like(torch.from_numpy(wl.lens.astype(np.int32)))
-    off_h = host_like(torch.from_numpy(off16.astype(np.int32))) if off16 is not None else None
-    verdict_h = host_like(torch.zeros(n, dtype=torch.uint8))
-    hdr_h = torch.from_numpy(wl.headers)
-    len0_h = torch.from_numpy(wl.lens.astype(np.int32))
-    h16 = arena_h[: total16 * 16].view(total16, 16)
-    gidx_h = gidx.reshape(-1).cpu() if off16 is not None else None
+    len_h = host_like(torch.from_numpy(lens_e.astype(np.int32)))
+    off_h = host_like(torch.from_numpy(off16_e.astype(np.int32))) if off16 is not None else None
+    verdict_h = host_like(torch.zeros(n_e, dtype=torch.uint8))
+    hdr_h = torch.from_numpy(np.ascontiguousarray(hdrs_e))
+    len0_h = torch.from_numpy(lens_e.astype(np.int32))
+    h16 = arena_h[: total16_e * 16].view(total16_e, 16)
+    gidx_h = gidx[:n_e].reshape(-1).cpu() if off16 is not None else None
 
     def restore_host():
         if off16 is None:
-            arena_h[: n * stride].view(n, stride)[:, :hw] = hdr_h
+            arena_h[: n_e * stride].view(n_e, stride)[:, :hw] = hdr_h
         else:
             h16.index_copy_(0, gidx_h, hdr_h.view(-1, 16))
         len_h.copy_(len0_h)
 
     arena_bytes = total16 * 16
+    arena_bytes_e = total16_e * 16
     tc_prog = wl.prog != "dhcp_fastpath_prog"
     hb = 64 if tc_prog else 448  # bytes of each frame a program can touch = what crosses PCIe from a pinned arena
 
@@ -416,26 +425,26 @@ def run_gpu(a):
         et = torch.tensor([tot], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(et, op=dist.ReduceOp.MAX)
-        return world * n * e2e_steps / float(et.item()) / 1e6
+        return world * n_e * e2e_steps / float(et.item()) / 1e6
 
     # (a) the frames as they sit in the host arena (full frames, IMIX on 64-byte boundaries)
-    e2e_val = e2e_run(arena_h, off_h, stride, restore_host, arena_bytes)
-    per_frame_in = float(np.minimum(wl.lens, hb).mean())
-    h2d = int(n * per_frame_in) + n * 4 + (n * 4 if off16 is not None else 0)
-    d2h = int(n * (per_frame_in - (16 if tc_prog else 0))) + n + (n * 4 if not tc_prog else 0)
+    e2e_val = e2e_run(arena_h, off_h, stride, restore_host, arena_bytes_e)
+    per_frame_in = float(np.minimum(lens_e, hb).mean())
+    h2d = int(n_e * per_frame_in) + n_e * 4 + (n_e * 4 if off16 is not None else 0)
+    d2h = int(n_e * (per_frame_in - (16 if tc_prog else 0))) + n_e + (n_e * 4 if not tc_prog else 0)
     e2e_extra = None
     if tc_prog and wl.imix:
         # (b) header-split receive: the NIC put the first 64 bytes of every frame in a contiguous ring
         # (len[] still carries the full frame length); that ring is all the TC programs ever touch
-        ring_h = host_arena(n * 64, a.arena)
+        ring_h = host_arena(n_e * 64, a.arena)
 
         def restore_ring():
-            ring_h.view(n, 64)[:, :hw] = hdr_h
+            ring_h.view(n_e, 64)[:, :hw] = hdr_h
             len_h.copy_(len0_h)
 
-        v = e2e_run(ring_h, None, 64, restore_ring, n * 64)
+        v = e2e_run(ring_h, None, 64, restore_ring, n_e * 64)
         e2e_extra = {"value": round(v, 2), "unit": "Mpps", "layout": "header-split ring (64 B per frame, len = full frame)",
-                     "h2d_bytes_per_step": n * 64 + n * 4, "d2h_bytes_per_step": n * 64 + n}
+                     "h2d_bytes_per_step": n_e * 64 + n_e * 4, "d2h_bytes_per_step": n_e * 64 + n_e}
 
     # ---- counter reconciliation over NCCL (outside the timed region, as in production) ----
     ptr, nst = dp.stats_device_ptr()
@@ -466,7 +475,8 @@ def run_gpu(a):
             "wire_gbps": round(value * 1e6 * float(wl.lens.mean()) * 8 / 1e9, 1),
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": round(e2e_val, 2), "unit": "Mpps", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "layout": "pinned host arena, full frames; only the bytes a program can touch cross PCIe"},
+                    "steps": e2e_steps, "frames_per_step": n_e,
+                    "layout": "pinned host arena, full frames; only the bytes a program can touch cross PCIe"},
             "e2e_header_split": e2e_extra, "host_affinity": numa,
             "gpu_launches": int(launches), "clocks": clocks,
             "verdict_drop_fraction_last_step": round(drops / n, 4),
@@ -516,6 +526,7 @@ def main():
                     help="dhcp_slow = BASELINE config #1: the DHCP slow path (CPU only, plumbing; no GPU involved)")
     ap.add_argument("--frames", type=int, default=1 << 22)
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-frames", type=int, default=1 << 20, help="frames per bng_prog_run call in the end-to-end leg")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--reference-capacities", action="store_true",
                     help="size every table for the reference's compile-time max_entries instead of the workload")
