@@ -766,6 +766,10 @@ static cudaError_t group_by_key(Launcher &L, u32 n, u64 key_space, Grouped *out)
     return cudaGetLastError();
 }
 
+// k_resolve walks one group per WARP and a batch of n frames can hold n groups: size its grid for n warps
+// (grid_for() still caps it at the resident-block limit), or a small batch leaves most of the GPU idle.
+#define WARP_PER_GROUP(n) ((u32)((u64)(n) * 32 > 0xFFFFFFFFull ? 0xFFFFFFFFull : (u64)(n) * 32))
+
 cudaError_t run_antispoof(Launcher &L, const DevCtx &c, const DevBatch &b) {
     LAUNCH(k_antispoof, b.n, 8, c, b);
     return cudaGetLastError();
@@ -778,9 +782,9 @@ cudaError_t run_qos(Launcher &L, const DevCtx &c, const DevBatch &b, bool egress
     cudaError_t e = group_by_key(L, b.n, (u64)t.mask + 1, &g);
     if (e != cudaSuccess) return e;
     if (egress)
-        LAUNCH((k_resolve<false, true, true>), b.n, 4, c, b, g, L.s.qslot, L.s.counters);
+        LAUNCH((k_resolve<false, true, true>), WARP_PER_GROUP(b.n), 4, c, b, g, L.s.qslot, L.s.counters);
     else
-        LAUNCH((k_resolve<false, true, false>), b.n, 4, c, b, g, L.s.qslot, L.s.counters);
+        LAUNCH((k_resolve<false, true, false>), WARP_PER_GROUP(b.n), 4, c, b, g, L.s.qslot, L.s.counters);
     return cudaGetLastError();
 }
 
@@ -789,7 +793,7 @@ cudaError_t run_nat_egress(Launcher &L, const DevCtx &c, const DevBatch &b) {
     Grouped g;
     cudaError_t e = group_by_key(L, b.n, (u64)c.sub_nat.mask + 1, &g);
     if (e != cudaSuccess) return e;
-    LAUNCH((k_resolve<true, false, false>), b.n, 8, c, b, g, L.s.qslot, L.s.counters);
+    LAUNCH((k_resolve<true, false, false>), WARP_PER_GROUP(b.n), 8, c, b, g, L.s.qslot, L.s.counters);
     return cudaGetLastError();
 }
 
@@ -809,6 +813,6 @@ cudaError_t run_pipeline_up(Launcher &L, const DevCtx &c, const DevBatch &b) {
     Grouped g;
     cudaError_t e = group_by_key(L, b.n, space, &g);
     if (e != cudaSuccess) return e;
-    LAUNCH((k_resolve<true, true, false>), b.n, 8, c, b, g, L.s.qslot, L.s.counters);
+    LAUNCH((k_resolve<true, true, false>), WARP_PER_GROUP(b.n), 8, c, b, g, L.s.qslot, L.s.counters);
     return cudaGetLastError();
 }
