@@ -264,7 +264,8 @@ BUILDERS = {
 def sizing(wl: "Workload") -> dict:
     """bng_open capacities for this workload: the control plane sizes the tables for the subscribers and
     flows it provisions (2x head-room) instead of the reference's compile-time maxima."""
-    subs = max(1024, 2 * wl.n_subs_local)  # sparse subscriber tables: a second probe costs a memory round trip
+    headroom = int(os.environ.get("BNG_SUBS_HEADROOM", "2"))
+    subs = max(1024, headroom * wl.n_subs_local)  # sparse subscriber tables: a second probe costs a memory round trip
     flows = max(4096, 2 * int(wl.info.get("flows", 0)))
     return {"max_subscribers": subs, "max_nat_sessions": flows, "max_eim_mappings": flows}
 
