@@ -5,11 +5,12 @@
 // order.  Three phases run back to back on the context's stream:
 //   CLASSIFY  one thread per frame over a persistent grid (a multiple of the
 //             SM count).  The first 64 bytes of the frame are held in
-//             registers (4 x 128-bit loads), the first probe slot of every
-//             table the frame may need is fetched up front so the loads are in
+//             registers (2 x 256-bit loads, or 4 x 128-bit for unaligned
+//             frames), the first probe slot of every table the frame may need
+//             is fetched up front as whole 32-byte sectors so the loads are in
 //             flight together, and everything whose effect commutes is
-//             finished here: verdicts, session counters (atomics), the in-place
-//             SNAT rewrite (128-bit stores of the touched chunks).  Frames
+//             finished here: verdicts, session counters (one atomic), the
+//             in-place SNAT rewrite (whole-sector stores).  Frames
 //             whose effect depends on earlier frames of the same subscriber
 //             (new NAT flows, token-bucket decisions) only get an ordering key.
 //   GROUP     a stable LSD radix sort (8-bit digits) of (key, frame index)
@@ -18,11 +19,12 @@
 //             without a key never enter the sort, and every later kernel reads
 //             its element count from device memory, so an all-hit batch costs
 //             a few empty launches and no host round trip.
-//   RESOLVE   one warp per subscriber walks its group 32 frames at a time:
-//             lanes gather the frames' lengths in parallel, new flows are
-//             created in index order, and the token bucket is applied with
-//             warp-uniform fast paths (whole chunk passes / whole chunk drops)
-//             before falling back to a lane-by-lane scan.
+//   RESOLVE   one warp per subscriber walks its group 32 frames at a time
+//             (two chunks' loads in flight): lanes gather the frames' lengths
+//             in parallel, new flows are created in index order, and the
+//             token bucket is applied with warp-uniform fast paths (whole
+//             chunk passes / whole chunk drops) before falling back to a
+//             lane-by-lane scan.
 #include <string.h>
 
 #include "kernels.h"
