@@ -387,21 +387,28 @@ static int p_nat_egress(ora_pkt *p) { /* nat44_egress, :565-802 */
         ++*stat(M_NAT_STATS, NS_CREATED);
         natlog(1, ld32(sub, 24), sip, nip, sp, nport, dip, dp, proto, hairpin);
     }
-    st32(f, 26, nip); /* SNAT rewrite, :752-798 */
+    /* SNAT rewrite, :752-798.  The reference works on the packet in place and reads the old port / id
+     * back from memory AFTER it has stored the new address: with ihl < 5 the L4 header overlaps the IP
+     * header and that read returns address bytes — the order of loads and stores below is the reference's. */
+    st32(f, 26, nip);
     st16(f, 24, csum32(ld16(f, 24), sip, nip));
     if (proto == 6) {
+        u16 op = ld16(f, l4);
         st16(f, l4, nport);
-        st16(f, l4 + 16, csum16(csum32(ld16(f, l4 + 16), sip, nip), sp, nport));
+        st16(f, l4 + 16, csum32(ld16(f, l4 + 16), sip, nip));
+        st16(f, l4 + 16, csum16(ld16(f, l4 + 16), op, nport));
     } else if (proto == 17) {
+        u16 op = ld16(f, l4);
         st16(f, l4, nport);
-        u16 c = ld16(f, l4 + 6);
-        if (c) {
-            c = csum16(csum32(c, sip, nip), sp, nport);
-            st16(f, l4 + 6, c ? c : 0xffff);
+        if (ld16(f, l4 + 6)) {
+            st16(f, l4 + 6, csum32(ld16(f, l4 + 6), sip, nip));
+            st16(f, l4 + 6, csum16(ld16(f, l4 + 6), op, nport));
+            if (ld16(f, l4 + 6) == 0) st16(f, l4 + 6, 0xffff);
         }
     } else {
+        u16 oid = ld16(f, l4 + 4);
         st16(f, l4 + 4, nport);
-        st16(f, l4 + 2, csum16(ld16(f, l4 + 2), sp, nport));
+        st16(f, l4 + 2, csum16(ld16(f, l4 + 2), oid, nport));
     }
     ++*stat(M_NAT_STATS, NS_SNAT);
     return 0;
@@ -455,21 +462,25 @@ static int p_nat_ingress(ora_pkt *p) { /* nat44_ingress, :805-948 */
     }
     u32 nip = ld32(ses, 8);
     u16 nport = ld16(ses, 6);
-    st32(f, 30, nip);
+    st32(f, 30, nip); /* DNAT rewrite, :896-944: same in-place load/store order as the reference */
     st16(f, 24, csum32(ld16(f, 24), dip, nip));
     if (proto == 6) {
+        u16 op = ld16(f, l4 + 2);
         st16(f, l4 + 2, nport);
-        st16(f, l4 + 16, csum16(csum32(ld16(f, l4 + 16), dip, nip), dp, nport));
+        st16(f, l4 + 16, csum32(ld16(f, l4 + 16), dip, nip));
+        st16(f, l4 + 16, csum16(ld16(f, l4 + 16), op, nport));
     } else if (proto == 17) {
+        u16 op = ld16(f, l4 + 2);
         st16(f, l4 + 2, nport);
-        u16 c = ld16(f, l4 + 6);
-        if (c) {
-            c = csum16(csum32(c, dip, nip), dp, nport);
-            st16(f, l4 + 6, c ? c : 0xffff);
+        if (ld16(f, l4 + 6)) {
+            st16(f, l4 + 6, csum32(ld16(f, l4 + 6), dip, nip));
+            st16(f, l4 + 6, csum16(ld16(f, l4 + 6), op, nport));
+            if (ld16(f, l4 + 6) == 0) st16(f, l4 + 6, 0xffff);
         }
     } else {
+        u16 oid = ld16(f, l4 + 4);
         st16(f, l4 + 4, nport);
-        st16(f, l4 + 2, csum16(ld16(f, l4 + 2), dp, nport));
+        st16(f, l4 + 2, csum16(ld16(f, l4 + 2), oid, nport));
     }
     ++*stat(M_NAT_STATS, NS_DNAT);
     return 0;
