@@ -216,7 +216,12 @@ struct DevBatch {
     u32 stride;
     u64 now;
     u32 base; // index of frame 0 within the caller's batch (event records carry base + i)
-    u32 pad;
+    // Bytes of a frame that are physically present in its slot (0 = the whole frame): the programs'
+    // bounds checks run against min(len, cap) — the linear data area, data_end - data in the reference —
+    // while byte counters use len (skb->len).  Fixed-stride arenas have cap = stride, so a frame whose
+    // length claims more than its slot holds (a header-split receive ring) is parsed as far as the slot
+    // goes and can never reach into its neighbour.
+    u32 cap;
     u64 arena_len; // bytes addressable from pkts (0 = unknown: no access may run past a frame's 16-byte chunks)
 };
 // may the 64 bytes at p be read with 32-byte accesses?
@@ -457,6 +462,7 @@ __device__ __forceinline__ u8 *ev_reserve(const DevCtx &c, const EvRing &r, u32 
 // are read the way the eBPF programs read them: little-endian loads of wire
 // bytes.  Even offsets are 2-byte aligned, so u16 accesses are always legal.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ u32 frame_dlen(const DevBatch &b, u32 len) { return (b.cap && len > b.cap) ? b.cap : len; }
 __device__ __forceinline__ u8 *frame_ptr(const DevBatch &b, u32 i) {
     return b.pkts + (b.off16 ? (size_t)b.off16[i] * 16 : (size_t)i * b.stride);
 }

@@ -768,8 +768,14 @@ static u32 zc_chunk_frames() { // frames per pipeline chunk; BNG_ZC_CHUNK_LOG2 o
 }
 #define ZC_CHUNK (zc_chunk_frames())
 static int run_host_zero_copy(bng_ctx *c, int prog, bng_batch *bb, u8 *arena_dev) {
-    const u32 hb = prog == P_DHCP ? 448u : 64u; // bytes of a frame a program can touch
-    const u32 first_chunk = prog == P_DHCP ? 0u : 1u; // TC programs never write the Ethernet addresses
+    // Bytes of a frame a program can touch (hostio.cu): 96 for the TC programs (Ethernet + IPv4 with options + 20
+    // bytes of L4), 448 for dhcp_fastpath_prog.  Frames that ARE a fixed slot no larger than that (64-byte
+    // frames, a header-split receive ring) move as they are with the copy engines.
+    const bool tc = prog != P_DHCP;
+    const u32 hb_need = tc ? 96u : 448u;
+    const bool contiguous = !bb->off16 && bb->stride <= hb_need;
+    const u32 hb = contiguous ? bb->stride : hb_need;         // compact slot stride
+    const u32 first_chunk = tc ? 1u : 0u; // TC programs write below byte 16 only in flagged frames (ihl = 0)
     if (!c->s_in) {
         CU(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
         CU(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
@@ -790,7 +796,7 @@ static int run_host_zero_copy(bng_ctx *c, int prog, bng_batch *bb, u8 *arena_dev
             c->zc_hdr[i] = nullptr;
         }
         c->zc_hb = 0;
-        for (int i = 0; i < 2; i++) CU(c, cudaMalloc((void **)&c->zc_hdr[i], (size_t)ZC_CHUNK * hb));
+        for (int i = 0; i < 2; i++) CU(c, cudaMalloc((void **)&c->zc_hdr[i], (size_t)ZC_CHUNK * hb + 64));
         c->zc_hb = hb;
     }
     cudaStream_t sc = c->L.stream;
@@ -805,15 +811,12 @@ static int run_host_zero_copy(bng_ctx *c, int prog, bng_batch *bb, u8 *arena_dev
         if (bb->priority)
             CU(c, cudaMemcpyAsync(c->zc_prio[buf], bb->priority + base, (size_t)cn * 4, cudaMemcpyHostToDevice, c->s_in));
         u8 *chunk_arena = bb->off16 ? arena_dev : arena_dev + (size_t)base * bb->stride;
-        // frames that ARE their header slot (fixed stride == header bytes, e.g. 64-byte frames or a
-        // header-split receive ring) move with the copy engines; anything else is gathered by SMs
-        const bool contiguous = !bb->off16 && bb->stride == hb;
         if (contiguous) {
             CU(c, cudaMemcpyAsync(c->zc_hdr[buf], (u8 *)bb->pkts + (size_t)base * hb, (size_t)cn * hb, cudaMemcpyHostToDevice,
                                   c->s_in));
         } else {
             CU(c, run_gather_frames(c->s_in, c->L.num_sms, chunk_arena, bb->off16 ? c->zc_off[buf] : nullptr, c->zc_len[buf],
-                                    bb->stride, cn, hb, c->zc_hdr[buf], c->zc_len0[buf]));
+                                    bb->stride, cn, hb, tc, c->zc_hdr[buf], c->zc_len0[buf]));
             c->L.launches++;
         }
         CU(c, cudaEventRecord(c->ev_in[buf], c->s_in));
@@ -829,6 +832,7 @@ static int run_host_zero_copy(bng_ctx *c, int prog, bng_batch *bb, u8 *arena_dev
         b.stride = hb;
         b.now = bb->now_ns;
         b.base = base;
+        b.cap = hb; // bounds checks never look past a compact slot (a no-op for whole frames: hostio.cu)
         b.arena_len = (u64)cn * hb;
         int r = dispatch(c, prog, b);
         if (r) return r;
@@ -873,6 +877,7 @@ int bng_prog_run(bng_ctx *c, int prog, bng_batch *bb) {
     // bytes the kernels may touch from pkts: a fixed-stride arena holds n * stride; with an offset table
     // the caller's arena_bytes (16-byte units, possibly rounded up) says, and 0 means unknown
     b.arena_len = bb->off16 ? (bb->arena_bytes ? (u64)bb->arena_bytes * 16 - 15 : 0) : (u64)bb->n * bb->stride;
+    b.cap = bb->off16 ? 0u : bb->stride; // a fixed-stride slot holds at most stride bytes of its frame
     if (bb->mem == BNG_MEM_DEVICE) {
         b.pkts = (u8 *)bb->pkts;
         b.off16 = bb->off16;
@@ -883,10 +888,15 @@ int bng_prog_run(bng_ctx *c, int prog, bng_batch *bb) {
     }
     if (bb->mem != BNG_MEM_HOST) return -EINVAL;
     {
-        void *mapped = nullptr; // pinned (cudaHostAlloc / cudaHostRegister) arenas are read in place
-        if (cudaHostGetDevicePointer(&mapped, bb->pkts, 0) == cudaSuccess && mapped)
+        // Pinned (cudaHostAlloc / cudaHostRegister) arenas are read in place.  The pointer's registered type is
+        // what decides: on systems with HMM / ATS cudaHostGetDevicePointer() also succeeds for PAGEABLE memory,
+        // which the GPU would then reach through page faults.
+        cudaPointerAttributes at{};
+        void *mapped = nullptr;
+        if (cudaPointerGetAttributes(&at, bb->pkts) == cudaSuccess && at.type == cudaMemoryTypeHost &&
+            cudaHostGetDevicePointer(&mapped, bb->pkts, 0) == cudaSuccess && mapped)
             return run_host_zero_copy(c, prog, bb, (u8 *)mapped);
-        cudaGetLastError(); // pageable memory: fall back to whole-arena staging copies
+        cudaGetLastError(); // pageable memory: whole-arena staging copies
     }
     size_t arena = bb->off16 ? (size_t)bb->arena_bytes * 16 : (size_t)bb->n * bb->stride;
     if (arena == 0) return -EINVAL;

@@ -46,14 +46,15 @@ __device__ __forceinline__ void put_opt32(u8 *o, int &off, u8 code, u32 v_le) { 
     o[off++] = (u8)(v_le >> 24);
 }
 
-__device__ __forceinline__ int dhcp_one(const DevCtx &c, BlockStats &bs, u8 *p, u32 &len, u64 now) {
+// dlen: bytes of the frame present in its slot (every bounds check); len: the frame length (tail adjustment)
+__device__ __forceinline__ int dhcp_one(const DevCtx &c, BlockStats &bs, u8 *p, u32 &len, const u32 dlen, u64 now) {
     // ---- parse_packet_headers(), :352-428 ----
-    if (len < 14) return XDP_PASS_;
+    if (dlen < 14) return XDP_PASS_;
     u32 proto = rd16(p, 12);
     u32 l3 = 14, vlan_off = 0, vlan_id = 0, inner_id = 0;
     bool tagged = false;
     if (proto == 0x0081u || proto == 0xA888u) { // 802.1Q / 802.1ad
-        if (len < 18) return XDP_PASS_;
+        if (dlen < 18) return XDP_PASS_;
         tagged = true;
         vlan_id = bswap16(rd16(p, 14)) & 0x0FFF;
         vlan_off = 4;
@@ -61,7 +62,7 @@ __device__ __forceinline__ int dhcp_one(const DevCtx &c, BlockStats &bs, u8 *p, 
         l3 = 18;
         bstats_add(bs, ST_DHCP_VLAN, 1);
         if (proto == 0x0081u) {
-            if (len < 22) return XDP_PASS_;
+            if (dlen < 22) return XDP_PASS_;
             inner_id = bswap16(rd16(p, 18)) & 0x0FFF;
             vlan_off = 8;
             proto = rd16(p, 20);
@@ -69,13 +70,13 @@ __device__ __forceinline__ int dhcp_one(const DevCtx &c, BlockStats &bs, u8 *p, 
         }
     }
     if (proto != ETH_P_IP_LE) return XDP_PASS_;
-    if (l3 + 20 > len) return XDP_PASS_;
+    if (l3 + 20 > dlen) return XDP_PASS_;
     if (p[l3 + 9] != 17) return XDP_PASS_;
     u32 udp = l3 + (u32)(p[l3] & 0x0f) * 4;
-    if (udp + 8 > len) return XDP_PASS_;
+    if (udp + 8 > dlen) return XDP_PASS_;
     if (rd16(p, udp + 2) != 0x4300u) return XDP_PASS_; // bpf_htons(67)
     u32 dh = udp + 8;
-    if (dh + 240 > len) return XDP_PASS_;
+    if (dh + 240 > dlen) return XDP_PASS_;
 
     // ---- :627-645 ----
     if (p[dh] != 1) return XDP_PASS_;
@@ -83,7 +84,7 @@ __device__ __forceinline__ int dhcp_one(const DevCtx &c, BlockStats &bs, u8 *p, 
     bstats_add(bs, ST_DHCP_TOTAL, 1);
     u32 opts = dh + 240;
     u32 msg_type = 0;
-    if (opts + 12 <= len) { // get_dhcp_msg_type(), :216-250
+    if (opts + 12 <= dlen) { // get_dhcp_msg_type(), :216-250
         const u8 *o = p + opts;
         if (o[0] == 53 && o[1] == 1) msg_type = o[2];
         else if (o[1] == 53 && o[2] == 1) msg_type = o[3];
@@ -104,15 +105,15 @@ __device__ __forceinline__ int dhcp_one(const DevCtx &c, BlockStats &bs, u8 *p, 
         const u8 *s = tbl_find<1, false>(c.vlan_pools, &vk);
         if (s) a = s + c.vlan_pools.voff;
     }
-    if (!a && opts + 64 <= len) { // extract_circuit_id_fixed(), :267-323
+    if (!a && opts + 64 <= dlen) { // extract_circuit_id_fixed(), :267-323
         const u8 *o = p + opts;
         int cid_at = -1;
         u32 cid_len = 0;
         if (o[3] == 82) {
             u32 l82 = o[4];
-            if (l82 >= 4 && opts + 5 + l82 <= len && o[5] == 1) {
+            if (l82 >= 4 && opts + 5 + l82 <= dlen && o[5] == 1) {
                 u32 cl = o[6];
-                if (cl > 0 && cl <= 32 && opts + 7 + cl <= len) {
+                if (cl > 0 && cl <= 32 && opts + 7 + cl <= dlen) {
                     cid_at = 7;
                     cid_len = cl;
                 }
@@ -120,11 +121,11 @@ __device__ __forceinline__ int dhcp_one(const DevCtx &c, BlockStats &bs, u8 *p, 
         }
         if (cid_at < 0) {
             for (int pos = 12; pos < 20; pos++) {
-                if (o[pos] == 82 && opts + pos + 8 <= len) {
+                if (o[pos] == 82 && opts + pos + 8 <= dlen) {
                     u32 l82 = o[pos + 1];
                     if (l82 >= 4 && o[pos + 2] == 1) {
                         u32 cl = o[pos + 3];
-                        if (cl > 0 && cl <= 32 && opts + pos + 4 + cl <= len) {
+                        if (cl > 0 && cl <= 32 && opts + pos + 4 + cl <= dlen) {
                             cid_at = pos + 4;
                             cid_len = cl;
                             break;
@@ -220,7 +221,7 @@ __device__ __forceinline__ int dhcp_one(const DevCtx &c, BlockStats &bs, u8 *p, 
 
     // The options bounds check comes AFTER the header rewrite (:769): a frame
     // shorter than options+64 leaves here rewritten but XDP_PASSed.
-    if (opts + 64 > len) return XDP_PASS_;
+    if (opts + 64 > dlen) return XDP_PASS_;
 
     // ---- build_dhcp_options(), :519-602 ----
     u8 *o = p + opts;
@@ -302,7 +303,8 @@ __global__ void __launch_bounds__(DH_TILE) k_dhcp_fastpath(const __grid_constant
         const bool act = i < b.n;
         u32 len = act ? b.len[i] : 0;
         u8 *g = act ? frame_ptr(b, i) : b.pkts;
-        u32 nbytes = ((len < DH_SLOT ? len : DH_SLOT) + 15u) & ~15u;
+        const u32 present = frame_dlen(b, len);
+        u32 nbytes = ((present < DH_SLOT ? present : DH_SLOT) + 15u) & ~15u;
         if (nbytes > DH_SLOT) nbytes = DH_SLOT;
         // ---- stage in ----
         if (nbytes) {
@@ -326,7 +328,7 @@ __global__ void __launch_bounds__(DH_TILE) k_dhcp_fastpath(const __grid_constant
         phase ^= 1;
         // ---- the program, on the staged copy ----
         bool direct = false; // the program would reach past the staged bytes: run it on the frame itself
-        if (act && len > DH_SLOT) {
+        if (act && present > DH_SLOT) {
             u32 et = rd16(mine, 12), l3 = 14;
             if (et == 0x0081u || et == 0xA888u) {
                 l3 = 18;
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(DH_TILE) k_dhcp_fastpath(const __grid_constant
         }
         if (act) {
             const u32 l0 = len;
-            int v = dhcp_one(c, bs, direct ? g : mine, len, b.now);
+            int v = dhcp_one(c, bs, direct ? g : mine, len, frame_dlen(b, l0), b.now);
             b.verdict[i] = (u8)v;
             if (len != l0) b.len[i] = len;
         }

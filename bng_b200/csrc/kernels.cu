@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(BLOCK) k_antispoof(const __grid_constant__ Dev
     for (u32 base = blockIdx.x * BLOCK + (threadIdx.x & ~31u); base < b.n; base += gridDim.x * BLOCK) {
         const u32 i = base + lane;
         const bool act = i < b.n;
-        const u32 len = act ? b.len[i] : 0;
+        const u32 len = act ? frame_dlen(b, b.len[i]) : 0; // antispoof only bounds-checks: the bytes present
         const u8 *p = act ? frame_ptr(b, i) : b.pkts;
         Hdr64 h;
         hdr_load_wide(h, p, len, __all_sync(0xffffffffu, !act || FRAME_WIDE_OK(b, p)));
@@ -96,12 +96,13 @@ __global__ void __launch_bounds__(BLOCK)
     const Tbl &t = egress ? c.qos_eg : c.qos_in;
     for (u32 i = blockIdx.x * BLOCK + threadIdx.x; i < b.n; i += gridDim.x * BLOCK) {
         u32 len = b.len[i];
+        const u32 dlen = frame_dlen(b, len);
         const u8 *p = frame_ptr(b, i);
         Hdr64 h;
-        hdr_load_wide(h, p, len < 34 ? len : 34, __all_sync(__activemask(), FRAME_WIDE_OK(b, p)));
+        hdr_load_wide(h, p, dlen < 34 ? dlen : 34, __all_sync(__activemask(), FRAME_WIDE_OK(b, p)));
         u32 prio;
         bool prio_set;
-        u32 key = qos_classify_one(c, bs, t, h, len, egress != 0, &prio, &prio_set);
+        u32 key = qos_classify_one(c, bs, t, h, len, dlen, egress != 0, &prio, &prio_set);
         if (prio_set && b.priority) b.priority[i] = prio;
         b.verdict[i] = TC_OK;
         skey[i] = key;
@@ -125,27 +126,28 @@ __global__ void __launch_bounds__(BLOCK) k_nat_ingress(const __grid_constant__ D
         const u32 i = base + lane;
         const bool act = i < b.n;
         const u32 len = act ? b.len[i] : 0;
+        const u32 dlen = frame_dlen(b, len);
         u8 *p = act ? frame_ptr(b, i) : b.pkts;
         const bool wide = __all_sync(0xffffffffu, !act || FRAME_WIDE_OK(b, p));
         Hdr64 h;
-        hdr_load_wide(h, p, len, wide);
+        hdr_load_wide(h, p, dlen, wide);
         if (act) b.verdict[i] = TC_OK; // nat44_ingress never drops
-        const bool ip4 = len >= 34 && h.b16(12) == ETH_P_IP_LE;
+        const bool ip4 = dlen >= 34 && h.b16(12) == ETH_P_IP_LE;
         if (ip4 && (h.b8(14) & 0x0f) != 5) { // options: fields are not at fixed offsets (rare)
-            nat_ingress_one(c, bs, p, len, b.now);
+            nat_ingress_one(c, bs, p, len, dlen, b.now);
             continue;
         }
         const u32 saddr = h.b32(26), daddr = h.b32(30), proto = h.b8(23);
         u16 sport = 0, dport = 0;
         bool go = ip4;
         if (proto == 6) {
-            go = go && len >= 54;
+            go = go && dlen >= 54;
             sport = h.b16(34), dport = h.b16(36);
         } else if (proto == 17) {
-            go = go && len >= 42;
+            go = go && dlen >= 42;
             sport = h.b16(34), dport = h.b16(36);
         } else if (proto == 1) {
-            go = go && len >= 42;
+            go = go && dlen >= 42;
             dport = h.b16(38); // the echo id is the "destination port" of a reply (bpf/nat44.c:845-848)
         } else {
             go = false;
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(BLOCK) k_nat_hairpin_xdp(const __grid_constant
     for (u32 i = blockIdx.x * BLOCK + threadIdx.x; i < b.n; i += gridDim.x * BLOCK) {
         b.verdict[i] = 2;
         if (!(flags & NATF_HAIRPIN)) continue;
-        u32 len = b.len[i];
+        u32 len = frame_dlen(b, b.len[i]);
         const u8 *p = frame_ptr(b, i);
         if (len < 14 || rd16(p, 12) != ETH_P_IP_LE || len < 34) continue;
         if (!is_private_ip(rd32(p, 26))) continue;
@@ -568,7 +570,7 @@ __global__ void __launch_bounds__(BLOCK, (NAT && !QOS) ? 8 : 4) k_resolve(const 
                         u32 l = __ffs(mm) - 1;
                         mm &= mm - 1;
                         if (lane == l) {
-                            NatOut o = nat_egress_one<true>(c, bs, frame_ptr(b, idx), len, idx + b.base, b.now, &pend);
+                            NatOut o = nat_egress_one<true>(c, bs, frame_ptr(b, idx), len, frame_dlen(b, len), idx + b.base, b.now, &pend);
                             if (o.verdict == TC_SHOT) {
                                 b.verdict[idx] = TC_SHOT;
                                 dropped = true;

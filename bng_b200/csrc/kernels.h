@@ -49,9 +49,9 @@ cudaError_t run_dhcp_fastpath(Launcher &L, const DevCtx &c, const DevBatch &b);
 
 // header gather / scatter between a pinned host arena and a compact device copy (hostio.cu)
 cudaError_t run_gather_frames(cudaStream_t st, int num_sms, const u8 *arena, const u32 *off16, const u32 *len, u32 stride,
-                              u32 n, u32 hb, u8 *dst, u32 *dlen0);
-cudaError_t run_scatter_frames(cudaStream_t st, int num_sms, u8 *arena, const u32 *off16, const u32 *dlen0, u32 stride, u32 n,
-                               u32 hb, const u8 *src, u32 first_chunk);
+                              u32 n, u32 slot, bool tc, u8 *dst, u32 *need);
+cudaError_t run_scatter_frames(cudaStream_t st, int num_sms, u8 *arena, const u32 *off16, const u32 *need, u32 stride, u32 n,
+                               u32 slot, const u8 *src, u32 first_chunk);
 
 // table maintenance (tableops.cu); keys/values/results are device pointers
 enum { TOP_UPDATE = 0, TOP_LOOKUP = 1, TOP_DELETE = 2 };

@@ -37,14 +37,15 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
     for (u32 base = blockIdx.x * BLOCK + (threadIdx.x & ~31u); base < b.n; base += gridDim.x * BLOCK) {
         const u32 i = base + lane;
         const bool act = i < b.n;
-        const u32 len = act ? b.len[i] : 0;
+        const u32 len = act ? b.len[i] : 0;      // skb->len: byte counters, token bucket
+        const u32 dlen = frame_dlen(b, len);     // data_end - data: every bounds check
         u8 *p = act ? frame_ptr(b, i) : b.pkts;
         const bool wide = __all_sync(0xffffffffu, !act || FRAME_WIDE_OK(b, p));
         Hdr64 h;
-        hdr_load_wide(h, p, len, wide);
+        hdr_load_wide(h, p, dlen, wide);
 
         // ---- phase 1: keys, and the first probe of every table this frame may need ----
-        const bool ip4 = len >= 34 && h.b16(12) == ETH_P_IP_LE;
+        const bool ip4 = dlen >= 34 && h.b16(12) == ETH_P_IP_LE;
         const u32 saddr = h.b32(26), daddr = h.b32(30), proto = h.b8(23);
         const bool ihl5 = (h.b8(14) & 0x0f) == 5;
         u64 mk = mac_key(h, 6);
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
         s0.w[2] = s0.w[3] = 0;
         const u8 *bslot0 = tbl_slot(c.bindings, bi);
         u8 *sslot0 = tbl_slot(c.sessions, hi);
-        if (AS && len >= 14) bv.s = ldg256(bslot0);
+        if (AS && dlen >= 14) bv.s = ldg256(bslot0);
         if (ip4) {
             sw0 = *(const u64 *)tbl_slot(c.sub_nat, si);
             if (QOS) { // key and the mirrored rate_bps in one 16-byte load
@@ -87,11 +88,11 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
         // ---- phase 2: antispoof_ingress ----
         int v = TC_OK;
         if (AS) {
-            const u8 *bind = len >= 14 ? tbl_finish<1>(c.bindings, &mk, bi, (u64)bv.s.w[0] | ((u64)bv.s.w[1] << 32), true) : nullptr;
+            const u8 *bind = dlen >= 14 ? tbl_finish<1>(c.bindings, &mk, bi, (u64)bv.s.w[0] | ((u64)bv.s.w[1] << 32), true) : nullptr;
             __syncwarp();
             bv.has = bind != nullptr;
             if (bind && bind != bslot0) bv.s = ldg256(bind); // found on a later probe
-            v = antispoof_eval(c, bs, h, len, i + b.base, b.now, bv, as_cfg, n_allowed);
+            v = antispoof_eval(c, bs, h, dlen, i + b.base, b.now, bv, as_cfg, n_allowed);
             __syncwarp();
         }
         const bool alive = act && v != TC_SHOT && ip4;
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
         __syncwarp();
         if (priv && !sub) bstats_add(bs, ST_NAT_PASSED, 1); // no allocation: to userspace (bpf/nat44.c:592-596)
         // L4 header in bounds and a translatable protocol (:608-653)
-        bool go = sub != nullptr && (proto == 6 ? len >= 54u : ((proto == 17 || proto == 1) && len >= 42u));
+        bool go = sub != nullptr && (proto == 6 ? dlen >= 54u : ((proto == 17 || proto == 1) && dlen >= 42u));
         if (go && proto != 1 && (nflags & (proto == 6 ? (NATF_ALG_FTP | NATF_ALG_SIP) : NATF_ALG_SIP)) && st.alg_n) {
             int ax = alg_find(st, ((u32)bswap16(dport) << 16) | proto);
             if (ax >= 0) { // ALG traffic goes to userspace untranslated (:615-642)
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
 
         // ---- IPv4 options: fields are not at fixed offsets, take the generic path (rare) ----
         if (alive && !ihl5) {
-            NatOut o = nat_egress_one<false>(c, bs, p, len, i + b.base, b.now);
+            NatOut o = nat_egress_one<false>(c, bs, p, len, dlen, i + b.base, b.now);
             v = o.verdict;
             miss = o.order_key != NO_KEY;
             sub_idx = o.order_key;

@@ -166,11 +166,11 @@ __device__ __forceinline__ bool tb_step(TokenBucket &tb, u64 now, u32 pkt_len) {
 // ordering key (bucket slot index) when the frame has to go through the
 // ordered token-bucket walk, NO_KEY when its verdict is already final.
 __device__ __forceinline__ u32 qos_classify_one(const DevCtx &c, BlockStats &bs, const Tbl &t, const Hdr64 &h,
-                                                u32 len, bool egress, u32 *prio_out, bool *prio_set) {
-    *prio_set = false;
-    if (len < 14) return NO_KEY;
+                                                u32 len, u32 dlen, bool egress, u32 *prio_out, bool *prio_set) {
+    *prio_set = false; // dlen: bytes present (bounds checks), len: skb->len (byte counters)
+    if (dlen < 14) return NO_KEY;
     if (h.b16(12) != ETH_P_IP_LE) return NO_KEY;
-    if (len < 34) return NO_KEY;
+    if (dlen < 34) return NO_KEY;
     u64 k = egress ? h.b32(30) : h.b32(26);
     const u8 *slot = tbl_find<1, false>(t, &k);
     if (!slot) return NO_KEY; // no policy: TC_ACT_OK without statistics
@@ -298,14 +298,14 @@ struct NatOut {
 //     subscriber's worker in frame-index order; counters that classify
 //     already bumped for this frame (hairpin) are not bumped again.
 template <bool RESOLVE>
-__device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs, u8 *p, u32 len, u32 idx, u64 now,
+__device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs, u8 *p, u32 len, u32 dlen, u32 idx, u64 now,
                                                  NatPend *pd = nullptr) {
-    NatOut o;
+    NatOut o; // dlen = data_end - data (bounds checks), len = skb->len (bytes_out)
     o.verdict = TC_OK;
     o.order_key = NO_KEY;
-    if (len < 14) return o;
+    if (dlen < 14) return o;
     if (rd16(p, 12) != ETH_P_IP_LE) return o;
-    if (len < 34) return o;
+    if (dlen < 34) return o;
     u32 saddr = rd32(p, 26);
     if (!is_private_ip(saddr)) return o;
     u64 sk = saddr;
@@ -320,7 +320,7 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
     u32 l4 = 14 + (u32)(p[14] & 0x0f) * 4;
     u16 sport = 0, dport = 0;
     if (proto == 6 || proto == 17) {
-        if (l4 + (proto == 6 ? 20u : 8u) > len) return o;
+        if (l4 + (proto == 6 ? 20u : 8u) > dlen) return o;
         sport = rd16(p, l4);
         dport = rd16(p, l4 + 2);
         u32 alg_mask = proto == 6 ? (NATF_ALG_FTP | NATF_ALG_SIP) : NATF_ALG_SIP;
@@ -337,7 +337,7 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
             }
         }
     } else if (proto == 1) {
-        if (l4 + 8 > len) return o;
+        if (l4 + 8 > dlen) return o;
         sport = rd16(p, l4 + 4); // echo id stands in for the source port (:647-649)
         dport = 0;
     } else {
@@ -462,24 +462,24 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
 
 // nat44_ingress, :805-948.  Every update is commutative (or made so with a
 // CAS on the state byte), so this is a classify-only program.
-__device__ __forceinline__ int nat_ingress_one(const DevCtx &c, BlockStats &bs, u8 *p, u32 len, u64 now) {
-    if (len < 14) return TC_OK;
+__device__ __forceinline__ int nat_ingress_one(const DevCtx &c, BlockStats &bs, u8 *p, u32 len, u32 dlen, u64 now) {
+    if (dlen < 14) return TC_OK;
     if (rd16(p, 12) != ETH_P_IP_LE) return TC_OK;
-    if (len < 34) return TC_OK;
+    if (dlen < 34) return TC_OK;
     u32 saddr = rd32(p, 26), daddr = rd32(p, 30);
     u32 proto = p[23];
     u32 l4 = 14 + (u32)(p[14] & 0x0f) * 4;
     u16 sport = 0, dport = 0;
     if (proto == 6) {
-        if (l4 + 20 > len) return TC_OK;
+        if (l4 + 20 > dlen) return TC_OK;
         sport = rd16(p, l4);
         dport = rd16(p, l4 + 2);
     } else if (proto == 17) {
-        if (l4 + 8 > len) return TC_OK;
+        if (l4 + 8 > dlen) return TC_OK;
         sport = rd16(p, l4);
         dport = rd16(p, l4 + 2);
     } else if (proto == 1) {
-        if (l4 + 8 > len) return TC_OK;
+        if (l4 + 8 > dlen) return TC_OK;
         sport = 0;
         dport = rd16(p, l4 + 4);
     } else {

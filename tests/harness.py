@@ -255,18 +255,30 @@ def run_script(be, script: Script, tables=TABLES) -> dict:
     return res
 
 
-def compare(a: dict, b: dict, what: str = ""):
-    ka, kb = set(a.keys()), set(b.keys())
-    assert ka == kb, f"{what}: result keys differ: {sorted(ka ^ kb)[:10]}"
-    for k in sorted(ka):
+def diff_keys(a: dict, b: dict) -> list:
+    """Every result key on which two result sets differ, as (key, description) pairs."""
+    out = []
+    for k in sorted(set(a.keys()) ^ set(b.keys())):
+        out.append((k, "present on one side only"))
+    for k in sorted(set(a.keys()) & set(b.keys())):
         x, y = np.asarray(a[k]), np.asarray(b[k])
         if x.shape[0] == 0 and y.shape[0] == 0:
             continue
-        assert x.shape == y.shape, f"{what}: {k}: shape {x.shape} vs {y.shape}"
-        if not np.array_equal(x, y):
+        if x.shape != y.shape:
+            out.append((k, f"shape {x.shape} vs {y.shape}"))
+        elif not np.array_equal(x, y):
             d = np.argwhere(x != y)
-            raise AssertionError(f"{what}: {k}: {len(d)} elements differ, first at {d[0].tolist()}: "
-                                 f"{x[tuple(d[0])]} vs {y[tuple(d[0])]}")
+            out.append((k, f"{len(d)} elements differ, first at {d[0].tolist()}: {x[tuple(d[0])]} vs {y[tuple(d[0])]}"))
+    return out
+
+
+def compare(a: dict, b: dict, what: str = ""):
+    """Asserts bit-identity of two result sets; the failure message lists EVERY differing key (verdicts, frames,
+    counters, table dumps, event streams), not just the first in sort order."""
+    diffs = diff_keys(a, b)
+    if diffs:
+        lines = "\n".join(f"  {k}: {msg}" for k, msg in diffs[:40])
+        raise AssertionError(f"{what}: {len(diffs)} result keys differ\n{lines}")
 
 
 def save_golden(path: str, res: dict):

@@ -529,6 +529,116 @@ def pipeline_script(seed=0x919E, n_subs=30, n=3000, flags=0x0F) -> Script:
     return sc
 
 
+# ---------------------------------------------------------------------------
+# IPv4 header lengths 0..15: L4 header anywhere from byte 14 (overlapping the IP header) to byte 74
+# ---------------------------------------------------------------------------
+def ihl_frames(r, n_subs, n, dst_base=0x08080000, width=128):
+    """u8[n,width] frames whose IPv4 header claims every ihl 0..15 (bpf/nat44.c:606 multiplies whatever the nibble
+    says), TCP / UDP / ICMP, long enough that the L4 header is present wherever it lands.  The L4 fields are
+    written first and the fixed IPv4 fields over them, so for ihl < 5 — where the two overlap — the source
+    address survives and the frame still reaches the NAT code."""
+    sub = r.integers(0, n_subs, n)
+    ihl = (np.arange(n) % 16).astype(np.int64)
+    r.shuffle(ihl)
+    proto = r.choice(np.array([6, 6, 17, 17, 1], dtype=np.uint32), n)
+    sport = (20000 + r.integers(0, 5, n)).astype(np.uint32)
+    dport = r.choice(np.array([443, 80, 53, 21, 5060], dtype=np.uint32), n)
+    dst = (np.uint32(dst_base) + r.integers(0, 3, n).astype(np.uint32)).astype(np.uint32)
+    base = S.ipv4_headers(S.sub_mac_key(sub), np.uint64(GW_MAC), S.sub_ip(sub), dst, np.uint32(47), 0, 0, np.full(n, width, np.uint32))
+    f = np.zeros((n, width), np.uint8)
+    f[:, 34:] = r.integers(0, 256, (n, width - 34), dtype=np.uint8)  # option bytes / payload: arbitrary
+    l4 = 14 + 4 * ihl
+    rows = np.arange(n)
+    ck = r.integers(0, 65536, n).astype(np.uint32)
+    ck = np.where((proto == 17) & (r.integers(0, 4, n) == 0), 0, ck)
+    for k, (val, tcpudp_off, icmp_off) in enumerate(((sport, 0, 4), (dport, 2, None))):
+        b = S.port_bytes(val)
+        for j in range(2):
+            m = proto != 1
+            f[rows[m], l4[m] + tcpudp_off + j] = b[m, j]
+            if icmp_off is not None:
+                m = proto == 1
+                f[rows[m], l4[m] + icmp_off + j] = b[m, j]
+    ckb = S.port_bytes(ck)
+    for j in range(2):
+        for pr, off in ((6, 16), (17, 6), (1, 2)):
+            m = proto == pr
+            f[rows[m], l4[m] + off + j] = ckb[m, j]
+    m = proto == 6
+    f[rows[m], l4[m] + 13] = r.choice(np.array([0x02, 0x10, 0x18, 0x11, 0x04], dtype=np.uint8), int(m.sum()))
+    f[:, 0:34] = base[:, 0:34]
+    f[:, 14] = (0x40 | ihl).astype(np.uint8)
+    f[:, 23] = proto
+    f[:, 24:26] = 0
+    f[:, 24:26] = S.ip_checksum(f[:, 14:34])
+    return f, ihl, proto
+
+
+def ipopts_script(seed=0x0B75, n_subs=12, n=1600) -> Script:
+    """Frames with IPv4 options (and with header lengths below 5) through every TC program and every arena layout:
+    the L4 header of a long-option frame lies past byte 63, i.e. outside the 64-byte header slot most frames need."""
+    r = rng(seed)
+    sc = Script("ipopts")
+    keys, v = S.bindings(n_subs)
+    sc.update("subscriber_bindings", keys, v)
+    cfg = np.zeros(1, L.antispoof_config)
+    cfg["default_mode"], cfg["log_violations"] = 1, 1
+    sc.update1("antispoof_config", np.uint32(0), cfg)
+    nat_maps(sc, n_subs, 256, 0x0F)
+    qk, qv = S.qos_buckets(n_subs)
+    qv["burst_bytes"] = np.minimum(qv["burst_bytes"], 30000)
+    qv["tokens"] = qv["burst_bytes"]
+    sc.update("qos_ingress", qk, qv)
+    sc.update("qos_egress", qk, qv)
+    t = 3 * 10**9
+    f, ihl, proto = ihl_frames(r, n_subs, n)
+    l4 = 14 + 4 * ihl
+    lens = r.choice(np.array([128, 128, 594, 1518], dtype=np.uint32), n)
+    cut = r.integers(0, 8, n)  # a slice of frames ends right at / just before the end of its L4 header
+    need = l4 + np.where(proto == 6, 20, 8)
+    lens = np.where(cut == 0, need, lens)
+    lens = np.where(cut == 1, need - 1, lens).astype(np.uint32)
+    # (a) packed arena, neighbours 16-byte adjacent; (b) 128-byte slots
+    arena, off16 = S.pack_arena(f, lens)
+    sc.run("nat44_egress", arena, lens, t, off16=off16)
+    sc.run("nat44_egress", arena, lens, t + 10**6, off16=off16)
+    l128 = np.minimum(lens, 128).astype(np.uint32)
+    sc.run("nat44_egress", fixed(f, 128), l128, t + 2 * 10**6, stride=128)
+    first_run = next(i for i, st in enumerate(sc.steps) if st[0] == "run")
+
+    def replies(res):
+        out_a = res[f"s{first_run:03d}_frames"]
+        fr = np.stack([out_a[int(o) * 16: int(o) * 16 + 128] for o in off16])
+        keep = (ihl >= 5) & (lens >= need) & (res[f"s{first_run:03d}_verdict"] == 0)
+        fr, k_l4, k_pr = fr[keep], l4[keep], proto[keep]
+        out = fr.copy()
+        out[:, 26:30], out[:, 30:34] = fr[:, 30:34], fr[:, 26:30]
+        rows = np.arange(len(out))
+        for j in range(2):
+            m = k_pr != 1
+            out[rows[m], k_l4[m] + j], out[rows[m], k_l4[m] + 2 + j] = fr[rows[m], k_l4[m] + 2 + j], fr[rows[m], k_l4[m] + j]
+        m = k_pr == 1
+        out[rows[m], k_l4[m]] = 0  # echo reply
+        ln = np.where(np.arange(len(out)) % 3 == 0, 594, 128).astype(np.uint32)
+        a, o16 = S.pack_arena(out, ln)
+        return {"arena": a, "lens": ln, "now_ns": t + 5 * 10**6, "off16": o16}
+
+    sc.run_from("nat44_ingress", replies)
+    sc.run_from("nat44_ingress", replies)
+    f2, ihl2, proto2 = ihl_frames(r, n_subs, n, dst_base=0x08080400)
+    lens2 = r.choice(np.array([110, 128, 594, 1518], dtype=np.uint32), n)
+    spoof = r.integers(0, 20, n) == 0
+    f2[spoof, 27] ^= 0x20
+    arena2, off2 = S.pack_arena(f2, lens2)
+    sc.run("pipeline_up", arena2, lens2, t + 10**7, off16=off2)
+    sc.run("pipeline_up", arena2, lens2, t + 10**7 + 10**6, off16=off2)
+    sc.run("antispoof_ingress", arena2, lens2, t + 2 * 10**7, off16=off2)
+    sc.run("qos_ingress_prog", arena2, lens2, t + 3 * 10**7, off16=off2)
+    sc.run("qos_egress_prog", arena2, lens2, t + 3 * 10**7, off16=off2, priority=np.zeros(n, np.uint32))
+    sc.run("nat44_hairpin_xdp", arena2, lens2, t + 3 * 10**7, off16=off2)
+    return sc
+
+
 ALL_SCRIPTS = {
     "antispoof": antispoof_script,
     "qos": qos_script,
@@ -544,4 +654,5 @@ ALL_SCRIPTS = {
     "dhcp": dhcp_script,
     "pipeline": pipeline_script,
     "pipeline_noeim": lambda: pipeline_script(seed=0x91A0, flags=0x06),
+    "ipopts": ipopts_script,
 }
