@@ -154,12 +154,43 @@ def cpu_run(workload: str, n: int, procs: int, steps: int, warmup: int):
     return pk / tmax / 1e6, kind, tmax
 
 
+def host_cpus() -> dict:
+    """CPUs this process may actually use: the scheduler affinity mask and the cgroup CPU quota, not os.cpu_count()
+    (a container on a 128-thread host can be limited to a fraction of it; sizing the reference arm's pool from
+    cpu_count() then oversubscribes the quota and makes the CPU arm look slower than the hardware is)."""
+    out = {"os_cpu_count": os.cpu_count() or 1}
+    try:
+        out["sched_affinity"] = len(os.sched_getaffinity(0))
+    except Exception:
+        out["sched_affinity"] = out["os_cpu_count"]
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    quota = int(txt[0]) / int(txt[1])
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    quota = q / int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            break
+        except Exception:
+            continue
+    out["cgroup_quota_cpus"] = None if quota is None else round(quota, 2)
+    usable = out["sched_affinity"]
+    if quota is not None:
+        usable = max(1, min(usable, int(quota)))
+    out["usable"] = usable
+    return out
+
+
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    procs = max(1, min(cores, 128))
+    cpus = host_cpus()
+    procs = max(1, min(cpus["usable"], 128))
     n = 1 << 18
     t0 = time.time()
     mpps, kind, tmax = cpu_run(a.workload, n, procs, a.steps, a.warmup)
@@ -167,12 +198,13 @@ def run_reference_arm(a):
         "impl": "reference", "metric": METRIC, "value": round(mpps, 3), "unit": "Mpps", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": round(tmax / a.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/u32/u64 integer", "data": "synthetic",
-        "config": {"workload": a.workload, "frames_per_step": n * procs, "host_procs": procs,
+        "config": {"workload": a.workload, "frames_per_step": n * procs, "host_procs": procs, "host_cpus": cpus,
                    "sharding": "subscriber MAC hash, one private map set per core"},
         "cpu_baseline": {"value": round(mpps, 3), "unit": "Mpps", "cores": procs,
                          "kind": "reference" if kind == "reference" else "port",
-                         "sample": f"{procs} cores x {n} frames x {a.steps} steps of {a.workload}; "
-                                   "reference eBPF C compiled natively (gcc -O2) over a userspace map runtime"},
+                         "sample": f"{procs} processes (sched_getaffinity {cpus['sched_affinity']}, cgroup quota "
+                                   f"{cpus['cgroup_quota_cpus']}, os.cpu_count {cpus['os_cpu_count']}) x {n} frames x {a.steps} "
+                                   f"steps of {a.workload}; reference eBPF C compiled natively (gcc -O2) over a userspace map runtime"},
         "e2e": {"value": round(mpps, 3), "unit": "Mpps", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": round(time.time() - t0, 1),
     }
@@ -182,33 +214,19 @@ def run_reference_arm(a):
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
-_ARENAS = []  # keeps registered mappings alive
-
-
-def host_arena(nbytes: int, kind: str):
-    """Pinned, GPU-mapped host buffer for the frame arena.  kind 'thp': anonymous memory advised to use
-    2 MB transparent huge pages, touched, then cudaHostRegister'ed; falls back to cudaHostAlloc."""
-    import mmap
+def host_arena(nbytes: int):
+    """Frame arena for the end-to-end leg from the library's own allocator: bng_host_alloc() = 2 MB transparent
+    huge pages registered with CUDA (falls back to cudaHostAlloc).  Returned as a torch uint8 view; arenas live
+    until the process ends."""
+    import ctypes
     import torch
-    if kind == "thp" and hasattr(mmap, "MADV_HUGEPAGE"):
-        try:
-            huge = 2 << 20
-            size = (nbytes + huge - 1) // huge * huge
-            mm = mmap.mmap(-1, size + huge, flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
-            base = np.frombuffer(mm, dtype=np.uint8)
-            addr = base.ctypes.data
-            off = (-addr) % huge
-            mm.madvise(mmap.MADV_HUGEPAGE, 0, size + huge)
-            arr = base[off:off + size]
-            arr[:] = 0  # first touch on this (NUMA-bound) thread
-            t = torch.from_numpy(arr)
-            rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), size, 1 | 2)  # portable | mapped
-            if int(rc) == 0:
-                _ARENAS.append((mm, base, t))
-                return t[:nbytes]
-        except Exception as e:  # noqa: BLE001
-            print(f"[bench] thp arena unavailable ({e}); using cudaHostAlloc", file=sys.stderr)
-    return torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
+    from bng_b200.dataplane import load_library
+    lib = load_library()
+    p = lib.bng_host_alloc(nbytes)
+    if not p:
+        raise RuntimeError("bng_host_alloc failed")
+    arr = np.ctypeslib.as_array((ctypes.c_uint8 * nbytes).from_address(p))
+    return torch.from_numpy(arr)
 
 
 def bind_to_gpu_numa_node(index: int):
@@ -221,44 +239,52 @@ def bind_to_gpu_numa_node(index: int):
         words = (os.cpu_count() + 63) // 64
         mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
         cpus = [64 * w + b for w in range(len(mask)) for b in range(64) if (mask[w] >> b) & 1]
-        cpus = [c for c in cpus if c < os.cpu_count()]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
         if cpus:
             os.sched_setaffinity(0, cpus)
             return {"cpus": f"{cpus[0]}-{cpus[-1]}", "count": len(cpus)}
     except Exception as e:  # affinity is an optimisation, never a requirement
         return {"error": str(e)[:80]}
     return None
-class DevPtr:
-    """__cuda_array_interface__ wrapper so torch can view library-owned device memory."""
-
-    def __init__(self, ptr, n, typestr="<i8"):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
-def run_gpu(a):
+class G:
+    """Process-wide state of the GPU arm (one rank)."""
+    rank = 0
+    world = 1
+    local = 0
+    dev = None
+    dist = None
+
+
+def _traffic(name, kernel, world, reference_capacities):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, with the capture it came from.
+    The capture is of ONE configuration (N = 1, workload-sized tables): any other run reports null."""
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(tp) or world != 1 or reference_capacities:
+        return None, "not captured for this configuration (profiles/ncu_traffic.json holds the N=1 workload-sized run)"
+    ent = json.load(open(tp)).get(name, {}).get(kernel)
+    if ent is None:
+        return None, "no capture of this kernel"
+    if isinstance(ent, dict):
+        return ent.get("bytes"), ent.get("source")
+    return ent, "profiles/ncu_traffic.json"
+
+
+def measure(a, name, frames, steps, warmup, *, wl=None, reference_capacities=False, subs_scale=1, keep=False):
+    """One workload on this rank's GPU: W warm-up steps, K timed steps (CUDA events on the library's stream, fresh
+    frames restored untimed between steps), max over ranks, then a per-kernel pass for the roofline.  Returns the
+    result dict; with keep=True also the live objects the end-to-end leg needs."""
     import torch
-    import torch.distributed as dist
-    from bng_b200 import MEM_DEVICE, MEM_HOST, Dataplane
+    from bng_b200 import MEM_DEVICE, Dataplane
     from bng_b200.layouts import as_bytes
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    # stdout carries exactly one JSON line: whatever native libraries print there while we run (NCCL's version
-    # banner, for one) goes to stderr instead
-    sys.stdout.flush()
-    json_fd = os.dup(1)
-    os.dup2(2, 1)
-    numa = bind_to_gpu_numa_node(local)  # pinned host buffers must live next to the GPU's PCIe root
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    n = a.frames
-    wl = W.BUILDERS[a.workload](n, rank, world)
-    n = wl.n  # a workload may hold fewer frames than asked for (nat_cold: one frame per flow)
-    dp = Dataplane(device=local, max_batch=max(n, 1 << 20), rank=rank, world=world,
-                   **({} if a.reference_capacities else W.sizing(wl)))
+    dev, dist, world, rank = G.dev, G.dist, G.world, G.rank
+    if wl is None:
+        wl = W.build(name, frames, rank, world, subs_scale)
+    n = wl.n
+    dp = Dataplane(device=G.local, max_batch=max(n, 1 << 20), rank=rank, world=world,
+                   **({} if reference_capacities else W.sizing(wl)))
     for m, k, v in wl.maps:
         r = dp.update_batch(m, as_bytes(k), as_bytes(v))
         assert r == 0, (m, r)
@@ -271,8 +297,9 @@ def run_gpu(a):
         dp.sync()
         if wl.derive is not None:
             translated.append(ph.cpu().numpy())
-    if wl.derive is not None:  # frames that depend on what the prewarm did (return traffic of translated flows)
+    if wl.derive is not None and not getattr(wl, "_derived", False):
         wl.headers, wl.lens = wl.derive(translated)
+        wl._derived = True
     hw = wl.headers.shape[1]
     off16, stride, total16 = W.slot16(wl.lens, wl.imix, hw, a.align)
     hdr_d = torch.from_numpy(wl.headers).to(dev)
@@ -280,22 +307,12 @@ def run_gpu(a):
     len_d = len0_d.clone()
     arena_d = torch.zeros(total16 * 16 + 64, dtype=torch.uint8, device=dev)
     a16 = arena_d[: total16 * 16].view(total16, 16)
-    off_d = None
+    off_d = gidx = None
     if off16 is not None:
         off_d = torch.from_numpy(off16.astype(np.int32)).to(dev)
         gidx = off_d.long()[:, None] + torch.arange(hw // 16, device=dev)[None, :]
     verdict_d = torch.zeros(n, dtype=torch.uint8, device=dev)
     lib_stream = torch.cuda.ExternalStream(dp.stream, device=dev)
-
-    def restore():
-        dp.sync()  # the previous step (asynchronous on the library's stream) must be done with the arena
-        if off16 is None:
-            arena_d[: n * stride].view(n, stride)[:, :hw] = hdr_d
-        else:
-            a16[gidx.reshape(-1)] = hdr_d.view(-1, 16)
-        len_d.copy_(len0_d)
-        torch.cuda.synchronize()
-        reset_state()
 
     def reset_state():
         for ring in ("spoof_events", "nat_log_rb"):  # the event consumer keeps the staging rings empty (untimed)
@@ -307,6 +324,16 @@ def run_gpu(a):
                 if m == "subscriber_nat":
                     dp.update_batch(m, as_bytes(k), as_bytes(v))
 
+    def restore():
+        dp.sync()  # the previous step (asynchronous on the library's stream) must be done with the arena
+        if off16 is None:
+            arena_d[: n * stride].view(n, stride)[:, :hw] = hdr_d
+        else:
+            a16[gidx.reshape(-1)] = hdr_d.view(-1, 16)
+        len_d.copy_(len0_d)
+        torch.cuda.synchronize()
+        reset_state()
+
     step_no = [0]
 
     def step():
@@ -314,18 +341,18 @@ def run_gpu(a):
         step_no[0] += 1
         dp.run(wl.prog, arena_d, len_d, now, off16=off_d, stride=stride, verdict=verdict_d, mem=MEM_DEVICE)
 
-    for _ in range(a.warmup):
+    for _ in range(warmup):
         restore()
         step()
         dp.sync()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(G.local)
     sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     launches0 = dp.launch_count
     evs = []
-    for _ in range(a.steps):
+    for _ in range(steps):
         restore()  # fresh frames for this step (untimed: stands in for the NIC filling the arena)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(lib_stream)
@@ -336,15 +363,17 @@ def run_gpu(a):
     torch.cuda.synchronize()
     launches = dp.launch_count - launches0
     step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
-    total_ms = sum(step_ms)
-    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    tmax = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    nsum = torch.tensor([n], dtype=torch.float64, device=dev)
     if world > 1:
         dist.barrier()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nsum, op=dist.ReduceOp.SUM)
     total_ms_max = float(tmax.item())
+    frames_all = float(nsum.item())
     clocks = sampler.result()
     drops = int((verdict_d == 2).sum().item())
-    value = world * n * a.steps / (total_ms_max * 1e-3) / 1e6
+    value = frames_all * steps / (total_ms_max * 1e-3) / 1e6
 
     # ---- per-kernel timing for the roofline (separate pass, events around every launch) ----
     dp.prof_enable(True)
@@ -359,31 +388,47 @@ def run_gpu(a):
     step_prof_ms = sum(v[1] for v in prof.values()) / 3
     peak, peak_src = peaks()
     algo = W.ALGO_BYTES[wl.name]
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(wl.name, {}).get(top[0])
+    traffic, traffic_src = _traffic(wl.name, top[0], world, reference_capacities)
     achieved = algo * n / (top_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": top[0], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_frame": algo, "kernel_ms": round(top_ms, 4),
                 "kernel_share_of_step": round(top[1][1] / 3 / step_prof_ms, 3),
-                "step_frac": round(algo * n / (total_ms_max / a.steps * 1e-3) / 1e9 / peak, 4),
+                "step_frac": round(algo * n / (total_ms_max / steps * 1e-3) / 1e9 / peak, 4),
                 "kernels_ms": {k: round(v[1] / v[0], 4) for k, v in prof.items()}}
+    res = {"value": round(value, 2), "unit": "Mpps", "ms_per_step": round(total_ms_max / steps, 4), "steps": steps, "warmup": warmup,
+           "frames_per_gpu_per_step": n, "subscribers_this_gpu": wl.n_subs_local, "step_ms": [round(float(x), 3) for x in step_ms],
+           "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks, "drop_fraction_last_step": round(drops / n, 4),
+           "tables": "reference capacities (1 M subscribers, 4 M sessions, 2 M EIM)" if reference_capacities else
+                     "sized for the provisioned subscribers / flows (2x head-room)",
+           "lru_overflow": int(dp.lru_overflow), "events_lost": int(dp.events_lost)}
+    if keep:
+        live = dict(dp=dp, wl=wl, off16=off16, stride=stride, total16=total16, hw=hw, gidx=gidx, step_no=step_no,
+                    reset_state=reset_state, n=n, arena_bytes=total16 * 16)
+        return res, live
+    dp.close()
+    del arena_d, hdr_d
+    torch.cuda.empty_cache()
+    return res, None
 
-    # ---- end to end through the C ABI with pinned host buffers ----
-    # One call = one batch of n_e frames (the first n_e of the workload).  The batch is capped at --e2e-frames
-    # (2^20) because what bounds this leg is the host side: behind the box's IOMMU the GPU's scattered header
-    # reads need the arena in 2 MB pages, and a 1.6 GB arena often cannot get them all (72 vs 290 Mpps seen).
+
+def e2e_leg(a, live):
+    """The same metric through bng_prog_run(BNG_MEM_HOST): frames in a pinned host arena, host<->device copies inside
+    the timed region (wall clock around the call, max over ranks)."""
+    import torch
+    from bng_b200 import MEM_HOST
+    dev, dist, world = G.dev, G.dist, G.world
+    dp, wl, off16, stride, total16, hw, gidx = (live[k] for k in ("dp", "wl", "off16", "stride", "total16", "hw", "gidx"))
+    n, step_no, reset_state = live["n"], live["step_no"], live["reset_state"]
     e2e_steps = max(1, min(a.steps, a.e2e_steps))
     n_e = min(n, max(1, a.e2e_frames))
     lens_e, hdrs_e = wl.lens[:n_e], wl.headers[:n_e]
     off16_e = off16[:n_e] if off16 is not None else None
     total16_e = total16 if n_e == n else (int(off16[n_e]) if off16 is not None else n_e * stride // 16)
-    arena_h = host_arena(total16_e * 16 + 64, a.arena)
+    arena_h = host_arena(total16_e * 16 + 64)
 
     def host_like(t):
-        h = host_arena(t.numel() * t.element_size(), a.arena).view(t.dtype)[: t.numel()]
+        h = host_arena(t.numel() * t.element_size()).view(t.dtype)[: t.numel()]
         h.copy_(t)
         return h
 
@@ -402,12 +447,10 @@ def run_gpu(a):
             h16.index_copy_(0, gidx_h, hdr_h.view(-1, 16))
         len_h.copy_(len0_h)
 
-    arena_bytes = total16 * 16
-    arena_bytes_e = total16_e * 16
     tc_prog = wl.prog != "dhcp_fastpath_prog"
-    hb = 64 if tc_prog else 448  # bytes of each frame a program can touch = what crosses PCIe from a pinned arena
+    hb = 64 if tc_prog else 448  # bytes of each frame that cross PCIe from a pinned arena (96 when ihl > 5)
 
-    def e2e_run(arena_t, off_t, strd, restore_fn, nbytes):
+    def run(arena_t, off_t, strd, restore_fn, nbytes):
         tot = 0.0
         for s in range(1 + e2e_steps):
             restore_fn()
@@ -427,31 +470,109 @@ def run_gpu(a):
             dist.all_reduce(et, op=dist.ReduceOp.MAX)
         return world * n_e * e2e_steps / float(et.item()) / 1e6
 
-    # (a) the frames as they sit in the host arena (full frames, IMIX on 64-byte boundaries)
-    e2e_val = e2e_run(arena_h, off_h, stride, restore_host, arena_bytes_e)
+    val = run(arena_h, off_h, stride, restore_host, total16_e * 16)
     per_frame_in = float(np.minimum(lens_e, hb).mean())
     h2d = int(n_e * per_frame_in) + n_e * 4 + (n_e * 4 if off16 is not None else 0)
     d2h = int(n_e * (per_frame_in - (16 if tc_prog else 0))) + n_e + (n_e * 4 if not tc_prog else 0)
-    e2e_extra = None
+    out = {"value": round(val, 2), "unit": "Mpps", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "steps": e2e_steps, "frames_per_step": n_e, "arena": "bng_host_alloc(): 2 MB huge pages registered with CUDA",
+           "layout": "pinned host arena, full frames; only the bytes a program can touch cross PCIe"}
+    extra = None
     if tc_prog and wl.imix:
-        # (b) header-split receive: the NIC put the first 64 bytes of every frame in a contiguous ring
-        # (len[] still carries the full frame length); that ring is all the TC programs ever touch
-        ring_h = host_arena(n_e * 64, a.arena)
+        # header-split receive: the NIC put the first 64 bytes of every frame in a contiguous ring (len[] still
+        # carries the full frame length, bounds checks stop at the slot: tests/test_gpu_slots.py)
+        ring_h = host_arena(n_e * 64)
 
         def restore_ring():
             ring_h.view(n_e, 64)[:, :hw] = hdr_h
             len_h.copy_(len0_h)
 
-        v = e2e_run(ring_h, None, 64, restore_ring, n_e * 64)
-        e2e_extra = {"value": round(v, 2), "unit": "Mpps", "layout": "header-split ring (64 B per frame, len = full frame)",
-                     "h2d_bytes_per_step": n_e * 64 + n_e * 4, "d2h_bytes_per_step": n_e * 64 + n_e}
+        v = run(ring_h, None, 64, restore_ring, n_e * 64)
+        extra = {"value": round(v, 2), "unit": "Mpps", "layout": "header-split ring (64 B per frame, len = full frame)",
+                 "h2d_bytes_per_step": n_e * 64 + n_e * 4, "d2h_bytes_per_step": n_e * 64 + n_e}
+    return out, extra
 
-    # ---- counter reconciliation over NCCL (outside the timed region, as in production) ----
-    ptr, nst = dp.stats_device_ptr()
-    stats_local = torch.as_tensor(DevPtr(ptr, nst), device=dev).clone()
-    stats_global = stats_local.clone()
+
+EXTRA_WORKLOADS = ("antispoof_64", "nat_steady_64", "nat_cold_64", "dhcp")
+
+
+def run_gpu(a):
+    import torch
+    import torch.distributed as dist
+    from bng_b200 import Dataplane
+
+    G.rank = rank = int(os.environ.get("RANK", "0"))
+    G.world = world = int(os.environ.get("WORLD_SIZE", "1"))
+    G.local = local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: whatever native libraries print there while we run (NCCL's version
+    # banner, for one) goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    numa = bind_to_gpu_numa_node(local)  # pinned host buffers must live next to the GPU's PCIe root
+    torch.cuda.set_device(local)
+    G.dev = dev = torch.device("cuda", local)
+    G.dist = dist
     if world > 1:
-        dist.all_reduce(stats_global, op=dist.ReduceOp.SUM)
+        dist.init_process_group("nccl", device_id=dev)
+    t_start = time.time()
+
+    # ---- headline: the workload at BASELINE's population, tables sized for it ----
+    head, live = measure(a, a.workload, a.frames, a.steps, a.warmup, reference_capacities=a.reference_capacities, keep=True)
+    wl, dp = live["wl"], live["dp"]
+    e2e, e2e_extra = e2e_leg(a, live)
+
+    # ---- counter reconciliation: NCCL all-reduce of the packed counter vector INSIDE the library (bng_sync_reduce)
+    #      over a communicator of the library's own; the unique id travels through the host plumbing ----
+    uid = [Dataplane.comm_unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(uid, src=0)
+    t0 = time.perf_counter()
+    dp.comm_init(uid[0], rank, world)
+    t_comm = time.perf_counter() - t0
+    stats_local = dp.sync_reduce() if world == 1 else None
+    t0 = time.perf_counter()
+    stats_global = dp.sync_reduce()
+    t_red = time.perf_counter() - t0
+    ptr, nst = dp.stats_device_ptr()
+    mine = torch.as_tensor(DevPtr(ptr, nst), device=dev).clone()
+    check = mine.clone()
+    if world > 1:
+        dist.all_reduce(check, op=dist.ReduceOp.SUM)  # the same reduction by torch: must agree
+    reduce_ok = bool((check.cpu().numpy().view(np.uint64) == stats_global).all())
+    coop = (int(mine[37].item()), int(mine[38].item()))
+    dp.close()
+    del live
+    torch.cuda.empty_cache()
+
+    # ---- the same workload with every table at the reference's compile-time capacity ----
+    refcap = None
+    if not a.reference_capacities and not a.no_extra:
+        r, _ = measure(a, a.workload, a.frames, max(3, min(a.steps, 10)), 3, wl=wl, reference_capacities=True)
+        refcap = {k: r[k] for k in ("value", "unit", "ms_per_step", "tables")}
+        refcap["roofline"] = {k: r["roofline"][k] for k in ("kernel", "kernel_ms", "frac", "step_frac", "kernels_ms")}
+    # ---- 10 k subscribers PER GPU (population grows with N: per-GPU tables keep their size) ----
+    pergpu = None
+    if not a.no_extra:
+        if world == 1:
+            pergpu = {"value": head["value"], "ms_per_step": head["ms_per_step"], "note": "identical to the headline at N = 1"}
+        else:
+            r, _ = measure(a, a.workload, a.frames, max(3, min(a.steps, 10)), 3, subs_scale=world)
+            pergpu = {k: r[k] for k in ("value", "unit", "ms_per_step", "subscribers_this_gpu", "drop_fraction_last_step")}
+            pergpu["roofline"] = {k: r["roofline"][k] for k in ("kernel", "kernel_ms", "frac", "step_frac", "kernels_ms")}
+    # ---- the other BASELINE configs, short (5 steps), sharded the same way ----
+    others = {}
+    if not a.no_extra:
+        for name in EXTRA_WORKLOADS:
+            if name == a.workload:
+                continue
+            r, _ = measure(a, name, a.frames, 5, 3)
+            rf = r["roofline"]
+            others[name] = {"value": r["value"], "unit": "Mpps", "ms_per_step": r["ms_per_step"], "kernel": rf["kernel"],
+                            "kernel_ms": rf["kernel_ms"], "frac": rf["frac"], "step_frac": rf["step_frac"], "traffic": rf["traffic"],
+                            "traffic_source": rf["traffic_source"], "algorithmic_bytes_per_frame": rf["algorithmic_bytes_per_frame"],
+                            "kernels_ms": rf["kernels_ms"], "frames_per_gpu_per_step": r["frames_per_gpu_per_step"],
+                            "subscribers_this_gpu": r["subscribers_this_gpu"], "gpu_launches": r["gpu_launches"]}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
@@ -461,34 +582,49 @@ def run_gpu(a):
                "sample": f"1 core x {c_n} frames x 4 passes of {a.workload} ({tt:.1f} s), reference eBPF C run natively"}
     if rank == 0:
         out = {
-            "metric": METRIC, "value": round(value, 2), "unit": "Mpps", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": round(total_ms_max / a.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": head["value"], "unit": "Mpps", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/u32/u64 integer", "data": "synthetic",
-            "config": {"workload": wl.name, "program": wl.prog, "frames_per_gpu_per_step": n,
-                       "subscribers_this_gpu": wl.n_subs_local, "sharding": f"splitmix64(mac) % {world}",
-                       "avg_frame_bytes": round(float(wl.lens.mean()), 1), "frame_align": a.align if wl.imix else stride,
+            "config": {"workload": wl.name, "program": wl.prog, "frames_per_gpu_per_step": head["frames_per_gpu_per_step"],
+                       "subscribers_this_gpu": wl.n_subs_local, "subscribers_total": "10 000 (BASELINE config #4), split over the GPUs"
+                       if wl.name.startswith("pipeline") else "see workloads.py",
+                       "sharding": f"splitmix64(mac) % {world}", "tables": head["tables"],
+                       "avg_frame_bytes": round(float(wl.lens.mean()), 1), "frame_align": a.align if wl.imix else live_stride(wl),
                        "step_ms_min_med_max": [round(float(x), 4) for x in
-                                               (min(step_ms), float(np.median(step_ms)), max(step_ms))],
-                       "step_ms_all": [round(float(x), 3) for x in step_ms],
-                       "l2_policy": "inputs larger than L2 (arena %.0f MB + tables) and rewritten between steps" % (arena_bytes / 1e6),
+                                               (min(head["step_ms"]), float(np.median(head["step_ms"])), max(head["step_ms"]))],
+                       "step_ms_all": head["step_ms"],
+                       "l2_policy": "inputs larger than L2 (frame arena + tables) and rewritten between steps",
                        **wl.info},
-            "wire_gbps": round(value * 1e6 * float(wl.lens.mean()) * 8 / 1e9, 1),
-            "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": round(e2e_val, 2), "unit": "Mpps", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "frames_per_step": n_e,
-                    "layout": "pinned host arena, full frames; only the bytes a program can touch cross PCIe"},
-            "e2e_header_split": e2e_extra, "host_affinity": numa,
-            "gpu_launches": int(launches), "clocks": clocks,
-            "verdict_drop_fraction_last_step": round(drops / n, 4),
-            "stats_allreduce": {"antispoof_allowed": int(stats_global[0].item()), "nat_snat": int(stats_global[10].item()),
-                                "qos_dropped": int(stats_global[7].item())},
-            "lru_overflow": int(dp.lru_overflow), "events_lost": int(dp.events_lost),
+            "wire_gbps": round(head["value"] * 1e6 * float(wl.lens.mean()) * 8 / 1e9, 1),
+            "roofline": head["roofline"], "cpu_baseline": cpu,
+            "e2e": e2e, "e2e_header_split": e2e_extra, "host_affinity": numa,
+            "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
+            "verdict_drop_fraction_last_step": head["drop_fraction_last_step"],
+            "reference_capacities": refcap, "per_gpu_constant": pergpu, "workloads": others,
+            "stats_allreduce": {"by": "bng_sync_reduce (ncclAllReduce inside libbng_b200.so)", "matches_torch_allreduce": reduce_ok,
+                                "comm_init_s": round(t_comm, 3), "reduce_ms": round(t_red * 1e3, 3),
+                                "antispoof_allowed": int(stats_global[0]), "nat_snat": int(stats_global[10]),
+                                "qos_dropped": int(stats_global[7])},
+            "lru_overflow": head["lru_overflow"], "events_lost": head["events_lost"],
+            "nat_ordered_frames": {"cooperative": coop[0], "sequential": coop[1]},
+            "wall_s": round(time.time() - t_start, 1),
         }
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(out) + "\n").encode())
-    dp.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def live_stride(wl):
+    return ((wl.headers.shape[1] + 15) // 16) * 16
+
+
+class DevPtr:
+    """__cuda_array_interface__ wrapper so torch can view library-owned device memory."""
+
+    def __init__(self, ptr, n, typestr="<i8"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
 def run_dhcp_slow(a):
@@ -531,9 +667,8 @@ def main():
     ap.add_argument("--reference-capacities", action="store_true",
                     help="size every table for the reference's compile-time max_entries instead of the workload")
     ap.add_argument("--align", type=int, default=64, help="frame placement granularity in the IMIX arena (16 or 64)")
-    ap.add_argument("--arena", default="thp", choices=["thp", "pinned"],
-                    help="host frame arena of the e2e leg: 2 MB transparent huge pages registered with CUDA (what a DPDK-style "
-                         "receive ring uses: far fewer IOMMU translations for the GPU's scattered header reads), or cudaHostAlloc")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="only the headline: skip the reference-capacities variant, the per-GPU-constant variant and the other configs")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.workload == "dhcp_slow":

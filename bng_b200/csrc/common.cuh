@@ -35,6 +35,9 @@ enum {
     ST_EV_LOST_SPOOF = 34,
     ST_EV_LOST_NATLOG = 35,
     ST_TABLE_FULL = 36,
+    ST_NAT_COOP = 37, // ordered-phase chunks created warp-cooperatively ...
+    ST_NAT_SEQ = 38,  // ... and chunks that had to be walked one frame at a time (diagnostics)
+    ST_LRU_EVICT = 39, // entries evicted from a full LRU map to make room for an insert
     ST_COUNT = 40,
 };
 
@@ -60,37 +63,54 @@ struct Tbl {
     u32 key_size;
     u32 value_size;
     u32 vlayout; // 0: value stored verbatim at voff; VL_SESSION: nat_sessions hot/cold layout below
-    u32 pad;
+    // BPF_MAP_TYPE_LRU_HASH: an insert into a full map evicts instead of failing.  0: plain hash (-E2BIG);
+    // LRU_TS | offset << 8: evict the entry with the oldest u64 timestamp at that slot offset among the
+    // slots next to the new key's home; LRU_ANY: no timestamp in the value (nat_reverse): the first live one.
+    u32 lru;
 };
+#define LRU_NONE 0u
+#define LRU_TS 1u
+#define LRU_ANY 2u
+#define LRU_WINDOW 16u
 
-// nat_sessions slots are 128 B: the first 64-byte DRAM granule holds everything
-// the per-frame hit paths read or update (key, translation, counters), the
-// second the fields only creation / control-plane reads touch.  The reference
-// layout of struct nat_session (bpf/nat44.c:123-141) is restored by
-// ses_abi_to_slot() whenever a value crosses the ABI.
+// nat_sessions slots are 128 B, laid out by what the per-frame paths touch:
+//   sector 0 [0,32)   key 16 | nat_ip 4 | nat_port 2 | epoch 2 | out_lo 8
+//            everything an upstream HIT needs — probe, translation and the out-direction counters — is
+//            ONE 32-byte sector: one 256-bit load plus one 64-bit atomic on the same sector.
+//   sector 1 [32,64)  last_seen 8 | orig_ip 4 | state word 4 | orig_port 2 | pad 6 | in_lo 8
+//            what a downstream hit adds (original tuple, TCP state, in-direction counters), and last_seen.
+//   sector 2 [64,96)  out_hi 8 | in_hi 8 | created 8 | dest_ip 4 | dest_port 2 | _pad1 2   (creation / carries / ABI)
+//   sector 3 [96,104) the struct's padding bytes (they cross the ABI verbatim)
+// `epoch` is not part of struct nat_session: it is the batch (low 16 bits of the batch sequence, 0 = never)
+// in which last_seen was last stored.  Every frame of a batch would store the same last_seen = now, so only
+// a frame that finds an older epoch stores it (and the epoch): one extra store per flow and batch instead of
+// a second sector written by every frame.  bng_prog_run() clears all epochs whenever the 16-bit batch
+// counter wraps (k_epoch_reset), so a stale epoch can never alias the current one.
+// The reference layout of struct nat_session (bpf/nat44.c:123-141) is restored by ses_abi_to_slot()
+// whenever a value crosses the ABI.
 #define VL_SESSION 1u
 #define VL_QOS 2u         // value verbatim at voff, plus a copy of rate_bps at QOS_RATE_COPY
 #define QOS_RATE_COPY 8u  // qos slot: key u64 @0, rate_bps copy @8, struct token_bucket @16
 enum {
     SES_NAT_IP = 16,    // u32
     SES_NAT_PORT = 20,  // u16
-    SES_ORIG_PORT = 22, // u16
-    // last_seen shares the 32-byte sector of the key and the translation: a hit reads it for free and
-    // stores it only when it differs from this batch's now (a plain store next to the counters' atomics
-    // cost 40 % of the classify kernel: profiles/r01_results.md)
-    SES_LAST_SEEN = 24, // u64
-    SES_ORIG_IP = 32,   // u32
-    SES_STATE = 36,     // u8 state, protocol@37, flags@38, is_hairpin@39
+    SES_EPOCH = 22,     // u16, dataplane-internal
     // The two counters of a direction advance with ONE 64-bit atomic: the low words of packets and
     // bytes share a u64 (packets in bits 0-31, bytes in bits 32-63), their high words a second u64 that
     // is touched only when a low word wraps (ses_count()).
-    SES_OUT_LO = 40, // u64: packets_out[31:0] | bytes_out[31:0] << 32
-    SES_OUT_HI = 48, // u64: packets_out[63:32] | bytes_out[63:32] << 32
+    SES_OUT_LO = 24,    // u64: packets_out[31:0] | bytes_out[31:0] << 32
+    SES_LAST_SEEN = 32, // u64
+    SES_ORIG_IP = 40,   // u32
+    SES_STATE = 44,     // u8 state, protocol@45, flags@46, is_hairpin@47
+    SES_ORIG_PORT = 48, // u16
     SES_IN_LO = 56,
-    SES_IN_HI = 64,
-    SES_CREATED = 72,
-    SES_DEST_IP = 80,   // u32
-    SES_DEST_PORT = 84, // u16, _pad1@86, implicit padding@88, tail padding@92
+    SES_OUT_HI = 64, // u64: packets_out[63:32] | bytes_out[63:32] << 32
+    SES_IN_HI = 72,
+    SES_CREATED = 80,
+    SES_DEST_IP = 88,   // u32
+    SES_DEST_PORT = 92, // u16, _pad1@94
+    SES_PAD_A = 96,     // struct bytes 20..23
+    SES_PAD_B = 100,    // struct bytes 76..79
 };
 // byte offset inside struct nat_session -> byte offset inside the slot
 __host__ __device__ __forceinline__ u32 ses_abi_to_slot(u32 a) {
@@ -100,7 +120,7 @@ __host__ __device__ __forceinline__ u32 ses_abi_to_slot(u32 a) {
     if (a < 12) return SES_ORIG_IP + (a - 8);
     if (a < 16) return SES_DEST_IP + (a - 12);
     if (a < 20) return SES_DEST_PORT + (a - 16);
-    if (a < 24) return 88 + (a - 20);
+    if (a < 24) return SES_PAD_A + (a - 20);
     if (a < 32) return SES_LAST_SEEN + (a - 24);
     if (a < 40) return SES_CREATED + (a - 32);
     if (a < 44) return SES_OUT_LO + (a - 40); // packets_out
@@ -112,13 +132,17 @@ __host__ __device__ __forceinline__ u32 ses_abi_to_slot(u32 a) {
     if (a < 68) return SES_IN_LO + 4 + (a - 64); // bytes_in
     if (a < 72) return SES_IN_HI + 4 + (a - 68);
     if (a < 76) return SES_STATE + (a - 72);
-    return 92 + (a - 76);
+    return SES_PAD_B + (a - 76);
 }
+__host__ __device__ __forceinline__ u32 ses_hi_of(u32 lo_off) { return lo_off == SES_OUT_LO ? (u32)SES_OUT_HI : (u32)SES_IN_HI; }
 #ifdef __CUDACC__
-// session->last_seen = now.  Every frame of a batch stores the same value, so only the first frame of a
-// flow needs to; a stale read merely repeats the store.
-__device__ __forceinline__ void ses_touch(u8 *ses, u64 now) {
-    if (*(const volatile u64 *)(ses + SES_LAST_SEEN) != now) *(u64 *)(ses + SES_LAST_SEEN) = now;
+// session->last_seen = now (bpf/nat44.c:677,881), once per flow and batch: `seen` is the epoch the caller
+// read with the probe, `epoch` the current batch's.
+__device__ __forceinline__ void ses_touch(u8 *ses, u64 now, u32 seen, u32 epoch) {
+    if (seen != epoch) {
+        *(u64 *)(ses + SES_LAST_SEEN) = now;
+        *(u16 *)(ses + SES_EPOCH) = (u16)epoch;
+    }
 }
 // Rare half of ses_count(): a low word wrapped.  c: the packet word carried into the byte word (undo
 // it there, count it in the high packet word); w: the byte word wrapped upwards.
@@ -129,7 +153,7 @@ static __device__ __noinline__ void ses_count_carry(u8 *ses, u32 lo_off, u32 c, 
         u64 old = atomicAdd((unsigned long long *)(ses + lo_off), 0xFFFFFFFF00000000ull); // byte word -= 1
         if ((old >> 32) == 0) add -= 1ull << 32;                                         // ... which wrapped downwards
     }
-    if (add) atomicAdd((unsigned long long *)(ses + lo_off + 8), add);
+    if (add) atomicAdd((unsigned long long *)(ses + ses_hi_of(lo_off)), add);
 }
 // packets += 1, bytes += len on the counter pair at lo_off (SES_OUT_LO / SES_IN_LO): exact u64
 // arithmetic, every wrap of a low word is seen by exactly one caller through the value the atomic returns.
@@ -140,6 +164,19 @@ __device__ __forceinline__ void ses_count(u8 *ses, u32 lo_off, u32 len) {
     if (c | w) ses_count_carry(ses, lo_off, c, w);
 }
 #endif
+
+// ---------------------------------------------------------------------------
+// Subscriber directory: one 16-byte slot per private address that owns a subscriber_nat entry and / or a
+// qos_ingress bucket: { u64 key (the address, zero-extended; doubles as the slot state), u32 nat slot,
+// u32 qos slot | DIR_QOS_UNLIMITED } with DIR_NONE for "no entry".  Derived state, maintained by the
+// table-update kernels (tableops.cu) whenever one of the two maps changes.  The upstream classify kernels
+// probe it instead of the two maps (one 128-bit load instead of two probes with a collision loop each),
+// and its slot index is the ordering key of the group-by: a dense 2^k key space whatever capacity the two
+// maps were opened with.
+// ---------------------------------------------------------------------------
+#define DIR_NONE 0xFFFFFFFFu
+#define DIR_QOS_UNLIMITED 0x80000000u // rate_bps == 0: the bucket never drops and is never written (bpf/qos_ratelimit.c:77-78)
+#define DIR_SLOT_MASK 0x7FFFFFFFu
 
 struct LpmTbl { // BPF_MAP_TYPE_LPM_TRIE with a 4-byte address: {prefixlen, addr bytes, value}
     u32 *ents;  // 3 x u32 per entry: prefixlen, addr (memory order), value
@@ -171,6 +208,7 @@ struct DevCtx {
     Tbl cid_subs;   // circuit_id_subscribers   32 B      -> 25 B
     Tbl ip_pools;   // ip_pools                 u32       -> 28 B
     Tbl cid_map;    // circuit_id_map           u64       -> u64 (never read by a program)
+    Tbl subdir;     // derived: private address -> {subscriber_nat slot, qos_ingress slot}
     LpmTbl ranges_v4;  // allowed_ranges_v4
     LpmTbl priv_ranges; // nat_private_ranges (never read by a program)
     u8 *as_config;     // antispoof_config[1]   8 B
@@ -182,7 +220,7 @@ struct DevCtx {
     EvRing natlog_ev;  // nat_log_rb,   payload 40 B
     const struct SmallTabs *small; // compact image of the tiny read-mostly maps (TMA-staged into shared memory)
     u32 batch_seq;
-    u32 pad;
+    u32 epoch; // (batch_seq % 65535) + 1: what ses_touch() stamps (0 = never)
 };
 
 // Compact image of the maps that every frame consults but only the control
@@ -303,6 +341,32 @@ __device__ __forceinline__ u8 *tbl_find(const Tbl &t, const u64 *k) {
     return nullptr;
 }
 
+// Approximate LRU eviction (the kernel's LRU hash is approximate too: per-CPU lists, batched promotion): when
+// an LRU map is at max_entries, one of the LRU_WINDOW slots following the new key's home slot gives way —
+// the one least recently used by its timestamp.  The victim becomes a tombstone; whatever still refers to it
+// (a nat_reverse entry whose session went, an EIM reference) is dealt with the way the reference deals with
+// entries the kernel evicted underneath it (stale-reverse path, bpf/nat44.c:871-876).
+__device__ __forceinline__ bool tbl_evict_near(const Tbl &t, u32 home, u64 *stats) {
+    const u32 mode = t.lru & 0xff, ts_off = t.lru >> 8;
+    u8 *best = nullptr;
+    u64 best_ts = ~0ull, best_w = 0;
+    for (u32 j = 0; j < LRU_WINDOW; j++) {
+        u8 *s = t.slots + (size_t)((home + j) & t.mask) * t.slot_bytes;
+        const u64 w0 = *(volatile const u64 *)s;
+        if (w0 >= K_BUSY) continue;
+        const u64 ts = mode == LRU_TS ? *(volatile const u64 *)(s + ts_off) : j;
+        if (ts < best_ts) {
+            best_ts = ts;
+            best = s;
+            best_w = w0;
+        }
+    }
+    if (!best || atomicCAS((u64 *)best, best_w, K_TOMB) != best_w) return false;
+    atomicSub(t.count, 1u);
+    if (stats) atomicAdd(&stats[ST_LRU_EVICT], 1ull);
+    return true;
+}
+
 // Find-or-claim.  Returns the slot; *created says whether this call claimed
 // it.  A claimed slot is left in the K_BUSY state with key words 1.. written:
 // the caller fills the value and then calls tbl_publish().  Returns nullptr
@@ -313,10 +377,12 @@ __device__ __forceinline__ u8 *tbl_find(const Tbl &t, const u64 *k) {
 // between a same-address atomic storm and none).  The max_entries check is then approximate by at
 // most the inserts in flight, which only matters for the LRU maps at the very edge of capacity.
 template <int KW, bool SKIP_BUSY = false>
-__device__ __forceinline__ u8 *tbl_find_or_claim(const Tbl &t, const u64 *k, bool *created, u32 *pending = nullptr) {
+__device__ __forceinline__ u8 *tbl_find_or_claim(const Tbl &t, const u64 *k, bool *created, u32 *pending = nullptr,
+                                                 u64 *stats = nullptr) {
     *created = false;
     if (k[0] >= K_BUSY) return nullptr;
-    u32 i = (u32)tbl_hash<KW>(k) & t.mask;
+    const u32 home = (u32)tbl_hash<KW>(k) & t.mask;
+    u32 i = home;
     int tomb = -1;
     for (u32 probe = 0; probe <= t.mask;) {
         u8 *s = tbl_slot(t, i);
@@ -337,10 +403,12 @@ __device__ __forceinline__ u8 *tbl_find_or_claim(const Tbl &t, const u64 *k, boo
             u64 expect = tomb >= 0 ? K_TOMB : K_EMPTY;
             u8 *ts = tbl_slot(t, target);
             if (pending) {
-                if (*(volatile u32 *)t.count + *pending >= t.max_entries) return nullptr;
+                if (*(volatile u32 *)t.count + *pending >= t.max_entries && !(t.lru && tbl_evict_near(t, home, stats))) return nullptr;
             } else if (atomicAdd(t.count, 1u) >= t.max_entries) {
-                atomicSub(t.count, 1u);
-                return nullptr;
+                if (!(t.lru && tbl_evict_near(t, home, stats))) { // (the victim's count goes, ours stays)
+                    atomicSub(t.count, 1u);
+                    return nullptr;
+                }
             }
             u64 old = atomicCAS((u64 *)ts, expect, K_BUSY);
             if (old == expect) {

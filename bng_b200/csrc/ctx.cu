@@ -7,10 +7,15 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <dlfcn.h>
+#include <sys/mman.h>
+
+#include <nccl.h> // types only: the library is resolved at run time (bng_comm_init), never linked
 
 #include <algorithm>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/bng_b200.h"
@@ -67,6 +72,18 @@ struct bng_ctx {
     u32 *zc_off[2] = {nullptr, nullptr}, *zc_len[2] = {nullptr, nullptr}, *zc_len0[2] = {nullptr, nullptr},
         *zc_prio[2] = {nullptr, nullptr};
     u32 zc_hb = 0;
+    u32 zc_chunk = 1u << 19; // frames per chunk of the zero-copy pipeline
+    // staged upserts (bng_map_update_staged): per map, keys/values in arrival order, applied at the next batch boundary
+    struct Staged {
+        std::vector<u8> keys, vals;
+        u64 n = 0;
+    };
+    std::vector<Staged> staged;
+    u64 staged_total = 0, staged_errors = 0, staged_flushes = 0;
+    // multi-GPU reconciliation (bng_comm_init / bng_sync_reduce)
+    ncclComm_t comm = nullptr;
+    u32 comm_rank = 0, comm_world = 1;
+    u64 *stats_global = nullptr; // device: all-reduced counter vector
 };
 
 namespace {
@@ -90,6 +107,14 @@ int fail(bng_ctx *c, int code, const char *fmt, ...) {
         if (e__ != cudaSuccess) return fail(c, -EIO, "%s: %s", #call, cudaGetErrorString(e__)); \
     } while (0)
 
+u32 zc_chunk_frames() { // frames per chunk of the zero-copy pipeline; BNG_ZC_CHUNK_LOG2 overrides for tuning (read at bng_open)
+    const char *e = getenv("BNG_ZC_CHUNK_LOG2");
+    int lg = e ? atoi(e) : 19;
+    if (lg < 10) lg = 10;
+    if (lg > 22) lg = 22;
+    return 1u << lg;
+}
+
 u32 pow2_at_least(u64 v) {
     u64 p = 1;
     while (p < v) p <<= 1;
@@ -112,7 +137,7 @@ int make_table(bng_ctx *c, Tbl *t, u32 key_size, u32 value_size, u32 voff, u32 m
     t->value_size = value_size;
     t->max_entries = max_entries;
     t->vlayout = vlayout;
-    t->pad = 0;
+    t->lru = LRU_NONE;
     t->slot_bytes = slot_bytes ? slot_bytes : ((voff + value_size + 31u) & ~31u);
     int r = dev_alloc(c, (void **)&t->slots, (size_t)cap * t->slot_bytes, 0xFF);
     if (r) return r;
@@ -204,7 +229,7 @@ int make_lpm(bng_ctx *c, LpmTbl *l, u32 max) {
 }
 
 // ---- control-plane commands on hash maps ----
-int hash_cmd(bng_ctx *c, MapReg *m, int op, const void *keys, void *vals, u64 n, u32 flags, int *first_err) {
+int hash_cmd(bng_ctx *c, MapReg *m, int op, const void *keys, void *vals, u64 n, u32 flags, int *first_err, u64 *n_err = nullptr) {
     const Tbl &t = *m->tbl;
     const u64 chunk_max = 1u << 18;
     *first_err = 0;
@@ -218,13 +243,18 @@ int hash_cmd(bng_ctx *c, MapReg *m, int op, const void *keys, void *vals, u64 n,
         if (op == TOP_UPDATE) memcpy(c->io_host + voff, (const u8 *)vals + done * t.value_size, vb);
         size_t up = op == TOP_UPDATE ? voff + vb : kb;
         CU(c, cudaMemcpyAsync(c->io_dev, c->io_host, up, cudaMemcpyHostToDevice, c->L.stream));
-        CU(c, run_table_op(c->L, t, op, c->io_dev + koff, c->io_dev + voff, (int *)(c->io_dev + roff), k, flags));
+        const int role = m->tbl == &c->dev.sub_nat ? 1 : (m->tbl == &c->dev.qos_in ? 2 : 0);
+        CU(c, run_table_op(c->L, t, op, c->io_dev + koff, c->io_dev + voff, (int *)(c->io_dev + roff), k, flags, c->dev.subdir,
+                           role));
         size_t dfrom = op == TOP_LOOKUP ? voff : roff;
         CU(c, cudaMemcpyAsync(c->io_host + dfrom, c->io_dev + dfrom, roff + rb - dfrom, cudaMemcpyDeviceToHost, c->L.stream));
         CU(c, cudaStreamSynchronize(c->L.stream));
         const int *res = (const int *)(c->io_host + roff);
         for (u64 i = 0; i < k; i++)
-            if (res[i] && !*first_err) *first_err = res[i];
+            if (res[i]) {
+                if (!*first_err) *first_err = res[i];
+                if (n_err) ++*n_err;
+            }
         if (op == TOP_LOOKUP) {
             for (u64 i = 0; i < k; i++)
                 if (!res[i])
@@ -250,6 +280,86 @@ bool lpm_same(u32 pl, u32 a, u32 b) { // first pl bits equal, bytes in memory or
 
 } // namespace
 
+// ---- staged upserts ----
+// The reference's Go callers issue one Map.Put per lease / session event (pkg/dhcp/server.go:708,780,798); a
+// synchronous bng_map_update costs a host->device copy, a kernel and a device->host copy each.  Staged updates
+// (BPF_ANY semantics) are queued on the host and applied together: at the next batch boundary (bng_prog_run),
+// at bng_sync, and before anything reads or changes the same map (so a staged Put is always visible to a
+// later Lookup / Delete / dump of that map).  Within one flush the LAST staged value of a key wins, as it
+// would had the Puts been applied one by one.
+int flush_staged_locked(bng_ctx *c, int only_map);
+bool feeds_small_tabs_p(const MapReg *m);
+int small_refresh_p(bng_ctx *c);
+
+int flush_staged_locked(bng_ctx *c, int only_map) {
+    if (!c->staged_total) return 0;
+    int rc = 0;
+    for (size_t mi = 0; mi < c->staged.size(); mi++) {
+        bng_ctx::Staged &q = c->staged[mi];
+        if (!q.n || (only_map >= 0 && (int)mi != only_map)) continue;
+        MapReg *m = &c->maps[mi];
+        const u32 ks = m->key_size, vs = m->value_size;
+        // last occurrence of every key, in order of that occurrence
+        std::unordered_map<std::string, u64> last;
+        last.reserve(q.n * 2);
+        for (u64 i = 0; i < q.n; i++) last[std::string((const char *)&q.keys[i * ks], ks)] = i;
+        std::vector<u8> k2, v2;
+        k2.reserve(last.size() * ks);
+        v2.reserve(last.size() * vs);
+        u64 uniq = 0;
+        for (u64 i = 0; i < q.n; i++) {
+            auto it = last.find(std::string((const char *)&q.keys[i * ks], ks));
+            if (it->second != i) continue;
+            k2.insert(k2.end(), &q.keys[i * ks], &q.keys[i * ks] + ks);
+            v2.insert(v2.end(), &q.vals[i * vs], &q.vals[i * vs] + vs);
+            uniq++;
+        }
+        int first = 0;
+        u64 nerr = 0;
+        int r = hash_cmd(c, m, TOP_UPDATE, k2.data(), v2.data(), uniq, BNG_ANY, &first, &nerr);
+        if (!r && feeds_small_tabs_p(m)) r = small_refresh_p(c);
+        c->staged_errors += nerr;
+        c->staged_total -= q.n;
+        c->staged_flushes++;
+        q.keys.clear();
+        q.vals.clear();
+        q.n = 0;
+        if (r && !rc) rc = r;
+    }
+    return rc;
+}
+
+// ---- NCCL, resolved at run time: the host process brings its own libnccl (the Go control plane links it, a
+// Python process has torch's loaded already); nothing here links against it ----
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+};
+NcclApi *nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *path = getenv("BNG_NCCL_LIB");
+        api.handle = dlopen(path ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!api.handle) {
+            api.err = std::string("dlopen libnccl.so.2: ") + (dlerror() ? dlerror() : "?");
+            return;
+        }
+        api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+        api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
+        api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+        api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+        if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) api.err = "libnccl.so.2 lacks the expected symbols";
+    });
+    return api.err.empty() ? &api : nullptr;
+}
+
 // ===========================================================================
 extern "C" {
 
@@ -265,17 +375,72 @@ uint32_t bng_shard_of_mac(uint64_t mac_key, uint32_t world) {
     return (uint32_t)(splitmix64(mac_key) % world);
 }
 
-// Pinned, GPU-mapped host memory for frame arenas.  (An arena the application backs with 2 MB huge pages
-// and registers itself with cudaHostRegister works as well and is faster behind an IOMMU — the GPU reads
-// scattered 64-byte headers straight out of it and every 4 KB page touched is a translation: bench.py
-// --arena thp measured 228 -> 289 Mpps end to end for IMIX and 207 -> 397 Mpps for the DMA path.)
+// Pinned, GPU-mapped host memory for frame arenas (BNG_MEM_HOST batches are then read in place, zero-copy).
+// The arena is backed by 2 MB transparent huge pages and registered with cudaHostRegister: behind an IOMMU in
+// translated mode the GPU's scattered 64-byte header reads cost one translation per page touched, and a
+// receive ring in 4 KB pages thrashes the IOTLB (measured on the bench box: 228 -> 289 Mpps end to end for
+// IMIX frames, 207 -> 397 Mpps for the contiguous DMA path).  Falls back to cudaHostAlloc when huge pages or
+// registration are not available.  BNG_HOST_ARENA=pinned forces the fallback.
+namespace {
+struct HostArena {
+    void *map_base;  // mmap() result (nullptr: cudaHostAlloc)
+    size_t map_bytes;
+    size_t reg_bytes;
+};
+std::mutex g_arena_mu;
+std::vector<std::pair<void *, HostArena>> g_arenas;
+} // namespace
+
 void *bng_host_alloc(size_t bytes) {
+    if (!bytes) bytes = 16;
+    const char *mode = getenv("BNG_HOST_ARENA");
+    const size_t huge = (size_t)2 << 20;
+    if (!mode || strcmp(mode, "pinned") != 0) {
+        size_t size = (bytes + huge - 1) / huge * huge;
+        void *base = mmap(nullptr, size + huge, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (base != MAP_FAILED) {
+            u8 *p = (u8 *)(((uintptr_t)base + huge - 1) & ~(uintptr_t)(huge - 1));
+#ifdef MADV_HUGEPAGE
+            madvise(p, size, MADV_HUGEPAGE);
+#endif
+            for (size_t o = 0; o < size; o += 4096) p[o] = 0; // first touch on the caller's (NUMA-bound) thread
+            if (cudaHostRegister(p, size, cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess) {
+                std::lock_guard<std::mutex> g(g_arena_mu);
+                g_arenas.push_back({p, HostArena{base, size + huge, size}});
+                return p;
+            }
+            cudaGetLastError();
+            munmap(base, size + huge);
+        }
+    }
     void *p = nullptr;
-    if (cudaMallocHost(&p, bytes ? bytes : 16) != cudaSuccess) return nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> g(g_arena_mu);
+    g_arenas.push_back({p, HostArena{nullptr, 0, 0}});
     return p;
 }
 void bng_host_free(void *p) {
-    if (p) cudaFreeHost(p);
+    if (!p) return;
+    HostArena a{nullptr, 0, 0};
+    bool found = false;
+    {
+        std::lock_guard<std::mutex> g(g_arena_mu);
+        for (size_t i = 0; i < g_arenas.size(); i++)
+            if (g_arenas[i].first == p) {
+                a = g_arenas[i].second;
+                g_arenas.erase(g_arenas.begin() + i);
+                found = true;
+                break;
+            }
+    }
+    if (!found) return; // not ours
+    if (a.map_base) {
+        cudaDeviceSynchronize(); // nothing may still be reading the arena when its mapping goes away
+        cudaHostUnregister(p);
+        munmap(a.map_base, a.map_bytes);
+    } else {
+        cudaFreeHost(p);
+    }
 }
 
 int bng_close(bng_ctx *c) {
@@ -284,6 +449,10 @@ int bng_close(bng_ctx *c) {
         std::lock_guard<std::mutex> g(c->mu);
         cudaSetDevice(c->device);
         if (c->L.stream) cudaStreamSynchronize(c->L.stream);
+        if (c->comm) {
+            if (NcclApi *a = nccl_api()) a->CommDestroy(c->comm);
+            c->comm = nullptr;
+        }
         for (void *p : c->allocs) cudaFree(p);
         Scratch &s = c->L.s;
         void *sp[] = {s.key_a, s.key_b, s.val_a, s.val_b, s.qslot, s.pflag, s.cub_tmp, s.counters,
@@ -349,6 +518,7 @@ bng_ctx *bng_open(const bng_open_opts *o) {
         return nullptr;
     }
     c->L.num_sms = prop.multiProcessorCount;
+    c->zc_chunk = zc_chunk_frames();
     OPEN_CU(cudaStreamCreateWithFlags(&c->L.stream, cudaStreamNonBlocking));
 
     u32 max_subs = opts.max_subscribers ? opts.max_subscribers : 1000000u;
@@ -365,6 +535,9 @@ bng_ctx *bng_open(const bng_open_opts *o) {
     OPEN_R(make_table(c, &d.sessions, 16, 80, 16, max_sess, VL_SESSION, 128));
     OPEN_R(make_table(c, &d.reverse, 16, 16, 16, max_sess));
     OPEN_R(make_table(c, &d.eim, 8, 32, 8, max_eim));
+    d.sessions.lru = LRU_TS | ((u32)SES_LAST_SEEN << 8); // the three LRU_HASH maps of bpf/nat44.c:218-244
+    d.reverse.lru = LRU_ANY;
+    d.eim.lru = LRU_TS | (24u << 8); // eim_mapping.last_used
     OPEN_R(make_table(c, &d.hairpin, 4, 1, 8, 1000));
     OPEN_R(make_table(c, &d.alg, 4, 8, 8, 64));
     OPEN_R(make_table(c, &d.sub_pools, 8, 25, 8, max_subs));
@@ -372,6 +545,9 @@ bng_ctx *bng_open(const bng_open_opts *o) {
     OPEN_R(make_table(c, &d.cid_subs, 32, 25, 32, max_subs));
     OPEN_R(make_table(c, &d.ip_pools, 4, 28, 8, 10000));
     OPEN_R(make_table(c, &d.cid_map, 8, 8, 8, max_subs));
+    // subscriber directory: 16-byte slots, as many as the per-subscriber maps have, room for both maps' keys
+    OPEN_R(make_table(c, &d.subdir, 4, 8, 8, max_subs, 0, 16));
+    d.subdir.max_entries = std::min<u64>(2ull * max_subs, d.subdir.mask);
     OPEN_R(make_lpm(c, &d.ranges_v4, 256));
     OPEN_R(make_lpm(c, &d.priv_ranges, 64));
     OPEN_R(dev_alloc(c, (void **)&d.as_config, 16, 0));
@@ -414,6 +590,7 @@ bng_ctx *bng_open(const bng_open_opts *o) {
     add_stats(c, "stats_map", T_ARRAY, 80, ST_DHCP);
     add_hash(c, "circuit_id_map", T_HASH, 8, 8, max_subs, &d.cid_map);
     add_hash(c, "circuit_id_subscribers", T_HASH, 32, 25, max_subs, &d.cid_subs);
+    c->staged.resize(c->maps.size());
     OPEN_R(small_refresh(c));
     cudaError_t se = cudaStreamSynchronize(c->L.stream);
     if (se != cudaSuccess) {
@@ -444,6 +621,7 @@ int bng_map_get_info(bng_ctx *c, int map, bng_map_info *out) {
     out->value_size = m->value_size;
     out->max_entries = m->max_entries;
     out->count = m->max_entries;
+    if (int fr = flush_staged_locked(c, map)) return fr;
     if (m->kind == KIND_HASH) {
         u32 cnt = 0;
         CU(c, cudaMemcpyAsync(&cnt, m->tbl->count, 4, cudaMemcpyDeviceToHost, c->L.stream));
@@ -469,6 +647,7 @@ int bng_map_update_batch(bng_ctx *c, int map, const void *keys, const void *valu
     if (flags > BNG_EXIST) return -EINVAL;
     std::lock_guard<std::mutex> g(c->mu);
     cudaSetDevice(c->device);
+    if (int fr = flush_staged_locked(c, map)) return fr; // staged Puts of this map come first
     switch (m->kind) {
     case KIND_HASH: {
         int first = 0;
@@ -521,6 +700,7 @@ int bng_map_lookup(bng_ctx *c, int map, const void *key, void *value_out) {
     if (!m || !key || !value_out) return -EINVAL;
     std::lock_guard<std::mutex> g(c->mu);
     cudaSetDevice(c->device);
+    if (int fr = flush_staged_locked(c, map)) return fr;
     switch (m->kind) {
     case KIND_HASH: {
         int first = 0;
@@ -560,6 +740,7 @@ int bng_map_delete(bng_ctx *c, int map, const void *key) {
     if (!m || !key) return -EINVAL;
     std::lock_guard<std::mutex> g(c->mu);
     cudaSetDevice(c->device);
+    if (int fr = flush_staged_locked(c, map)) return fr;
     if (m->kind == KIND_HASH) {
         int first = 0;
         int r = hash_cmd(c, m, TOP_DELETE, key, nullptr, 1, 0, &first);
@@ -586,9 +767,18 @@ int bng_map_clear(bng_ctx *c, int map) {
     if (!m || m->kind != KIND_HASH) return -EINVAL;
     std::lock_guard<std::mutex> g(c->mu);
     cudaSetDevice(c->device);
+    if (c->staged_total) { // staged Puts of a map that is being emptied are void
+        bng_ctx::Staged &q = c->staged[map];
+        c->staged_total -= q.n;
+        q.keys.clear();
+        q.vals.clear();
+        q.n = 0;
+    }
     const Tbl &t = *m->tbl;
     CU(c, cudaMemsetAsync(t.slots, 0xFF, ((size_t)t.mask + 1) * t.slot_bytes, c->L.stream));
     CU(c, cudaMemsetAsync(t.count, 0, 4, c->L.stream));
+    if (m->tbl == &c->dev.sub_nat || m->tbl == &c->dev.qos_in)
+        CU(c, run_dir_clear_half(c->L, c->dev.subdir, m->tbl == &c->dev.sub_nat ? 1 : 2));
     CU(c, cudaStreamSynchronize(c->L.stream));
     return feeds_small_tabs(m) ? small_refresh(c) : 0;
 }
@@ -598,6 +788,7 @@ int64_t bng_map_dump(bng_ctx *c, int map, void *keys_out, void *values_out, uint
     if (!m || !keys_out || !values_out) return -EINVAL;
     std::lock_guard<std::mutex> g(c->mu);
     cudaSetDevice(c->device);
+    if (int fr = flush_staged_locked(c, map)) return fr;
     return map_dump_locked(c, m, keys_out, values_out, cap);
 }
 
@@ -656,6 +847,11 @@ static int small_refresh(bng_ctx *c) {
     delete im;
     return rc;
 }
+
+} // extern "C"
+bool feeds_small_tabs_p(const MapReg *m) { return feeds_small_tabs(m); }
+int small_refresh_p(bng_ctx *c) { return small_refresh(c); }
+extern "C" {
 
 static bool feeds_small_tabs(const MapReg *m) {
     return !strcmp(m->name, "antispoof_config") || !strcmp(m->name, "nat_config_map") || !strcmp(m->name, "alg_ports") ||
@@ -755,18 +951,7 @@ static int dispatch(bng_ctx *c, int prog, const DevBatch &b) {
 //   s_out  : header scatter back into the host arena (+ verdict / length D2H)
 // so PCIe reads, PCIe writes and compute of successive chunks overlap, and only the bytes a
 // program can touch ever cross the bus.
-static u32 zc_chunk_frames() { // frames per pipeline chunk; BNG_ZC_CHUNK_LOG2 overrides for tuning
-    static u32 v = 0;
-    if (!v) {
-        const char *e = getenv("BNG_ZC_CHUNK_LOG2");
-        int lg = e ? atoi(e) : 19;
-        if (lg < 10) lg = 10;
-        if (lg > 22) lg = 22;
-        v = 1u << lg;
-    }
-    return v;
-}
-#define ZC_CHUNK (zc_chunk_frames())
+#define ZC_CHUNK (c->zc_chunk)
 static int run_host_zero_copy(bng_ctx *c, int prog, bng_batch *bb, u8 *arena_dev) {
     // Bytes of a frame a program can touch (hostio.cu): 96 for the TC programs (Ethernet + IPv4 with options + 20
     // bytes of L4), 448 for dhcp_fastpath_prog.  Frames that ARE a fixed slot no larger than that (64-byte
@@ -869,7 +1054,10 @@ int bng_prog_run(bng_ctx *c, int prog, bng_batch *bb) {
     cudaSetDevice(c->device);
     int r = ensure_scratch(c, bb->n);
     if (r) return r;
+    if ((r = flush_staged_locked(c, -1)) != 0) return r; // the batch boundary: staged upserts become visible
     c->dev.batch_seq++;
+    c->dev.epoch = c->dev.batch_seq % 65535u + 1; // what a session hit stamps next to last_seen (common.cuh)
+    if (c->dev.epoch == 1 && c->dev.batch_seq > 1) CU(c, run_epoch_reset(c->L, c->dev.sessions)); // the 16-bit stamp wraps
     DevBatch b{};
     b.n = bb->n;
     b.stride = bb->stride;
@@ -945,12 +1133,114 @@ int bng_sync(bng_ctx *c) {
     if (!c) return -EINVAL;
     std::lock_guard<std::mutex> g(c->mu);
     cudaSetDevice(c->device);
+    int r = flush_staged_locked(c, -1);
     CU(c, cudaStreamSynchronize(c->L.stream));
     prof_collect(c->L);
+    return r;
+}
+
+int bng_map_update_staged(bng_ctx *c, int map, const void *key, const void *value) {
+    MapReg *m = get_map(c, map);
+    if (!m || !key || !value) return -EINVAL;
+    if (m->kind != KIND_HASH) return bng_map_update(c, map, key, value, BNG_ANY); // arrays / tries: nothing to batch
+    std::lock_guard<std::mutex> g(c->mu);
+    bng_ctx::Staged &q = c->staged[map];
+    q.keys.insert(q.keys.end(), (const u8 *)key, (const u8 *)key + m->key_size);
+    q.vals.insert(q.vals.end(), (const u8 *)value, (const u8 *)value + m->value_size);
+    q.n++;
+    c->staged_total++;
+    if (q.n >= (1u << 18)) { // bound the host-side queue
+        cudaSetDevice(c->device);
+        return flush_staged_locked(c, map);
+    }
     return 0;
 }
 
+int bng_staged_info(bng_ctx *c, uint64_t *pending, uint64_t *flushes, uint64_t *errors) {
+    if (!c) return -EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    if (pending) *pending = c->staged_total;
+    if (flushes) *flushes = c->staged_flushes;
+    if (errors) *errors = c->staged_errors;
+    return 0;
+}
+
+// ---- multi-GPU reconciliation ----
+int bng_comm_unique_id(void *id_out, uint64_t cap) {
+    if (!id_out || cap < sizeof(ncclUniqueId)) return -EINVAL;
+    NcclApi *a = nccl_api();
+    if (!a) return -ENOSYS;
+    ncclUniqueId id;
+    if (a->GetUniqueId(&id) != ncclSuccess) return -EIO;
+    memcpy(id_out, &id, sizeof(id));
+    return 0;
+}
+
+int bng_comm_init(bng_ctx *c, const void *id, uint32_t rank, uint32_t world) {
+    if (!c || !id || world == 0 || rank >= world) return -EINVAL;
+    NcclApi *a = nccl_api();
+    if (!a) return fail(c, -ENOSYS, "NCCL is not available in this process (set BNG_NCCL_LIB)");
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    if (c->comm) return fail(c, -EEXIST, "communicator already initialised");
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    ncclResult_t r = a->CommInitRank(&c->comm, (int)world, uid, (int)rank);
+    if (r != ncclSuccess) {
+        c->comm = nullptr;
+        return fail(c, -EIO, "ncclCommInitRank: %s", a->GetErrorString ? a->GetErrorString(r) : "error");
+    }
+    c->comm_rank = rank;
+    c->comm_world = world;
+    return 0;
+}
+
+int bng_sync_reduce(bng_ctx *c, uint64_t *totals_out) {
+    if (!c) return -EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    int fr = flush_staged_locked(c, -1);
+    if (!c->stats_global) {
+        CU(c, cudaMalloc((void **)&c->stats_global, ST_COUNT * 8));
+        c->allocs.push_back(c->stats_global);
+    }
+    if (c->comm) {
+        NcclApi *a = nccl_api();
+        ncclResult_t r = a->AllReduce(c->dev.stats, c->stats_global, ST_COUNT, ncclUint64, ncclSum, c->comm, c->L.stream);
+        if (r != ncclSuccess) return fail(c, -EIO, "ncclAllReduce: %s", a->GetErrorString ? a->GetErrorString(r) : "error");
+    } else {
+        CU(c, cudaMemcpyAsync(c->stats_global, c->dev.stats, ST_COUNT * 8, cudaMemcpyDeviceToDevice, c->L.stream));
+    }
+    if (totals_out) CU(c, cudaMemcpyAsync(totals_out, c->stats_global, ST_COUNT * 8, cudaMemcpyDeviceToHost, c->L.stream));
+    CU(c, cudaStreamSynchronize(c->L.stream));
+    prof_collect(c->L);
+    return fr;
+}
+
 void *bng_stream(bng_ctx *c) { return c ? (void *)c->L.stream : nullptr; }
+
+// Session expiry sweep (sweep.cu): removes every nat_sessions entry idle for longer than the timeout of its
+// protocol / TCP state at now_ns, with its nat_reverse entry, its EIM reference, the subscriber's active-session
+// count; counts sessions_expired and logs NAT_LOG_SESSION_DELETE.  A batch of its own between program runs.
+int bng_sweep(bng_ctx *c, uint64_t now_ns, uint64_t *expired_out) {
+    if (!c) return -EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    int r = flush_staged_locked(c, -1);
+    if (r) return r;
+    c->dev.batch_seq++;
+    c->dev.epoch = c->dev.batch_seq % 65535u + 1;
+    if (c->dev.epoch == 1 && c->dev.batch_seq > 1) CU(c, run_epoch_reset(c->L, c->dev.sessions));
+    u32 *cnt = c->L.s.counters + 8; // scratch words 8.. are free between program runs
+    CU(c, cudaMemsetAsync(cnt, 0, 4, c->L.stream));
+    CU(c, run_nat_sweep(c->L, c->dev, now_ns, cnt));
+    u32 n = 0;
+    CU(c, cudaMemcpyAsync(&n, cnt, 4, cudaMemcpyDeviceToHost, c->L.stream));
+    CU(c, cudaStreamSynchronize(c->L.stream));
+    prof_collect(c->L);
+    if (expired_out) *expired_out = n;
+    return 0;
+}
 
 // ---------------------------------------------------------------------------
 // events
@@ -980,11 +1270,14 @@ int bng_events_drain(bng_ctx *c, int map, void *buf, uint64_t cap_records, uint6
         for (u32 i = 0; i < cnt; i++) order[i] = i;
         const u8 *base = raw.data();
         u32 rb = r.rec_bytes;
+        const u32 payload = m->ev_payload;
         std::sort(order.begin(), order.end(), [&](u32 a, u32 b) {
             const u32 *ta = (const u32 *)(base + (size_t)a * rb + rb - 8);
             const u32 *tb = (const u32 *)(base + (size_t)b * rb + rb - 8);
             if (ta[1] != tb[1]) return ta[1] < tb[1];
-            return ta[0] < tb[0];
+            if (ta[0] != tb[0]) return ta[0] < tb[0];
+            // records of one sweep (marker 0xFFFFFFFE, no frame index): by content, so the order is defined
+            return memcmp(base + (size_t)a * rb + 8, base + (size_t)b * rb + 8, payload - 8) < 0;
         });
         // BPF_MAP_TYPE_RINGBUF capacity: 8-byte header + payload rounded to 8;
         // a reserve fails once producer-consumer distance would exceed size-1
@@ -1060,6 +1353,7 @@ static uint64_t read_stat(bng_ctx *c, int idx) {
     return v;
 }
 uint64_t bng_lru_overflow(bng_ctx *c) { return read_stat(c, ST_LRU_OVERFLOW); }
+uint64_t bng_lru_evictions(bng_ctx *c) { return read_stat(c, ST_LRU_EVICT); }
 uint64_t bng_events_lost(bng_ctx *c) { return read_stat(c, ST_EV_LOST_SPOOF) + read_stat(c, ST_EV_LOST_NATLOG); }
 
 } // extern "C"

@@ -356,12 +356,11 @@ __global__ void __launch_bounds__(DH_TILE) k_dhcp_fastpath(const __grid_constant
 }
 
 cudaError_t run_dhcp_fastpath(Launcher &L, const DevCtx &c, const DevBatch &b) {
-    static bool attr_set = false;
     const int smem = DH_TILE * DH_SLOT;
-    if (!attr_set) {
+    if (!L.dhcp_smem_set) { // function attributes are per device: set on the device this context runs on
         cudaError_t e = cudaFuncSetAttribute(k_dhcp_fastpath, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        L.dhcp_smem_set = 1;
     }
     long want = ((long)b.n + DH_TILE - 1) / DH_TILE;
     long cap = (long)L.num_sms * 4; // 4 x 50 KB of staging per SM

@@ -34,7 +34,7 @@
 #define MISS_FLAG 0x80000000u
 
 // device-side counters (Scratch::counters)
-enum { CNT_M = 0, CNT_NSEG = 1, CNT_DEFERRED = 2, CNT_MAXKEY = 3 };
+enum { CNT_M = 0, CNT_NSEG = 1, CNT_DEFERRED = 2, CNT_MAXKEY = 3, CNT_WORK = 4 };
 
 // The grouped (key, value) arrays live in one of two ping-pong buffers depending on how many radix
 // passes actually ran: passes whose digit is zero for every key of the batch (largest key < 2^(8p))
@@ -175,23 +175,26 @@ __global__ void __launch_bounds__(BLOCK) k_nat_ingress(const __grid_constant__ D
             ok[1] = (u64)r.w[6] | ((u64)r.w[7] << 32);
         }
         if (go && !have) n_passed++; // no mapping: to the stack untouched (:861-867)
-        // ---- nat_sessions: sector 0 (key, translation, last_seen), then orig_ip + state from sector 1 ----
+        // ---- nat_sessions: sector 0 (key, epoch) and sector 1 (last_seen, orig_ip, state, orig_port, in counters),
+        //      requested together: one round trip, not two ----
         u8 *ses = nullptr;
-        uint4 tr = make_uint4(0, 0, 0, 0);
-        uint2 os = make_uint2(0, 0); // orig_ip, state word
+        u32 seen = 0;
+        U256 s1; // w[2] orig_ip, w[3] state word, w[4] orig_port
+#pragma unroll
+        for (int k = 0; k < 8; k++) s1.w[k] = 0;
         if (have && ok[0] < K_BUSY) {
             u8 *s0 = tbl_slot(c.sessions, tbl_hash<2>(ok) & c.sessions.mask);
             const U256 s = ldg256(s0);
-            os = *(const uint2 *)(s0 + SES_ORIG_IP); // issued with the probe: one round trip, not two
+            s1 = ldg256(s0 + 32);
             const u64 w0 = (u64)s.w[0] | ((u64)s.w[1] << 32), w1 = (u64)s.w[2] | ((u64)s.w[3] << 32);
-            tr = make_uint4(s.w[4], s.w[5], s.w[6], s.w[7]);
+            seen = s.w[5] >> 16;
             if (w0 == ok[0] && w1 == ok[1]) {
                 ses = s0;
             } else if (w0 != K_EMPTY) {
                 ses = tbl_find<2, false>(c.sessions, ok);
                 if (ses) {
-                    tr = *(const uint4 *)(ses + SES_NAT_IP);
-                    os = *(const uint2 *)(ses + SES_ORIG_IP);
+                    seen = *(const u16 *)(ses + SES_EPOCH);
+                    s1 = ldg256(ses + 32);
                 }
             }
         }
@@ -202,12 +205,12 @@ __global__ void __launch_bounds__(BLOCK) k_nat_ingress(const __grid_constant__ D
                 n_passed++;
         }
         if (ses) {
-            if (((u64)tr.z | ((u64)tr.w << 32)) != b.now) *(u64 *)(ses + SES_LAST_SEEN) = b.now;
+            ses_touch(ses, b.now, seen, c.epoch);
             ses_count(ses, SES_IN_LO, len);
             if (proto == 6) { // :885-895; CLOSING(3) is absorbing, NEW(0) -> ESTABLISHED(1) on ack
                 const u32 tf = h.b8(47);
                 const bool finrst = (tf & 0x05) != 0, ack = (tf & 0x10) != 0;
-                u32 cur = os.y;
+                u32 cur = s1.w[3];
                 while (finrst || ack) {
                     const u32 st = cur & 0xff, nst = finrst ? 3u : (st == 0 ? 1u : st);
                     if (nst == st) break;
@@ -216,8 +219,8 @@ __global__ void __launch_bounds__(BLOCK) k_nat_ingress(const __grid_constant__ D
                     cur = prev;
                 }
             }
-            const u32 new_ip = os.x;
-            const u16 new_port = (u16)(tr.y >> 16); // orig_port
+            const u32 new_ip = s1.w[2];
+            const u16 new_port = (u16)s1.w[4]; // orig_port
             h.s32(30, new_ip);
             h.s16(24, csum_upd32(h.b16(24), daddr, new_ip));
             if (proto == 6) {
@@ -507,146 +510,201 @@ __global__ void __launch_bounds__(BLOCK) k_heads(const __grid_constant__ Grouped
 }
 
 // ---------------------------------------------------------------------------
-// RESOLVE: one warp per group, frames in index order.
-//   NAT:  frames flagged MISS_FLAG run the full sequential nat44_egress
-//         (session re-lookup, EIM, port allocation, inserts, log, rewrite).
-//   QOS:  token_bucket_check() for every surviving frame of the group.
+// RESOLVE: one TEAM (a single warp in every program as built: concurrency across groups hides more latency
+// than parallelism inside one; the code is written for any multiple of 32) per group, frames in index order.
+//   stage   all threads copy the group's (value, length) pairs into shared memory, RS_STAGE frames per
+//           sweep: the dependent gather sval -> len[idx] runs on every lane at once instead of 32 frames
+//           per round trip of a single warp (a fat group — 3 000 frames per subscriber when 10 k subscribers
+//           are sharded over 8 GPUs — used to be ~50 serial round trips of one warp).
+//   NAT     warp 0 creates the new flows (MISS_FLAG) chunk by chunk, warp-cooperatively when the chunk's
+//           flows provably do not interact (nat_chunk_coop), else one lane at a time in index order.
+//   QOS     warp 0 applies token_bucket_check() to the staged lengths with warp-uniform fast paths
+//           (whole chunk fits / nothing fits / lane-by-lane), out of shared memory.
+//   write   all threads publish verdicts / priorities and count.
+// The group key is the subscriber-directory slot (programs with a NAT stage) or the bucket's own slot.
 // ---------------------------------------------------------------------------
-template <bool NAT, bool QOS, bool EGRESS>
-#ifndef RESOLVE_CHUNKS
-#define RESOLVE_CHUNKS 2
-#endif
-// The NAT-only walk is a chain of dependent table accesses per new flow: what hides its latency is the
-// number of resident warps, so it is compiled for 8 blocks per SM (32 registers, a few spills); with
-// the token-bucket walk in the same kernel the spills cost more than the occupancy gives.
-__global__ void __launch_bounds__(BLOCK, (NAT && !QOS) ? 8 : 4) k_resolve(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b,
-                                                   const __grid_constant__ Grouped g, const u32 *seg, const u32 *cnt) {
+#define DROP_FLAG 0x40000000u // staged value: nat44_egress dropped the frame (port exhaustion): no QoS stage
+#define IDX_MASK 0x3FFFFFFFu
+#define RS_PER_THREAD 16
+
+template <bool NAT, bool QOS, bool EGRESS, int TEAM>
+__global__ void __launch_bounds__(TEAM, (TEAM == 128 ? 6 : 20)) k_resolve(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b,
+                                                  const __grid_constant__ Grouped g, const u32 *seg, u32 *cnt) {
+    constexpr int STAGE = TEAM * RS_PER_THREAD;
     __shared__ BlockStats bs;
+    __shared__ u32 s_sv[STAGE], s_len[STAGE];
+    __shared__ u32 s_pass[STAGE / 32];
+    __shared__ u32 s_cnt, s_next;
     bstats_init(bs);
     const u32 *skey, *sval;
     grouped_select(g, cnt, skey, sval);
     const Tbl &qt = EGRESS ? c.qos_eg : c.qos_in;
-    const u32 lane = threadIdx.x & 31;
-    const u32 warp = (blockIdx.x * BLOCK + threadIdx.x) >> 5, nwarps = (gridDim.x * BLOCK) >> 5;
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 m = cnt[CNT_M], nseg = cnt[CNT_NSEG];
-    u64 pp = 0, pb = 0, dp = 0, db = 0; // per-lane partial QoS counters
+    u64 pp = 0, pb = 0, dp = 0, db = 0; // per-thread partial QoS counters
     NatPend pend;
     pend.ses = pend.rev = pend.eim = 0;
     pend.log_rec = nullptr;
     pend.logged = false;
-    for (u32 s = warp; s < nseg; s += nwarps) {
+    // groups are handed out dynamically (fat and thin groups mix: a static stride leaves blocks idle at the end)
+    for (;;) {
+        if (tid == 0) s_next = atomicAdd(&cnt[CNT_WORK], 1u);
+        __syncthreads();
+        const u32 s = s_next;
+        if (s >= nseg) break;
         const u32 start = seg[s];
         const u32 key = skey[start];
-        const bool has_bucket = QOS && key <= qt.mask;
-        u8 *slot = has_bucket ? tbl_slot(qt, key) : nullptr;
+        u8 *sub = nullptr, *slot = nullptr;
+        if (NAT) {
+            const u64 w = *(const u64 *)(c.subdir.slots + (size_t)key * 16 + 8);
+            const u32 ns = (u32)w, qs = (u32)(w >> 32);
+            if (ns != DIR_NONE) sub = tbl_slot(c.sub_nat, ns);
+            if (QOS && qs != DIR_NONE) slot = tbl_slot(qt, qs & DIR_SLOT_MASK);
+        } else {
+            slot = tbl_slot(qt, key);
+        }
         TokenBucket tb;
-        if (has_bucket) tb_load(tb, slot);
-        // one chunk = 32 consecutive frames of the group; returns false when the group ended in it
-        auto chunk = [&](const bool valid, const u32 sv, const u32 len) -> bool {
-            const u32 vmask = __ballot_sync(0xffffffffu, valid);
-            if (!vmask) return false;
-            const u32 idx = sv & ~MISS_FLAG;
-            bool dropped = false;
-            if (NAT) {
-                const bool is_miss = valid && (sv & MISS_FLAG);
-                u32 mm = __ballot_sync(0xffffffffu, is_miss);
-                if (mm) {
+        if (QOS && slot) tb_load(tb, slot);
+        for (u32 pos = start;; pos += STAGE) {
+            // ---- stage ----
+            if (tid == 0) s_cnt = STAGE;
+            __syncthreads();
+            {
+                u32 sv[RS_PER_THREAD];
+                bool ok[RS_PER_THREAD];
+#pragma unroll
+                for (int t = 0; t < RS_PER_THREAD; t++) {
+                    const u32 q = pos + t * TEAM + tid;
+                    ok[t] = q < m && skey[q] == key;
+                    sv[t] = ok[t] ? sval[q] : 0;
+                }
+                u32 first_bad = STAGE;
+#pragma unroll
+                for (int t = 0; t < RS_PER_THREAD; t++) {
+                    const u32 j = t * TEAM + tid;
+                    if (ok[t]) {
+                        s_sv[j] = sv[t];
+                        s_len[j] = b.len[sv[t] & IDX_MASK];
+                    } else if (j < first_bad) {
+                        first_bad = j;
+                    }
+                }
+                if (first_bad < STAGE) atomicMin(&s_cnt, first_bad); // keys are sorted: the valid positions are a prefix
+            }
+            __syncthreads();
+            const u32 n_here = s_cnt;
+            const u32 nchunk = (n_here + 31) / 32;
+            // ---- new flows of this subscriber, strictly in index order ----
+            if (NAT && warp == 0 && sub) {
+                for (u32 cb = 0; cb < nchunk; cb++) {
+                    const u32 j = cb * 32 + lane;
+                    const bool valid = j < n_here;
+                    const u32 sv = valid ? s_sv[j] : 0;
+                    const bool is_miss = valid && (sv & MISS_FLAG);
+                    u32 mm = __ballot_sync(0xffffffffu, is_miss);
+                    if (!mm) continue;
+                    const u32 idx = sv & IDX_MASK, len = valid ? s_len[j] : 0;
                     // one nat_log_rb reservation for all new flows of this chunk (every one of them
                     // logs at most one record; a slot left unused is tagged invalid for the drain)
                     const EvRing &r = c.natlog_ev;
-                    u32 cnt = __popc(mm), basepos = 0;
-                    if (lane == 0) basepos = atomicAdd(r.count, cnt);
+                    u32 nrec = __popc(mm), basepos = 0;
+                    if (lane == 0) basepos = atomicAdd(r.count, nrec);
                     basepos = __shfl_sync(0xffffffffu, basepos, 0);
-                    if (lane == 0 && basepos + cnt > r.cap) { // staging ring full: the tail of the chunk has no slot
-                        u32 over = basepos >= r.cap ? cnt : basepos + cnt - r.cap;
+                    if (lane == 0 && basepos + nrec > r.cap) { // staging ring full: the tail of the chunk has no slot
+                        u32 over = basepos >= r.cap ? nrec : basepos + nrec - r.cap;
                         atomicSub(r.count, over);
                         atomicAdd(&c.stats[r.lost_stat], (u64)over);
                     }
-                    u32 pos = basepos + __popc(mm & ((1u << lane) - 1));
-                    pend.log_rec = (is_miss && pos < r.cap) ? r.buf + (size_t)pos * r.rec_bytes : nullptr;
+                    const u32 rpos = basepos + __popc(mm & ((1u << lane) - 1));
+                    pend.log_rec = (is_miss && rpos < r.cap) ? r.buf + (size_t)rpos * r.rec_bytes : nullptr;
                     pend.logged = false;
                     if (pend.log_rec) *(uint2 *)(pend.log_rec + r.rec_bytes - 8) = make_uint2(idx + b.base, c.batch_seq);
-                    while (mm) { // new flows of this subscriber, strictly in index order
-                        u32 l = __ffs(mm) - 1;
-                        mm &= mm - 1;
+                    bool dropped = false;
+                    u32 todo = mm;
+                    while (todo) {
+                        // the longest prefix of the remaining new flows that does not interact: all at once
+                        const u32 took = nat_chunk_coop(c, bs, b, sub, is_miss && ((todo >> lane) & 1), idx, len, pend, lane);
+                        todo &= ~took;
+                        if (lane == 0 && took) bstats_add(bs, ST_NAT_COOP, __popc(took));
+                        if (!todo) break;
+                        const u32 l = __ffs(todo) - 1; // ... then the frame that does, through the sequential code
+                        todo &= todo - 1;
                         if (lane == l) {
-                            NatOut o = nat_egress_one<true>(c, bs, frame_ptr(b, idx), len, frame_dlen(b, len), idx + b.base, b.now, &pend);
+                            NatOut o = nat_egress_one<true>(c, bs, frame_ptr(b, idx), sub, len, frame_dlen(b, len), idx + b.base, b.now, &pend);
                             if (o.verdict == TC_SHOT) {
                                 b.verdict[idx] = TC_SHOT;
                                 dropped = true;
                             }
-                            if (!pend.logged && pend.log_rec) // e.g. the session was created earlier in this batch
-                                *(uint2 *)(pend.log_rec + r.rec_bytes - 8) = make_uint2(0xFFFFFFFFu, c.batch_seq);
+                            bstats_add(bs, ST_NAT_SEQ, 1);
                         }
                         __syncwarp();
                     }
+                    if (is_miss && !pend.logged && pend.log_rec) // e.g. the session was created earlier in this batch
+                        *(uint2 *)(pend.log_rec + r.rec_bytes - 8) = make_uint2(0xFFFFFFFFu, c.batch_seq);
+                    if (dropped) s_sv[j] = sv | DROP_FLAG;
                 }
             }
-            if (has_bucket) {
-                const bool elig = valid && !dropped;
-                u32 em = __ballot_sync(0xffffffffu, elig);
-                if (em) {
-                    bool pass = true;
-                    if (tb.rate_bps != 0) { // rate 0: unlimited, bucket untouched (bpf/qos_ratelimit.c:77-78)
-                        tb_refill(tb, b.now);
-                        u32 mylen = elig ? len : 0;
-                        u32 tot = __reduce_add_sync(0xffffffffu, mylen);
-                        u32 mn = __reduce_min_sync(0xffffffffu, elig ? len : 0xffffffffu);
-                        if (tb.tokens >= (u64)tot) { // the whole chunk fits
-                            tb.tokens -= tot;
-                        } else if (tb.tokens < (u64)mn) { // nothing in the chunk fits
-                            pass = false;
-                        } else { // mixed: frame by frame, uniform across the warp
-                            pass = false;
-                            while (em) {
-                                u32 l = __ffs(em) - 1;
-                                em &= em - 1;
-                                u32 ll = __shfl_sync(0xffffffffu, len, l);
-                                bool ok = tb.tokens >= (u64)ll;
-                                if (ok) tb.tokens -= ll;
-                                if (lane == l) pass = ok;
+            if (NAT && QOS) __syncthreads();
+            // ---- token bucket over the staged lengths ----
+            if (QOS && slot) {
+                if (warp == 0) {
+                    for (u32 cb = 0; cb < nchunk; cb++) {
+                        const u32 j = cb * 32 + lane;
+                        const bool elig = j < n_here && !(s_sv[j] & DROP_FLAG);
+                        const u32 len = elig ? s_len[j] : 0;
+                        u32 em = __ballot_sync(0xffffffffu, elig);
+                        bool pass = true;
+                        if (em && tb.rate_bps != 0) { // rate 0: unlimited, bucket untouched (bpf/qos_ratelimit.c:77-78)
+                            tb_refill(tb, b.now);
+                            const u32 tot = __reduce_add_sync(0xffffffffu, len);
+                            const u32 mn = __reduce_min_sync(0xffffffffu, elig ? len : 0xffffffffu);
+                            if (tb.tokens >= (u64)tot) { // the whole chunk fits
+                                tb.tokens -= tot;
+                            } else if (tb.tokens < (u64)mn) { // nothing in the chunk fits
+                                pass = false;
+                            } else { // mixed: frame by frame, uniform across the warp
+                                pass = false;
+                                while (em) {
+                                    const u32 l = __ffs(em) - 1;
+                                    em &= em - 1;
+                                    const u32 ll = __shfl_sync(0xffffffffu, len, l);
+                                    const bool ok = tb.tokens >= (u64)ll;
+                                    if (ok) tb.tokens -= ll;
+                                    if (lane == l) pass = ok;
+                                }
                             }
                         }
+                        const u32 pm = __ballot_sync(0xffffffffu, pass);
+                        if (lane == 0) s_pass[cb] = pm;
                     }
-                    if (elig) {
-                        if (pass) {
-                            pp++;
-                            pb += len;
-                            if (EGRESS && b.priority) b.priority[idx] = tb.prio;
-                        } else {
-                            dp++;
-                            db += len;
-                            b.verdict[idx] = TC_SHOT;
-                        }
+                }
+                __syncthreads();
+                // ---- verdicts, priorities, statistics ----
+                for (u32 j = tid; j < n_here; j += TEAM) {
+                    const u32 sv = s_sv[j];
+                    if (sv & DROP_FLAG) continue;
+                    const u32 idx = sv & IDX_MASK, len = s_len[j];
+                    if ((s_pass[j >> 5] >> (j & 31)) & 1) {
+                        pp++;
+                        pb += len;
+                        if (EGRESS && b.priority) b.priority[idx] = tb.prio;
+                    } else {
+                        dp++;
+                        db += len;
+                        b.verdict[idx] = TC_SHOT;
                     }
                 }
             }
-            return vmask == 0xffffffffu; // else the group ended inside this chunk
-        };
-        // RESOLVE_CHUNKS chunks per trip: their (key, value) loads and their length gathers are issued
-        // together, which divides the number of dependent memory round trips of the walk; the chunks
-        // themselves are applied one after the other, in index order.
-        for (u32 q0 = start;; q0 += 32 * RESOLVE_CHUNKS) {
-            bool v[RESOLVE_CHUNKS], more = true;
-            u32 sv[RESOLVE_CHUNKS], ln[RESOLVE_CHUNKS];
-#pragma unroll
-            for (int t = 0; t < RESOLVE_CHUNKS; t++) {
-                const u32 q = q0 + 32 * t + lane;
-                v[t] = q < m && skey[q] == key;
-                sv[t] = v[t] ? sval[q] : 0;
-            }
-#pragma unroll
-            for (int t = 0; t < RESOLVE_CHUNKS; t++) ln[t] = v[t] ? b.len[sv[t] & ~MISS_FLAG] : 0;
-#pragma unroll
-            for (int t = 0; t < RESOLVE_CHUNKS; t++) more = more && chunk(v[t], sv[t], ln[t]);
-            if (!more) break;
+            if (n_here < (u32)STAGE) break; // the group ended inside this sweep
+            __syncthreads();                // ... else the staging buffers are reused
         }
-        if (has_bucket && lane == 0) {
+        if (QOS && slot && tid == 0) {
             *(u64 *)(slot + 16) = tb.tokens;
             *(u64 *)(slot + 24) = tb.last_update;
         }
+        __syncthreads();
     }
-    if (NAT) { // live-entry counts of the flow tables: one global atomic per warp and table
+    if (NAT && warp == 0) { // live-entry counts of the flow tables: one global atomic per block and table
         u32 a = __reduce_add_sync(0xffffffffu, pend.ses), r2 = __reduce_add_sync(0xffffffffu, pend.rev),
             e = __reduce_add_sync(0xffffffffu, pend.eim);
         if (lane == 0) {
@@ -770,9 +828,22 @@ static cudaError_t group_by_key(Launcher &L, u32 n, u64 key_space, Grouped *out)
     return cudaGetLastError();
 }
 
-// k_resolve walks one group per WARP and a batch of n frames can hold n groups: size its grid for n warps
-// (grid_for() still caps it at the resident-block limit), or a small batch leaves most of the GPU idle.
-#define WARP_PER_GROUP(n) ((u32)((u64)(n) * 32 > 0xFFFFFFFFull ? 0xFFFFFFFFull : (u64)(n) * 32))
+// k_resolve walks one group per block and a batch of n frames can hold n groups: the grid is sized for n blocks,
+// capped at what the GPU holds at once (the blocks loop over the groups).
+template <bool NAT, bool QOS, bool EGRESS, int TEAM>
+static void launch_resolve(Launcher &L, const DevCtx &c, const DevBatch &b, const Grouped &g, const char *name) {
+    int &per_sm = L.resolve_bps[(NAT ? 2 : 0) + (EGRESS ? 1 : 0)]; // resident blocks per SM of this instantiation
+    if (!per_sm) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resolve<NAT, QOS, EGRESS, TEAM>, TEAM, 0) != cudaSuccess || per_sm < 1)
+            per_sm = 8;
+    }
+    long cap = (long)L.num_sms * per_sm, want = b.n ? b.n : 1;
+    int grid = (int)(want < cap ? want : cap);
+    prof_begin(L, name);
+    k_resolve<NAT, QOS, EGRESS, TEAM><<<grid, TEAM, 0, L.stream>>>(c, b, g, L.s.qslot, L.s.counters);
+    prof_end(L);
+    L.launches++;
+}
 
 cudaError_t run_antispoof(Launcher &L, const DevCtx &c, const DevBatch &b) {
     LAUNCH(k_antispoof, b.n, 8, c, b);
@@ -786,18 +857,18 @@ cudaError_t run_qos(Launcher &L, const DevCtx &c, const DevBatch &b, bool egress
     cudaError_t e = group_by_key(L, b.n, (u64)t.mask + 1, &g);
     if (e != cudaSuccess) return e;
     if (egress)
-        LAUNCH((k_resolve<false, true, true>), WARP_PER_GROUP(b.n), 4, c, b, g, L.s.qslot, L.s.counters);
+        launch_resolve<false, true, true, 32>(L, c, b, g, "(k_resolve<false, true, true>)");
     else
-        LAUNCH((k_resolve<false, true, false>), WARP_PER_GROUP(b.n), 4, c, b, g, L.s.qslot, L.s.counters);
+        launch_resolve<false, true, false, 32>(L, c, b, g, "(k_resolve<false, true, false>)");
     return cudaGetLastError();
 }
 
 cudaError_t run_nat_egress(Launcher &L, const DevCtx &c, const DevBatch &b) {
     LAUNCH((k_pipe_classify<false, false>), b.n, CLASSIFY_BPS(false), c, b, L.s.key_a, L.s.val_a);
     Grouped g;
-    cudaError_t e = group_by_key(L, b.n, (u64)c.sub_nat.mask + 1, &g);
+    cudaError_t e = group_by_key(L, b.n, (u64)c.subdir.mask + 1, &g);
     if (e != cudaSuccess) return e;
-    LAUNCH((k_resolve<true, false, false>), WARP_PER_GROUP(b.n), 8, c, b, g, L.s.qslot, L.s.counters);
+    launch_resolve<true, false, false, 32>(L, c, b, g, "(k_resolve<true, false, false>)");
     return cudaGetLastError();
 }
 
@@ -813,10 +884,9 @@ cudaError_t run_nat_hairpin_xdp(Launcher &L, const DevCtx &c, const DevBatch &b)
 
 cudaError_t run_pipeline_up(Launcher &L, const DevCtx &c, const DevBatch &b) {
     LAUNCH((k_pipe_classify<true, true>), b.n, CLASSIFY_BPS(true), c, b, L.s.key_a, L.s.val_a);
-    u64 space = (u64)(c.qos_in.mask + 1) + (c.sub_nat.mask + 1);
     Grouped g;
-    cudaError_t e = group_by_key(L, b.n, space, &g);
+    cudaError_t e = group_by_key(L, b.n, (u64)c.subdir.mask + 1, &g);
     if (e != cudaSuccess) return e;
-    LAUNCH((k_resolve<true, true, false>), WARP_PER_GROUP(b.n), 8, c, b, g, L.s.qslot, L.s.counters);
+    launch_resolve<true, true, false, 32>(L, c, b, g, "(k_resolve<true, true, false>)");
     return cudaGetLastError();
 }

@@ -24,6 +24,10 @@ struct Launcher {
     int num_sms;
     Scratch s;
     unsigned long long launches;
+    // per-context (= per-device) launch configuration, filled on first use: nothing here may be process-wide,
+    // one process can hold contexts on several GPUs
+    int dhcp_smem_set;  // cudaFuncAttributeMaxDynamicSharedMemorySize applied on this context's device
+    int resolve_bps[4]; // resident blocks per SM of the k_resolve instantiations
     int prof;
     ProfPending pend[32];
     int npend;
@@ -55,5 +59,11 @@ cudaError_t run_scatter_frames(cudaStream_t st, int num_sms, u8 *arena, const u3
 
 // table maintenance (tableops.cu); keys/values/results are device pointers
 enum { TOP_UPDATE = 0, TOP_LOOKUP = 1, TOP_DELETE = 2 };
-cudaError_t run_table_op(Launcher &L, const Tbl &t, int op, const u8 *keys, u8 *vals, int *results, u64 n, u32 flags);
+// dir / dir_role: the subscriber directory and which half of it table t feeds (0 none, 1 subscriber_nat, 2 qos_ingress)
+cudaError_t run_table_op(Launcher &L, const Tbl &t, int op, const u8 *keys, u8 *vals, int *results, u64 n, u32 flags,
+                         const Tbl &dir, int dir_role);
+cudaError_t run_dir_clear_half(Launcher &L, const Tbl &dir, int role);
+cudaError_t run_epoch_reset(Launcher &L, const Tbl &sessions);
+// session expiry sweep (sweep.cu); n_expired: device counter, incremented by the number of sessions removed
+cudaError_t run_nat_sweep(Launcher &L, const DevCtx &c, u64 now, u32 *n_expired);
 cudaError_t run_table_dump(Launcher &L, const Tbl &t, u8 *keys_out, u8 *vals_out, u32 *count_out, u64 cap);

@@ -3,10 +3,11 @@
 //
 // All three stages key their mutable state on the subscriber's private
 // address, so one group-by serves both the NAT new-flow ordering and the
-// token-bucket ordering.  Ordering key: the qos_ingress bucket slot when the
-// subscriber has a bucket, else qos capacity + subscriber_nat slot.  MISS_FLAG
-// in the value marks frames whose NAT session must be created in the ordered
-// phase.
+// token-bucket ordering.  The per-address state is reached through the
+// subscriber directory (common.cuh): ONE 16-byte probe tells whether the
+// address owns a subscriber_nat entry, a qos_ingress bucket, and whether that
+// bucket is unlimited; the directory slot is the ordering key.  MISS_FLAG in
+// the value marks frames whose NAT session must be created in the ordered phase.
 //
 // The body is written as a sequence of warp-convergent phases (a predicate per
 // frame, __syncwarp() between phases): divergence would serialise the memory
@@ -14,13 +15,11 @@
 // gather-heavy kernel like this one.
 #pragma once
 
-// Resident blocks per SM each instantiation is compiled for: the three-stage pipeline keeps two 256-bit
-// table probes and the 64-byte header live at once and spills at 48 registers (5 blocks), so it runs 4
-// blocks of 64 registers; the NAT-only instantiation fits 48.
+// Resident blocks per SM each instantiation is compiled for (registers: 65536 / (256 x blocks)).
 #define CLASSIFY_BPS(AS) ((AS) ? 4 : 5)
 
-// AS: run antispoof_ingress first; QOS: look up the qos_ingress bucket.  <false,false> is the
-// standalone nat44_egress classify (ordering key = subscriber_nat slot).
+// AS: run antispoof_ingress first; QOS: honour the qos_ingress bucket.  <false,false> is the
+// standalone nat44_egress classify.
 template <bool AS, bool QOS>
 __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
     k_pipe_classify(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b, u32 *skey, u32 *sval) {
@@ -32,7 +31,9 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
     smem_stage_wait(&bar);
     const u32 as_cfg = st.as_cfg, nflags = st.nat_flags;
     const u32 lane = threadIdx.x & 31;
-    u32 n_allowed = 0, n_snat = 0;
+    const u32 epoch = c.epoch;
+    u32 n_allowed = 0, n_snat = 0, n_qpass = 0;
+    u64 n_qbytes = 0;
     // warp-uniform trip count: every lane stays in the loop, inactive lanes are predicated off
     for (u32 base = blockIdx.x * BLOCK + (threadIdx.x & ~31u); base < b.n; base += gridDim.x * BLOCK) {
         const u32 i = base + lane;
@@ -51,8 +52,7 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
         u64 mk = mac_key(h, 6);
         const u32 bi = tbl_hash<1>(&mk) & c.bindings.mask;
         u64 sk = saddr;
-        const u32 ai = tbl_hash<1>(&sk); // subscriber_nat and qos_ingress share the key, hence the hash
-        const u32 si = ai & c.sub_nat.mask, qi = ai & c.qos_in.mask;
+        const u32 di = tbl_hash<1>(&sk) & c.subdir.mask;
         u16 sport, dport;
         if (proto == 1) {
             sport = h.b16(38); // echo id stands in for the source port (bpf/nat44.c:647-649)
@@ -65,22 +65,17 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
         key[0] = (u64)saddr | ((u64)daddr << 32);
         key[1] = (u64)sport | ((u64)dport << 16) | ((u64)proto << 32);
         const u32 hi = tbl_hash<2>(key) & c.sessions.mask;
-        // whole 32-byte sectors per probe: the binding slot, and the flow slot's key + translation
-        u64 sw0 = K_EMPTY, qw0 = K_EMPTY, qrate0 = 0;
+        // whole 32-byte sectors per probe: the binding slot, and the flow slot's key + translation + counters
         BindVal bv;
         U256 s0;
         bv.s.w[0] = bv.s.w[1] = s0.w[0] = s0.w[1] = 0xFFFFFFFFu; // K_EMPTY
         s0.w[2] = s0.w[3] = 0;
+        ulonglong2 d0 = make_ulonglong2(K_EMPTY, ~0ull);
         const u8 *bslot0 = tbl_slot(c.bindings, bi);
         u8 *sslot0 = tbl_slot(c.sessions, hi);
         if (AS && dlen >= 14) bv.s = ldg256(bslot0);
         if (ip4) {
-            sw0 = *(const u64 *)tbl_slot(c.sub_nat, si);
-            if (QOS) { // key and the mirrored rate_bps in one 16-byte load
-                const ulonglong2 q = *(const ulonglong2 *)tbl_slot(c.qos_in, qi);
-                qw0 = q.x;
-                qrate0 = q.y;
-            }
+            d0 = *(const ulonglong2 *)tbl_slot(c.subdir, di);
             s0 = ldg256(sslot0);
         }
         const u64 kw0 = (u64)s0.w[0] | ((u64)s0.w[1] << 32), kw1 = (u64)s0.w[2] | ((u64)s0.w[3] << 32);
@@ -97,19 +92,29 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
         }
         const bool alive = act && v != TC_SHOT && ip4;
 
-        // ---- phase 3: table lookups of the NAT / QoS stages ----
-        const u8 *qsl = (QOS && alive) ? tbl_finish<1>(c.qos_in, &sk, qi, qw0, true) : nullptr;
+        // ---- phase 3: the subscriber directory: does this address own a NAT block / a bucket? ----
+        u32 nat_slot = DIR_NONE, qos_slot = DIR_NONE, dir_idx = 0;
+        if (alive) {
+            const u8 *de = tbl_finish<1>(c.subdir, &sk, di, d0.x, true);
+            if (de) {
+                const u64 w = de == tbl_slot(c.subdir, di) ? d0.y : *(const u64 *)(de + 8);
+                nat_slot = (u32)w;
+                qos_slot = (u32)(w >> 32);
+                dir_idx = (u32)((de - c.subdir.slots) >> 4);
+            }
+        }
         __syncwarp();
-        const bool priv = alive && ihl5 && is_private_ip(saddr);
-        const u8 *sub = priv ? tbl_finish<1>(c.sub_nat, &sk, si, sw0, true) : nullptr;
-        __syncwarp();
-        if (priv && !sub) bstats_add(bs, ST_NAT_PASSED, 1); // no allocation: to userspace (bpf/nat44.c:592-596)
-        // L4 header in bounds and a translatable protocol (:608-653)
-        bool go = sub != nullptr && (proto == 6 ? dlen >= 54u : ((proto == 17 || proto == 1) && dlen >= 42u));
+        if (!QOS) qos_slot = DIR_NONE;
+        const bool priv = alive && is_private_ip(saddr); // only private sources are translated (:583-585)
+        const bool has_sub = priv && nat_slot != DIR_NONE;
+        if (priv && !has_sub) bstats_add(bs, ST_NAT_PASSED, 1); // no allocation: to userspace (:592-596)
+        // L4 header in bounds and a translatable protocol (:608-653); fixed offsets need ihl = 5
+        bool go = has_sub && ihl5 && (proto == 6 ? dlen >= 54u : ((proto == 17 || proto == 1) && dlen >= 42u));
         if (go && proto != 1 && (nflags & (proto == 6 ? (NATF_ALG_FTP | NATF_ALG_SIP) : NATF_ALG_SIP)) && st.alg_n) {
             int ax = alg_find(st, ((u32)bswap16(dport) << 16) | proto);
             if (ax >= 0) { // ALG traffic goes to userspace untranslated (:615-642)
                 bstats_add(bs, ST_NAT_ALG, 1);
+                const u8 *sub = tbl_slot(c.sub_nat, nat_slot);
                 nat_log(c, i + b.base, b.now, 7, *(const u32 *)(sub + 32), saddr, 0, sport, 0, daddr, dport, (u8)proto, st.alg_type[ax]);
                 go = false;
             }
@@ -122,14 +127,13 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
 
         // ---- phase 4: session hit: counters and the SNAT rewrite (:674-680, :752-798) ----
         bool miss = go && !ses;
-        u32 sub_idx = miss ? (u32)((sub - c.sub_nat.slots) / c.sub_nat.slot_bytes) : 0;
         if (ses) {
-            // the key's own sector also carries nat_ip, nat_port|orig_port, last_seen
-            uint4 tr = make_uint4(s0.w[4], s0.w[5], s0.w[6], s0.w[7]);
-            if (ses != sslot0) tr = *(const uint4 *)(ses + SES_NAT_IP); // found on a later probe
+            // the key's own sector also carries nat_ip, nat_port | epoch, and the out-direction counters
+            uint2 tr = make_uint2(s0.w[4], s0.w[5]);
+            if (ses != sslot0) tr = *(const uint2 *)(ses + SES_NAT_IP); // found on a later probe
             const u32 nat_ip = tr.x;
             const u16 nat_port = (u16)tr.y;
-            if (((u64)tr.z | ((u64)tr.w << 32)) != b.now) *(u64 *)(ses + SES_LAST_SEEN) = b.now;
+            ses_touch(ses, b.now, tr.y >> 16, epoch);
             ses_count(ses, SES_OUT_LO, len);
             h.s32(26, nat_ip);
             h.s16(24, csum_upd32(h.b16(24), saddr, nat_ip));
@@ -166,27 +170,21 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
         __syncwarp();
 
         // ---- IPv4 options: fields are not at fixed offsets, take the generic path (rare) ----
-        if (alive && !ihl5) {
-            NatOut o = nat_egress_one<false>(c, bs, p, len, dlen, i + b.base, b.now);
+        if (has_sub && !ihl5) {
+            NatOut o = nat_egress_one<false>(c, bs, p, tbl_slot(c.sub_nat, nat_slot), len, dlen, i + b.base, b.now);
             v = o.verdict;
-            miss = o.order_key != NO_KEY;
-            sub_idx = o.order_key;
+            miss = o.miss;
         }
         __syncwarp();
 
-        // ---- phase 5: ordering key ----
+        // ---- phase 5: ordering key = the directory slot ----
         u32 okey = NO_KEY, oval = i;
         if (alive && v != TC_SHOT) {
-            if (qsl) {
-                const u64 rate = qsl == tbl_slot(c.qos_in, qi) ? qrate0 : *(const u64 *)(qsl + QOS_RATE_COPY);
-                if (!miss && rate == 0) { // unlimited bucket and nothing left to order
-                    bstats_add(bs, ST_QOS_PASS_PKTS, 1);
-                    bstats_add(bs, ST_QOS_PASS_BYTES, len);
-                } else {
-                    okey = (u32)((qsl - c.qos_in.slots) / c.qos_in.slot_bytes);
-                }
-            } else if (miss) {
-                okey = (QOS ? (c.qos_in.mask + 1) : 0u) + sub_idx;
+            if (qos_slot != DIR_NONE && (qos_slot & DIR_QOS_UNLIMITED) && !miss) {
+                n_qpass++; // unlimited bucket and nothing left to order (bpf/qos_ratelimit.c:77-78)
+                n_qbytes += len;
+            } else if (qos_slot != DIR_NONE || miss) {
+                okey = dir_idx;
             }
             if (miss) oval |= MISS_FLAG;
         }
@@ -198,5 +196,9 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
     }
     if (AS) warp_stat_flush(bs, ST_AS_ALLOWED, n_allowed);
     warp_stat_flush(bs, ST_NAT_SNAT, n_snat);
+    if (QOS) {
+        warp_stat_flush(bs, ST_QOS_PASS_PKTS, n_qpass);
+        warp_stat_flush64(bs, ST_QOS_PASS_BYTES, n_qbytes);
+    }
     bstats_flush(bs, c.stats);
 }

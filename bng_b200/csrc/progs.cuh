@@ -286,71 +286,101 @@ __device__ __forceinline__ void nat_snat_rewrite(u8 *p, u32 l4, u32 proto, u32 o
     }
 }
 
+// A freshly claimed nat_sessions slot becomes struct nat_session new_session (:713-728).
+__device__ __forceinline__ void nat_ses_fill(u8 *ns, u32 nat_ip, u16 nat_port, u16 sport, u32 saddr, u32 daddr, u16 dport,
+                                             u32 proto, u8 is_hairpin, u32 len, u64 now, u32 epoch) {
+    *(u32 *)(ns + SES_NAT_IP) = nat_ip;
+    *(u32 *)(ns + SES_NAT_PORT) = (u32)nat_port | (epoch << 16);
+    *(u64 *)(ns + SES_OUT_LO) = 1ull | ((u64)len << 32); // packets_out = 1, bytes_out = len
+    *(u64 *)(ns + SES_LAST_SEEN) = now;
+    *(u32 *)(ns + SES_ORIG_IP) = saddr;
+    *(u32 *)(ns + SES_STATE) = (proto << 8) | ((u32)is_hairpin << 24); // state NEW, protocol, flags 0, hairpin
+    *(u64 *)(ns + SES_ORIG_PORT) = (u64)sport;                           // orig_port, then 6 unused bytes
+    *(u64 *)(ns + SES_IN_LO) = 0;
+    *(u64 *)(ns + SES_OUT_HI) = 0;
+    *(u64 *)(ns + SES_IN_HI) = 0;
+    *(u64 *)(ns + SES_CREATED) = now;
+    *(u32 *)(ns + SES_DEST_IP) = daddr;
+    *(u32 *)(ns + SES_DEST_PORT) = (u32)dport; // dest_port, _pad1 = 0
+    *(u64 *)(ns + SES_PAD_A) = 0;              // the struct's padding bytes
+}
+
+// The parse of nat44_egress up to the session lookup (:569-665), shared by the sequential and the
+// warp-cooperative paths of the ordered phase.  `sub` is the frame's subscriber_nat slot (never null here).
+struct NatFlow {
+    u32 saddr, daddr, proto, l4;
+    u16 sport, dport;
+    u8 is_hairpin;
+    bool ok; // reaches the session lookup
+};
+template <bool COUNT>
+__device__ __forceinline__ NatFlow nat_parse(const DevCtx &c, BlockStats &bs, const u8 *p, u32 dlen, u32 idx, u64 now,
+                                             const u8 *sub, u32 cfg_flags) {
+    NatFlow f;
+    f.ok = false;
+    f.saddr = rd32(p, 26);
+    f.daddr = rd32(p, 30);
+    f.proto = p[23];
+    f.l4 = 14 + (u32)(p[14] & 0x0f) * 4;
+    f.sport = f.dport = 0;
+    f.is_hairpin = 0;
+    if (f.proto == 6 || f.proto == 17) {
+        if (f.l4 + (f.proto == 6 ? 20u : 8u) > dlen) return f;
+        f.sport = rd16(p, f.l4);
+        f.dport = rd16(p, f.l4 + 2);
+        u32 alg_mask = f.proto == 6 ? (NATF_ALG_FTP | NATF_ALG_SIP) : NATF_ALG_SIP;
+        if (cfg_flags & alg_mask) {
+            u64 ak = ((u32)bswap16(f.dport) << 16) | f.proto;
+            const u8 *alg = tbl_find<1, false>(c.alg, &ak);
+            if (alg) { // ALG traffic goes to userspace untranslated (:615-642)
+                if (COUNT) {
+                    bstats_add(bs, ST_NAT_ALG, 1);
+                    nat_log(c, idx, now, 7, *(const u32 *)(sub + 32), f.saddr, 0, f.sport, 0, f.daddr, f.dport, (u8)f.proto,
+                            alg[8 + 3]);
+                }
+                return f;
+            }
+        }
+    } else if (f.proto == 1) {
+        if (f.l4 + 8 > dlen) return f;
+        f.sport = rd16(p, f.l4 + 4); // echo id stands in for the source port (:647-649)
+    } else {
+        return f;
+    }
+    if (cfg_flags & NATF_HAIRPIN) {
+        u64 hk = f.daddr;
+        if (tbl_find<1, false>(c.hairpin, &hk)) {
+            f.is_hairpin = 1;
+            if (COUNT) bstats_add(bs, ST_NAT_HAIRPIN, 1);
+        }
+    }
+    f.ok = true;
+    return f;
+}
+
 struct NatOut {
     int verdict;
-    u32 order_key; // subscriber_nat slot index when the frame needs the ordered phase
+    bool miss; // classify only: the session does not exist yet, the ordered phase has to create it
 };
 
-// nat44_egress, :565-802.
-//   RESOLVE=false (classify): everything up to the session lookup, the hit
-//     path, and the rewrite for hits.  A session miss returns order_key.
+// nat44_egress, :565-802, from the subscriber_nat lookup on (the caller did the Ethernet / IPv4 / private-source
+// checks and found `sub`).
+//   RESOLVE=false (classify, frames with IPv4 options): everything up to the session lookup, the hit
+//     path, and the rewrite for hits.  A session miss is reported back.
 //   RESOLVE=true: full sequential semantics for one frame, executed by the
 //     subscriber's worker in frame-index order; counters that classify
 //     already bumped for this frame (hairpin) are not bumped again.
 template <bool RESOLVE>
-__device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs, u8 *p, u32 len, u32 dlen, u32 idx, u64 now,
-                                                 NatPend *pd = nullptr) {
-    NatOut o; // dlen = data_end - data (bounds checks), len = skb->len (bytes_out)
+__device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs, u8 *p, u8 *sub, u32 len, u32 dlen, u32 idx,
+                                                 u64 now, NatPend *pd = nullptr) {
+    NatOut o;
     o.verdict = TC_OK;
-    o.order_key = NO_KEY;
-    if (dlen < 14) return o;
-    if (rd16(p, 12) != ETH_P_IP_LE) return o;
-    if (dlen < 34) return o;
-    u32 saddr = rd32(p, 26);
-    if (!is_private_ip(saddr)) return o;
-    u64 sk = saddr;
-    u8 *sub = tbl_find<1, RESOLVE, RESOLVE>(c.sub_nat, &sk);
-    if (!sub) {
-        if (!RESOLVE) bstats_add(bs, ST_NAT_PASSED, 1);
-        return o;
-    }
-    u32 cfg_flags = *(const u32 *)c.nat_config;
-    u32 daddr = rd32(p, 30);
-    u32 proto = p[23];
-    u32 l4 = 14 + (u32)(p[14] & 0x0f) * 4;
-    u16 sport = 0, dport = 0;
-    if (proto == 6 || proto == 17) {
-        if (l4 + (proto == 6 ? 20u : 8u) > dlen) return o;
-        sport = rd16(p, l4);
-        dport = rd16(p, l4 + 2);
-        u32 alg_mask = proto == 6 ? (NATF_ALG_FTP | NATF_ALG_SIP) : NATF_ALG_SIP;
-        if (cfg_flags & alg_mask) {
-            u64 ak = ((u32)bswap16(dport) << 16) | proto;
-            const u8 *alg = tbl_find<1, false>(c.alg, &ak);
-            if (alg) { // ALG traffic goes to userspace untranslated (:615-642)
-                if (!RESOLVE) {
-                    bstats_add(bs, ST_NAT_ALG, 1);
-                    nat_log(c, idx, now, 7, *(const u32 *)(sub + 32), saddr, 0, sport, 0, daddr, dport, (u8)proto,
-                            alg[8 + 3]);
-                }
-                return o;
-            }
-        }
-    } else if (proto == 1) {
-        if (l4 + 8 > dlen) return o;
-        sport = rd16(p, l4 + 4); // echo id stands in for the source port (:647-649)
-        dport = 0;
-    } else {
-        return o;
-    }
-    u8 is_hairpin = 0;
-    if (cfg_flags & NATF_HAIRPIN) {
-        u64 hk = daddr;
-        if (tbl_find<1, false>(c.hairpin, &hk)) {
-            is_hairpin = 1;
-            if (!RESOLVE) bstats_add(bs, ST_NAT_HAIRPIN, 1);
-        }
-    }
+    o.miss = false;
+    const u32 cfg_flags = *(const u32 *)c.nat_config;
+    const NatFlow f = nat_parse<!RESOLVE>(c, bs, p, dlen, idx, now, sub, cfg_flags);
+    if (!f.ok) return o;
+    const u32 saddr = f.saddr, daddr = f.daddr, proto = f.proto;
+    const u16 sport = f.sport, dport = f.dport;
     u64 key[2];
     key[0] = (u64)saddr | ((u64)daddr << 32);
     key[1] = (u64)sport | ((u64)dport << 16) | ((u64)proto << 32);
@@ -358,13 +388,14 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
     u32 nat_ip;
     u16 nat_port;
     if (ses) { // :674-680
+        const u32 tr = *(const volatile u32 *)(ses + SES_NAT_PORT);
         nat_ip = *(const u32 *)(ses + SES_NAT_IP);
-        nat_port = *(const u16 *)(ses + SES_NAT_PORT);
-        ses_touch(ses, now);
+        nat_port = (u16)tr;
+        ses_touch(ses, now, tr >> 16, c.epoch);
         ses_count(ses, SES_OUT_LO, len);
     } else {
         if (!RESOLVE) {
-            o.order_key = (u32)((sub - c.sub_nat.slots) / c.sub_nat.slot_bytes);
+            o.miss = true;
             return o;
         }
         u32 sub_id = *(const u32 *)(sub + 32);
@@ -383,7 +414,7 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
                     bstats_add(bs, ST_NAT_EXHAUST, 1);
                 } else {
                     bool created;
-                    m = tbl_find_or_claim<1, true>(c.eim, &ek, &created, pd ? &pd->eim : nullptr);
+                    m = tbl_find_or_claim<1, true>(c.eim, &ek, &created, pd ? &pd->eim : nullptr, c.stats);
                     if (m && created) {
                         *(u32 *)(m + 8) = pub_ip;
                         *(u32 *)(m + 12) = ext; // external_port (host order) + zero pad
@@ -420,21 +451,9 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
             nat_port = bswap16(ap);
         }
         bool created;
-        u8 *ns = tbl_find_or_claim<2, true>(c.sessions, key, &created, pd ? &pd->ses : nullptr); // BPF_ANY (:730)
+        u8 *ns = tbl_find_or_claim<2, true>(c.sessions, key, &created, pd ? &pd->ses : nullptr, c.stats); // BPF_ANY (:730)
         if (ns) {
-            *(u32 *)(ns + SES_NAT_IP) = nat_ip;
-            *(u32 *)(ns + SES_NAT_PORT) = (u32)nat_port | ((u32)sport << 16); // nat_port, orig_port
-            *(u32 *)(ns + SES_ORIG_IP) = saddr;
-            *(u32 *)(ns + SES_STATE) = (proto << 8) | ((u32)is_hairpin << 24); // state NEW, protocol, flags 0, hairpin
-            *(u64 *)(ns + SES_LAST_SEEN) = now;
-            *(u64 *)(ns + SES_OUT_LO) = 1ull | ((u64)len << 32); // packets_out = 1, bytes_out = len
-            *(u64 *)(ns + SES_OUT_HI) = 0;
-            *(u64 *)(ns + SES_IN_LO) = 0;
-            *(u64 *)(ns + SES_IN_HI) = 0;
-            *(u64 *)(ns + SES_CREATED) = now;
-            *(u32 *)(ns + SES_DEST_IP) = daddr;
-            *(u32 *)(ns + SES_DEST_PORT) = (u32)dport; // dest_port, _pad1 = 0
-            *(u64 *)(ns + 88) = 0;                      // the struct's padding bytes
+            nat_ses_fill(ns, nat_ip, nat_port, sport, saddr, daddr, dport, proto, f.is_hairpin, len, now, c.epoch);
             if (created) tbl_publish<false>(ns, key[0]);
         } else {
             bstats_add(bs, ST_LRU_OVERFLOW, 1);
@@ -442,7 +461,7 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
         u64 rk[2];
         rk[0] = (u64)daddr | ((u64)nat_ip << 32);
         rk[1] = (u64)dport | ((u64)nat_port << 16) | ((u64)proto << 32);
-        u8 *rs = tbl_find_or_claim<2, true>(c.reverse, rk, &created, pd ? &pd->rev : nullptr); // BPF_ANY (:740)
+        u8 *rs = tbl_find_or_claim<2, true>(c.reverse, rk, &created, pd ? &pd->rev : nullptr, c.stats); // BPF_ANY (:740)
         if (rs) {
             *(u64 *)(rs + 16) = key[0];
             *(u64 *)(rs + 24) = key[1];
@@ -453,11 +472,186 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
         atomicAdd((u64 *)(sub + 40), 1ull);
         atomicAdd((u64 *)(sub + 48), 1ull);
         bstats_add(bs, ST_NAT_CREATED, 1);
-        nat_log(c, idx, now, 1, sub_id, saddr, nat_ip, sport, nat_port, daddr, dport, (u8)proto, is_hairpin, pd);
+        nat_log(c, idx, now, 1, sub_id, saddr, nat_ip, sport, nat_port, daddr, dport, (u8)proto, f.is_hairpin, pd);
     }
-    nat_snat_rewrite(p, l4, proto, saddr, nat_ip, nat_port);
+    nat_snat_rewrite(p, f.l4, proto, saddr, nat_ip, nat_port);
     bstats_add(bs, ST_NAT_SNAT, 1);
     return o;
+}
+
+// ---------------------------------------------------------------------------
+// The ordered phase, warp-cooperatively: up to 32 new-flow frames of ONE subscriber (consecutive in index
+// order) are created together.  The sequential walk above spends ~15 dependent table accesses per flow
+// with one lane active; here every lane parses its frame, probes nat_sessions / eim_table and proposes its
+// port at once, and the creations are committed in parallel.  That is only equivalent to running the
+// frames one after the other when they do not interact, so the warp first finds the longest PREFIX (in
+// index order) of the frames still to do that provably does not — nothing is modified until it has —
+// commits that prefix and returns its lane mask; the caller runs the first frame after it through the
+// sequential code and calls again for the rest.  A frame ends the prefix when
+//   - an EARLIER frame of the chunk has the same 5-tuple, the same (address, port, protocol) endpoint
+//     without a mapping yet, or the same nat_reverse key (the later frame must see what the earlier one
+//     created, :469-487, :674, :740)
+//   - its proposed port collides with an existing endpoint or with one an earlier frame of the chunk
+//     creates (allocate_port_from_block() would skip it, :450-459)
+//   - its proposed port lies past the end of the block (the counter wraps at that frame)
+// and nothing is committed (mask 0) when port parity is filtered or a flow table is within 64 entries of
+// max_entries: those chunks go frame by frame.
+// Exhaustion never happens on the cooperative path: every proposed port is inside the block.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ u32 nat_chunk_coop(const DevCtx &c, BlockStats &bs, const DevBatch &b, u8 *sub, bool mine, u32 idx,
+                                              u32 len, NatPend &pend, u32 lane) {
+    const u32 cfg_flags = *(const u32 *)c.nat_config;
+    if (cfg_flags & NATF_PARITY) return 0;
+    const bool eim_on = (cfg_flags & NATF_EIM) != 0;
+    u8 *p = mine ? frame_ptr(b, idx) : nullptr;
+    NatFlow f;
+    f.ok = false;
+    if (mine) f = nat_parse<false>(c, bs, p, frame_dlen(b, len), idx + b.base, b.now, sub, cfg_flags);
+    const bool go = mine && f.ok; // (a frame classify flagged always parses; kept as a guard)
+    u64 key[2] = {0, 0}, ek = 0;
+    u8 *ses = nullptr, *m = nullptr;
+    if (go) {
+        key[0] = (u64)f.saddr | ((u64)f.daddr << 32);
+        key[1] = (u64)f.sport | ((u64)f.dport << 16) | ((u64)f.proto << 32);
+        ek = (u64)f.saddr | ((u64)f.sport << 32) | ((u64)f.proto << 48);
+        ses = tbl_find<2, true, true>(c.sessions, key);
+        if (!ses && eim_on) m = tbl_find<1, true, true>(c.eim, &ek);
+    }
+    const bool create = go && !ses;          // needs a session
+    const bool alloc = create && !m;         // ... and a port (EIM: a new mapping)
+    const u32 below = (1u << lane) - 1;
+    const u32 cmask = __ballot_sync(0xffffffffu, create), amask = __ballot_sync(0xffffffffu, alloc);
+    bool clash = false, all_clash = false; // clash: this frame ends the prefix; all_clash: nothing can be committed
+    if (cmask) {
+        // same 5-tuple as an earlier creating lane?
+        const u32 g0 = __match_any_sync(0xffffffffu, create ? key[0] : (u64)lane | (1ull << 63));
+        const u32 g1 = __match_any_sync(0xffffffffu, create ? key[1] : (u64)lane | (1ull << 63));
+        if (create && (g0 & g1 & cmask & below)) clash = true;
+        // same endpoint as an earlier lane that would create its mapping?
+        if (eim_on) {
+            const u32 ge = __match_any_sync(0xffffffffu, alloc ? ek : (u64)lane | (1ull << 63));
+            if (alloc && (ge & amask & below)) clash = true;
+        }
+    }
+    const u32 nalloc = __popc(amask);
+    u32 port = 0;
+    const u32 port_start = *(const u16 *)(sub + 12), port_end = *(const u16 *)(sub + 14);
+    const u32 next = *(volatile u32 *)(sub + 16);
+    const u32 pub_ip = *(const u32 *)(sub + 8);
+    if (nalloc) {
+        if (next > 0xFFFFu) all_clash = true;
+        port = next + __popc(amask & below);
+        if (alloc && port > port_end) clash = true; // the counter wraps here: that frame goes through the sequential code
+        const u64 ck = (u64)f.saddr | ((u64)port << 32) | ((u64)f.proto << 48);
+        if (alloc && !all_clash && tbl_find<1, true, true>(c.eim, &ck)) clash = true; // candidate taken (:450-459)
+        if (eim_on) { // ... or about to be: an endpoint an earlier lane creates whose network-order port reads as my candidate
+            for (u32 j = 0; j < 32; j++) {
+                const u64 o = __shfl_sync(0xffffffffu, ek, j);
+                if (alloc && j < lane && ((amask >> j) & 1) && o == ck) clash = true;
+            }
+        }
+    }
+    // translation of every creating lane, and its nat_reverse key: an earlier flow of the chunk must not own it
+    // (a port handed out twice after the counter wrapped; :740 is BPF_ANY, the later frame has to win)
+    u32 nat_ip = 0;
+    u16 nat_port = 0;
+    u64 rk[2] = {0, 0};
+    if (create) {
+        nat_ip = m ? *(const u32 *)(m + 8) : pub_ip;
+        nat_port = m ? bswap16(*(const u16 *)(m + 12)) : bswap16((u16)port);
+        rk[0] = (u64)f.daddr | ((u64)nat_ip << 32);
+        rk[1] = (u64)f.dport | ((u64)nat_port << 16) | ((u64)f.proto << 32);
+    }
+    const u32 ncreate = __popc(cmask);
+    if (ncreate) {
+        const u32 r0 = __match_any_sync(0xffffffffu, create ? rk[0] : (u64)lane | (1ull << 63));
+        const u32 r1 = __match_any_sync(0xffffffffu, create ? rk[1] : (u64)lane | (1ull << 63));
+        if (create && (r0 & r1 & cmask & below)) clash = true;
+        const u32 room = 64 + ncreate;
+        if (*(volatile u32 *)c.sessions.count + pend.ses + room >= c.sessions.max_entries ||
+            *(volatile u32 *)c.reverse.count + pend.rev + room >= c.reverse.max_entries ||
+            (eim_on && *(volatile u32 *)c.eim.count + pend.eim + room >= c.eim.max_entries))
+            all_clash = true;
+    }
+    if (__any_sync(0xffffffffu, all_clash)) return 0;
+    // the prefix: every frame of this call below the first one that interacts with an earlier frame
+    const u32 todo = __ballot_sync(0xffffffffu, mine), cl = __ballot_sync(0xffffffffu, clash);
+    const u32 take = cl ? (todo & ((1u << (__ffs(cl) - 1)) - 1)) : todo;
+    if (!take) return 0;
+    const bool in = (take >> lane) & 1;
+    const u32 nalloc_take = __popc(amask & take);
+
+    // ---- commit: nothing below depends on another lane of the chunk ----
+    if (nalloc_take && lane == 0) {
+        const u32 nn = next + nalloc_take;
+        *(volatile u32 *)(sub + 16) = nn > port_end ? port_start : nn;
+    }
+    u32 n_hit = 0, n_miss = 0, n_created = 0, n_snat = 0;
+    if (go && in) {
+        const u32 sub_id = *(const u32 *)(sub + 32);
+        if (ses) { // created earlier in this batch (or by a previous chunk): the hit path, :674-680
+            const u32 tr = *(const volatile u32 *)(ses + SES_NAT_PORT);
+            nat_ip = *(const u32 *)(ses + SES_NAT_IP);
+            nat_port = (u16)tr;
+            ses_touch(ses, b.now, tr >> 16, c.epoch);
+            ses_count(ses, SES_OUT_LO, len);
+        } else {
+            if (m) { // existing endpoint mapping (:482-487)
+                *(u64 *)(m + 24) = b.now;
+                atomicAdd((u32 *)(m + 32), 1u);
+                n_hit = 1;
+            } else if (eim_on) { // new mapping (:495-517)
+                bool created;
+                u8 *nm = tbl_find_or_claim<1, true>(c.eim, &ek, &created, &pend.eim, c.stats);
+                if (nm && created) {
+                    *(u32 *)(nm + 8) = pub_ip;
+                    *(u32 *)(nm + 12) = port;
+                    *(u64 *)(nm + 16) = b.now;
+                    *(u64 *)(nm + 24) = b.now;
+                    *(u32 *)(nm + 32) = 1;
+                    *(u32 *)(nm + 36) = 0;
+                    tbl_publish<false>(nm, ek);
+                } else {
+                    bstats_add(bs, ST_LRU_OVERFLOW, 1); // unreachable: room was checked
+                }
+                n_miss = 1;
+            }
+            bool created;
+            u8 *ns = tbl_find_or_claim<2, true>(c.sessions, key, &created, &pend.ses, c.stats);
+            if (ns) {
+                nat_ses_fill(ns, nat_ip, nat_port, f.sport, f.saddr, f.daddr, f.dport, f.proto, f.is_hairpin, len, b.now, c.epoch);
+                if (created) tbl_publish<false>(ns, key[0]);
+            } else {
+                bstats_add(bs, ST_LRU_OVERFLOW, 1);
+            }
+            u8 *rs = tbl_find_or_claim<2, true>(c.reverse, rk, &created, &pend.rev, c.stats);
+            if (rs) {
+                *(u64 *)(rs + 16) = key[0];
+                *(u64 *)(rs + 24) = key[1];
+                if (created) tbl_publish<false>(rs, rk[0]);
+            } else {
+                bstats_add(bs, ST_LRU_OVERFLOW, 1);
+            }
+            n_created = 1;
+            nat_log(c, idx + b.base, b.now, 1, sub_id, f.saddr, nat_ip, f.sport, nat_port, f.daddr, f.dport, (u8)f.proto, f.is_hairpin,
+                    &pend);
+        }
+        nat_snat_rewrite(p, f.l4, f.proto, f.saddr, nat_ip, nat_port);
+        n_snat = 1;
+    }
+    const u32 t_created = __reduce_add_sync(0xffffffffu, n_created), t_hit = __reduce_add_sync(0xffffffffu, n_hit),
+              t_miss = __reduce_add_sync(0xffffffffu, n_miss), t_snat = __reduce_add_sync(0xffffffffu, n_snat);
+    if (lane == 0) {
+        if (t_created) {
+            atomicAdd((u64 *)(sub + 40), (u64)t_created);
+            atomicAdd((u64 *)(sub + 48), (u64)t_created);
+            bstats_add(bs, ST_NAT_CREATED, t_created);
+        }
+        if (t_hit) bstats_add(bs, ST_NAT_EIM_HIT, t_hit);
+        if (t_miss) bstats_add(bs, ST_NAT_EIM_MISS, t_miss);
+        if (t_snat) bstats_add(bs, ST_NAT_SNAT, t_snat);
+    }
+    return take;
 }
 
 // nat44_ingress, :805-948.  Every update is commutative (or made so with a
@@ -508,7 +702,7 @@ __device__ __forceinline__ int nat_ingress_one(const DevCtx &c, BlockStats &bs, 
             bstats_add(bs, ST_NAT_PASSED, 1);
         return TC_OK;
     }
-    ses_touch(ses, now);
+    ses_touch(ses, now, *(const volatile u16 *)(ses + SES_EPOCH), c.epoch);
     ses_count(ses, SES_IN_LO, len);
     if (proto == 6) { // :885-895; CLOSING(3) is absorbing, NEW(0)->ESTABLISHED(1) on ack
         u32 tf = p[l4 + 13];

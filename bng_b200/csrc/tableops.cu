@@ -23,6 +23,7 @@ __device__ __forceinline__ void copy_bytes(u8 *dst, const u8 *src, u32 n) {
 __device__ __forceinline__ void val_to_slot(const Tbl &t, u8 *slot, const u8 *abi) {
     if (t.vlayout == VL_SESSION) {
         for (u32 i = 0; i < t.value_size; i++) slot[ses_abi_to_slot(i)] = abi[i];
+        *(u16 *)(slot + SES_EPOCH) = 0; // last_seen came from the control plane: no batch has stamped it
     } else {
         copy_bytes(slot + t.voff, abi, t.value_size);
         // token buckets: rate_bps (value offset 16) is mirrored next to the key, so that the per-frame
@@ -38,8 +39,33 @@ __device__ __forceinline__ void val_from_slot(const Tbl &t, u8 *abi, const u8 *s
     }
 }
 
+// ---- subscriber directory (common.cuh): derived from subscriber_nat and qos_ingress ----
+// role: which half of the directory entry the table being changed owns
+enum { DIR_ROLE_NONE = 0, DIR_ROLE_NAT = 1, DIR_ROLE_QOS = 2 };
+
+__device__ __forceinline__ void dir_set(const Tbl &dir, u64 key, int role, u32 val) {
+    bool created;
+    u8 *d = tbl_find_or_claim<1>(dir, &key, &created);
+    if (!d) return; // cannot happen: the directory is sized for both maps' max_entries
+    if (created) *(u64 *)(d + 8) = ~0ull; // DIR_NONE | DIR_NONE << 32
+    *(u32 *)(d + (role == DIR_ROLE_NAT ? 8 : 12)) = val;
+    if (created) tbl_publish(d, key);
+}
+__device__ __forceinline__ void dir_unset(const Tbl &dir, u64 key, int role) {
+    u8 *d = tbl_find<1, true>(dir, &key);
+    if (!d) return;
+    *(u32 *)(d + (role == DIR_ROLE_NAT ? 8 : 12)) = DIR_NONE;
+    if (*(volatile u64 *)(d + 8) == ~0ull) tbl_erase<1>(dir, &key); // neither map knows the address any more
+}
+__device__ __forceinline__ u32 dir_value(const Tbl &t, const u8 *slot, int role) {
+    u32 idx = (u32)((slot - t.slots) / t.slot_bytes);
+    if (role == DIR_ROLE_QOS && *(const u64 *)(slot + QOS_RATE_COPY) == 0) idx |= DIR_QOS_UNLIMITED;
+    return idx;
+}
+
 template <int KW>
-__global__ void k_table_op(const __grid_constant__ Tbl t, int op, const u8 *keys, u8 *vals, int *results, u64 n, u32 flags) {
+__global__ void k_table_op(const __grid_constant__ Tbl t, int op, const u8 *keys, u8 *vals, int *results, u64 n, u32 flags,
+                           const __grid_constant__ Tbl dir, int dir_role) {
     for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
         u64 kw[KW];
         load_key<KW>(t, keys + i * t.key_size, kw);
@@ -54,17 +80,19 @@ __global__ void k_table_op(const __grid_constant__ Tbl t, int op, const u8 *keys
                 r = -ENOENT;
         } else if (op == TOP_DELETE) {
             r = tbl_erase<KW>(t, kw) ? 0 : -ENOENT;
+            if (!r && dir_role) dir_unset(dir, kw[0], dir_role);
         } else {
             const u8 *v = vals + i * t.value_size;
+            u8 *s = nullptr;
             if (flags == 2) { // BPF_EXIST
-                u8 *s = tbl_find<KW, true>(t, kw);
+                s = tbl_find<KW, true>(t, kw);
                 if (s)
                     val_to_slot(t, s, v);
                 else
                     r = -ENOENT;
             } else {
                 bool created;
-                u8 *s = tbl_find_or_claim<KW>(t, kw, &created);
+                s = tbl_find_or_claim<KW>(t, kw, &created);
                 if (!s) {
                     r = -E2BIG;
                 } else if (!created && flags == 1) { // BPF_NOEXIST
@@ -76,8 +104,30 @@ __global__ void k_table_op(const __grid_constant__ Tbl t, int op, const u8 *keys
                     if (created) tbl_publish(s, kw[0]);
                 }
             }
+            if (!r && dir_role) dir_set(dir, kw[0], dir_role, dir_value(t, s, dir_role));
         }
         results[i] = r;
+    }
+}
+
+// bng_map_clear() of subscriber_nat / qos_ingress: that half of every directory entry goes
+__global__ void k_dir_clear_half(const __grid_constant__ Tbl dir, int role) {
+    u64 slots = (u64)dir.mask + 1;
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < slots; i += (u64)gridDim.x * blockDim.x) {
+        u8 *d = dir.slots + i * 16;
+        const u64 k = *(volatile u64 *)d;
+        if (k >= K_BUSY) continue;
+        *(u32 *)(d + (role == DIR_ROLE_NAT ? 8 : 12)) = DIR_NONE;
+        if (*(volatile u64 *)(d + 8) == ~0ull && atomicCAS((u64 *)d, k, K_TOMB) == k) atomicSub(dir.count, 1u);
+    }
+}
+
+// nat_sessions: every slot's epoch back to "never" (the 16-bit batch counter is about to reuse its values)
+__global__ void k_epoch_reset(const __grid_constant__ Tbl t) {
+    u64 slots = (u64)t.mask + 1;
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < slots; i += (u64)gridDim.x * blockDim.x) {
+        u8 *s = t.slots + i * t.slot_bytes;
+        if (*(const u64 *)s < K_BUSY) *(u16 *)(s + SES_EPOCH) = 0;
     }
 }
 
@@ -94,17 +144,30 @@ __global__ void k_table_dump(const __grid_constant__ Tbl t, u8 *keys_out, u8 *va
     }
 }
 
-cudaError_t run_table_op(Launcher &L, const Tbl &t, int op, const u8 *keys, u8 *vals, int *results, u64 n, u32 flags) {
+cudaError_t run_table_op(Launcher &L, const Tbl &t, int op, const u8 *keys, u8 *vals, int *results, u64 n, u32 flags,
+                         const Tbl &dir, int dir_role) {
     if (n == 0) return cudaSuccess;
     int block = 128;
     u64 want = (n + block - 1) / block;
     int grid = (int)(want < (u64)L.num_sms * 8 ? want : (u64)L.num_sms * 8);
     if (t.key_size <= 8)
-        k_table_op<1><<<grid, block, 0, L.stream>>>(t, op, keys, vals, results, n, flags);
+        k_table_op<1><<<grid, block, 0, L.stream>>>(t, op, keys, vals, results, n, flags, dir, dir_role);
     else if (t.key_size == 16)
-        k_table_op<2><<<grid, block, 0, L.stream>>>(t, op, keys, vals, results, n, flags);
+        k_table_op<2><<<grid, block, 0, L.stream>>>(t, op, keys, vals, results, n, flags, dir, 0);
     else
-        k_table_op<4><<<grid, block, 0, L.stream>>>(t, op, keys, vals, results, n, flags);
+        k_table_op<4><<<grid, block, 0, L.stream>>>(t, op, keys, vals, results, n, flags, dir, 0);
+    L.launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t run_dir_clear_half(Launcher &L, const Tbl &dir, int role) {
+    k_dir_clear_half<<<L.num_sms * 4, 256, 0, L.stream>>>(dir, role);
+    L.launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t run_epoch_reset(Launcher &L, const Tbl &sessions) {
+    k_epoch_reset<<<L.num_sms * 8, 256, 0, L.stream>>>(sessions);
     L.launches++;
     return cudaGetLastError();
 }

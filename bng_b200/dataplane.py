@@ -74,6 +74,13 @@ def load_library() -> C.CDLL:
         "bng_map_update_batch": ([vp, i32, vp, vp, u64, u64], i32),
         "bng_map_lookup": ([vp, i32, vp, vp], i32),
         "bng_map_delete": ([vp, i32, vp], i32),
+        "bng_map_update_staged": ([vp, i32, vp, vp], i32),
+        "bng_staged_info": ([vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)], i32),
+        "bng_comm_unique_id": ([vp, u64], i32),
+        "bng_comm_init": ([vp, vp, u32, u32], i32),
+        "bng_sync_reduce": ([vp, vp], i32),
+        "bng_sweep": ([vp, u64, C.POINTER(u64)], i32),
+        "bng_lru_evictions": ([vp], u64),
         "bng_map_dump": ([vp, i32, vp, vp, u64], C.c_int64),
         "bng_map_clear": ([vp, i32], i32),
         "bng_prog_id": ([vp, C.c_char_p], i32),
@@ -106,7 +113,8 @@ EXPORTED_SYMBOLS = (
     "bng_prog_id",
     "bng_prog_run", "bng_sync", "bng_stream", "bng_events_drain", "bng_event_size", "bng_shard_of_mac",
     "bng_stats_device_ptr", "bng_launch_count", "bng_lru_overflow", "bng_events_lost", "bng_prof_enable",
-    "bng_prof_read", "bng_host_alloc", "bng_host_free",
+    "bng_prof_read", "bng_host_alloc", "bng_host_free", "bng_map_update_staged", "bng_staged_info",
+    "bng_comm_unique_id", "bng_comm_init", "bng_sync_reduce", "bng_sweep", "bng_lru_evictions",
 )
 
 
@@ -207,6 +215,19 @@ class Dataplane:
         self._chk(r, "map_lookup")
         return out
 
+    def update_staged(self, name: str, key, value) -> int:
+        """Queue a BPF_ANY upsert; applied at the next batch boundary / sync / read of the same map."""
+        k = np.ascontiguousarray(as_bytes(np.asarray(key))).reshape(-1)
+        v = np.ascontiguousarray(as_bytes(np.asarray(value))).reshape(-1)
+        ks, vs = self._sizes(name)
+        assert k.size == ks and v.size == vs, (name, k.size, ks, v.size, vs)
+        return self.lib.bng_map_update_staged(self.h, self.map_id(name), k.ctypes.data, v.ctypes.data)
+
+    def staged_info(self) -> dict:
+        p, f, e = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._chk(self.lib.bng_staged_info(self.h, C.byref(p), C.byref(f), C.byref(e)), "staged_info")
+        return {"pending": p.value, "flushes": f.value, "errors": e.value}
+
     def delete(self, name: str, key) -> int:
         k = np.ascontiguousarray(as_bytes(np.asarray(key))).reshape(-1)
         return self.lib.bng_map_delete(self.h, self.map_id(name), k.ctypes.data)
@@ -280,6 +301,16 @@ class Dataplane:
     def sync(self):
         self._chk(self.lib.bng_sync(self.h), "sync")
 
+    def sweep(self, now_ns: int) -> int:
+        """Session expiry sweep at now_ns; returns the number of sessions removed."""
+        n = C.c_uint64(0)
+        self._chk(self.lib.bng_sweep(self.h, now_ns, C.byref(n)), "sweep")
+        return n.value
+
+    @property
+    def lru_evictions(self) -> int:
+        return self.lib.bng_lru_evictions(self.h)
+
     @property
     def stream(self) -> int:
         return self.lib.bng_stream(self.h) or 0
@@ -290,6 +321,25 @@ class Dataplane:
         n = C.c_uint32()
         self._chk(self.lib.bng_stats_device_ptr(self.h, C.byref(p), C.byref(n)), "stats_device_ptr")
         return p.value, n.value
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128-byte NCCL unique id (rank 0 makes it, the host plumbing distributes it)."""
+        buf = C.create_string_buffer(128)
+        r = load_library().bng_comm_unique_id(buf, 128)
+        if r < 0:
+            raise BngError(-r, "bng_comm_unique_id")
+        return buf.raw
+
+    def comm_init(self, uid: bytes, rank: int, world: int):
+        buf = C.create_string_buffer(uid, 128)
+        self._chk(self.lib.bng_comm_init(self.h, buf, rank, world), "comm_init")
+
+    def sync_reduce(self) -> np.ndarray:
+        """Flush staged upserts and all-reduce the packed counter vector over the communicator; u64[40] totals."""
+        out = np.zeros(40, dtype=np.uint64)
+        self._chk(self.lib.bng_sync_reduce(self.h, out.ctypes.data), "sync_reduce")
+        return out
 
     def prof_enable(self, on: bool = True):
         self._chk(self.lib.bng_prof_enable(self.h, 1 if on else 0), "prof_enable")

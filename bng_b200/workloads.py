@@ -94,7 +94,7 @@ def _nat_maps(subs_global: int, subs: np.ndarray, flags=0x0F):
     keys, v, pubs = S.nat_blocks(subs_global)
     return [("subscriber_nat", keys[subs], v[subs]),
             ("nat_config_map", np.zeros(1, "<u4"), S.nat_config(flags)),
-            ("hairpin_ips", S.ip_bytes(pubs), np.ones(len(pubs), np.uint8)),
+            ("hairpin_ips", S.ip_bytes(pubs[:1000]), np.ones(len(pubs[:1000]), np.uint8)),  # the map holds 1000 (bpf/nat44.c:41)
             ("alg_ports", np.array([(21 << 16) | 6], "<u4"), np.array([(21, 6, 1, 0)], L.alg_config))]
 
 
@@ -259,6 +259,29 @@ BUILDERS = {
     "qos_egress_64": lambda n, r, wd: qos(n, r, wd, egress=True),
     "dhcp": dhcp,
 }
+
+
+def build(name: str, n: int, rank: int = 0, world: int = 1, subs_scale: int = 1) -> "Workload":
+    """BUILDERS[name] with the subscriber population multiplied by subs_scale: subs_scale = world keeps the
+    per-GPU population constant as GPUs are added (10 k subscribers PER GPU) instead of splitting BASELINE's 10 k
+    over them — per-GPU tables then stay the same size, so a 1 -> 8 curve is not flattered by tables that shrink
+    into L2."""
+    if subs_scale == 1:
+        return BUILDERS[name](n, rank, world)
+    k = subs_scale
+    if name in ("pipeline_imix", "pipeline_64"):
+        return pipeline(n, rank, world, n_subs=10_000 * k, flows_per_sub=_FPS, imix=name == "pipeline_imix")
+    if name == "antispoof_64":
+        return antispoof(n, rank, world, n_subs=10_000 * k)
+    if name in ("nat_steady_64", "nat_cold_64"):
+        return nat(n, rank, world, n_subs=16_384 * k, cold=name == "nat_cold_64")
+    if name == "nat_ingress_64":
+        return nat_ingress(n, rank, world, n_subs=16_384 * k)
+    if name in ("qos_64", "qos_egress_64"):
+        return qos(n, rank, world, n_subs=10_000 * k, egress=name == "qos_egress_64")
+    if name == "dhcp":
+        return dhcp(n, rank, world, n_subs=(1 << 20) * k)
+    raise KeyError(name)
 
 
 def sizing(wl: "Workload") -> dict:

@@ -18,7 +18,12 @@
  *     -EINVAL bad argument, -ENOMEM, -EIO CUDA failure; bng_last_error() has text)
  *   - key/value buffers are borrowed for the duration of the call only
  *   - all entry points are thread-safe (one mutex per context); program runs
- *     on one context are serialised on that context's CUDA stream
+ *     on one context are serialised on that context's CUDA stream.  Nothing in
+ *     the library is process-wide: one process may hold contexts on several GPUs
+ *   - reserved keys: a hash-map key whose first 8 bytes (zero-extended when the
+ *     key is shorter) are 0xFFFFFFFFFFFFFFFD..FF cannot be stored (update:
+ *     -EINVAL, lookup/delete: -ENOENT); no frame produces such a key except a
+ *     nat_reverse lookup for 255.255.255.253-255 -> 255.255.255.255, which misses
  *   - PERCPU_ARRAY statistics maps read back as aggregated totals
  *   - there is NO CPU fallback: without a CUDA device bng_open() fails
  */
@@ -32,7 +37,7 @@
 extern "C" {
 #endif
 
-#define BNG_ABI_VERSION 1
+#define BNG_ABI_VERSION 2
 
 /* bpf(2) BPF_MAP_UPDATE_ELEM flags (include/uapi/linux/bpf.h) */
 #define BNG_ANY 0u
@@ -105,6 +110,14 @@ int bng_map_update(bng_ctx *ctx, int map, const void *key, const void *value, ui
 int bng_map_update_batch(bng_ctx *ctx, int map, const void *keys, const void *values, uint64_t n, uint64_t flags);
 int bng_map_lookup(bng_ctx *ctx, int map, const void *key, void *value_out);
 int bng_map_delete(bng_ctx *ctx, int map, const void *key);
+/* Staged upsert (BPF_ANY): queued on the host and applied with all other staged updates at the next batch
+ * boundary (bng_prog_run), at bng_sync(), or before the next call that reads or changes the same map —
+ * so it is always visible to a later lookup.  The last staged value of a key wins, as with one Put after
+ * the other.  This is what the per-lease / per-session Map.Put calls of the Go managers should bind to
+ * (pkg/dhcp/server.go:708,780,798; pkg/nat/manager.go:563-640): a synchronous bng_map_update costs two PCIe
+ * copies and a kernel launch per call.  Returns 0, or -EINVAL. */
+int bng_map_update_staged(bng_ctx *ctx, int map, const void *key, const void *value);
+int bng_staged_info(bng_ctx *ctx, uint64_t *pending, uint64_t *flushes, uint64_t *errors);
 int bng_map_clear(bng_ctx *ctx, int map); /* drop every entry of a hash map (= close + re-create the eBPF map) */
 /* copies up to cap (key,value) pairs out; returns the number written or a negative errno */
 int64_t bng_map_dump(bng_ctx *ctx, int map, void *keys_out, void *values_out, uint64_t cap);
@@ -113,8 +126,19 @@ int64_t bng_map_dump(bng_ctx *ctx, int map, void *keys_out, void *values_out, ui
  *      a batch run is the analogue of BPF_PROG_TEST_RUN over n frames) ---- */
 int bng_prog_id(bng_ctx *ctx, const char *name);
 int bng_prog_run(bng_ctx *ctx, int prog, bng_batch *batch);
-int bng_sync(bng_ctx *ctx);     /* wait for everything queued on the context's stream */
+int bng_sync(bng_ctx *ctx);     /* apply staged upserts, wait for everything queued on the context's stream */
 void *bng_stream(bng_ctx *ctx); /* the context's cudaStream_t */
+
+/* ---- session expiry (the reference declares the timeouts, bpf/nat44.c:50-53, and enforces
+ *      them nowhere: pkg/nat/manager.go:667-679 is a logger) ----
+ * One streaming pass over nat_sessions: a session idle longer than its timeout at now_ns (ICMP 60 s, UDP 120 s,
+ * TCP established 7200 s, other TCP states 240 s) is removed with its nat_reverse entry (when that still points
+ * at it) and one reference of its EIM mapping (the mapping goes with its last session); the subscriber's
+ * sessions_active is decremented, nat_stats.sessions_expired counted, a NAT_LOG_SESSION_DELETE record logged
+ * (records of one sweep drain ordered by their bytes).  *expired_out = sessions removed.
+ * The three NAT flow maps are BPF_MAP_TYPE_LRU_HASH in the reference: an insert into a full one evicts the least
+ * recently used entry among the 16 slots next to the new key's home slot instead of failing. */
+int bng_sweep(bng_ctx *ctx, uint64_t now_ns, uint64_t *expired_out);
 
 /* ---- events (spoof_events perf buffer, nat_log_rb ring buffer) ----
  * Records come out in the order the reference would have emitted them (batch
@@ -132,15 +156,28 @@ uint32_t bng_event_size(bng_ctx *ctx, int map);
 #define BNG_NUM_STATS 40
 uint32_t bng_shard_of_mac(uint64_t mac_key, uint32_t world);
 int bng_stats_device_ptr(bng_ctx *ctx, void **dptr, uint32_t *n_u64);
+/* Counter reconciliation over NCCL ("ncclAllReduce(SUM, uint64) on the packed counter vector at
+ * bng_sync").  One context per GPU, one communicator over all of them: rank 0 calls bng_comm_unique_id(), the
+ * host plumbing hands the 128 bytes to every rank, every rank calls bng_comm_init() (collective).
+ * bng_sync_reduce() then flushes staged upserts and all-reduces the BNG_NUM_STATS counters on the context's
+ * stream — per-shard counters stay what they are; the totals land in totals_out (host, may be NULL).  Without a
+ * communicator it returns this context's own counters.  libnccl.so.2 is resolved at run time from the host
+ * process (BNG_NCCL_LIB overrides the name): the library does not link it.  -ENOSYS when it cannot be found. */
+int bng_comm_unique_id(void *id_out, uint64_t cap /* >= 128 */);
+int bng_comm_init(bng_ctx *ctx, const void *id, uint32_t rank, uint32_t world);
+int bng_sync_reduce(bng_ctx *ctx, uint64_t *totals_out /* [BNG_NUM_STATS] */);
 
 /* ---- diagnostics ---- */
 uint64_t bng_launch_count(bng_ctx *ctx);  /* kernels launched by this context so far */
-uint64_t bng_lru_overflow(bng_ctx *ctx);  /* inserts refused because an LRU map was full (eviction not modelled) */
+uint64_t bng_lru_overflow(bng_ctx *ctx);  /* inserts that found no victim to evict in a full LRU map (should stay 0) */
+uint64_t bng_lru_evictions(bng_ctx *ctx); /* entries evicted from full LRU maps by the data path */
 uint64_t bng_events_lost(bng_ctx *ctx);   /* event records dropped because the staging buffer was full */
 /* per-kernel device timing (CUDA events around every launch); read returns "name launches total_ms\n" lines */
 int bng_prof_enable(bng_ctx *ctx, int on);
 int64_t bng_prof_read(bng_ctx *ctx, char *buf, uint64_t cap);
-void *bng_host_alloc(size_t bytes);       /* pinned host memory for BNG_MEM_HOST batches */
+/* Pinned, GPU-mapped host memory for BNG_MEM_HOST frame arenas: 2 MB transparent huge pages registered with
+ * CUDA where possible (far fewer IOMMU translations for the GPU's scattered header reads), else cudaHostAlloc. */
+void *bng_host_alloc(size_t bytes);
 void bng_host_free(void *p);
 
 #ifdef __cplusplus

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     missing = [f for f in declared_functions() if not hasattr(lib, f)]
     assert not missing, f"libbng_b200.so lacks {missing}"
     assert set(dataplane.EXPORTED_SYMBOLS) == set(declared_functions())
-    assert lib.bng_abi_version() == 1
+    assert lib.bng_abi_version() == 2
 
 
 def test_shard_function_matches_host_mirror():

@@ -16,6 +16,7 @@ from bng_b200 import workloads as W
 from bng_b200.layouts import as_bytes
 
 pytestmark = pytest.mark.gpu
+TABLES = ("nat_sessions", "qos_ingress", "qos_egress", "subscriber_nat", "eim_table", "nat_reverse")
 
 
 def _load(dp, wl):
@@ -56,7 +57,7 @@ def _oracle_run(wl, arena, off16, stride, steps):
     stats = {m: o.lookup(m, np.zeros(4, np.uint8)).view("<u8").copy()
              for m in ("antispoof_stats", "qos_stats_map", "nat_stats_map", "stats_map")}
     events = {m: o.drain(m) for m in ("spoof_events", "nat_log_rb")}
-    tables = {m: o.dump(m) for m in ("nat_sessions", "qos_ingress", "subscriber_nat", "eim_table", "nat_reverse")}
+    tables = {m: o.dump(m) for m in TABLES}
     return outs, stats, events, tables
 
 
@@ -93,7 +94,7 @@ def _gpu_run(wl, arena, off16, stride, steps, mode):
             outs.append((np.asarray(v), a, l))
         stats = {m: dp.stats(m) for m in ("antispoof_stats", "qos_stats_map", "nat_stats_map", "stats_map")}
         events = {m: dp.drain(m) for m in ("spoof_events", "nat_log_rb")}
-        tables = {m: dp.dump(m) for m in ("nat_sessions", "qos_ingress", "subscriber_nat", "eim_table", "nat_reverse")}
+        tables = {m: dp.dump(m) for m in TABLES}
         assert dp.lru_overflow == 0 and dp.events_lost == 0
         return outs, stats, events, tables
     finally:
@@ -125,10 +126,26 @@ def _same(a, b, what):
         assert np.array_equal(x, y), f"{what}: {m}: values differ"
 
 
-@pytest.mark.parametrize("name", ["pipeline_imix", "nat_cold_64", "antispoof_64", "qos_64"])
+@pytest.mark.parametrize("name", ["pipeline_imix", "pipeline_64", "nat_cold_64", "nat_steady_64", "nat_ingress_64", "antispoof_64",
+                                  "qos_64", "qos_egress_64"])
 def test_million_frames_against_reference(name):
+    """Every bench workload at BASELINE scale (10 k subscribers / 1 M flows of config #3, 2^20 frames) against the
+    reference oracle, bit for bit: verdicts, frame bytes, counters, event streams, table dumps."""
     n = 1 << 20
     wl = W.BUILDERS[name](n, 0, 1)
+    if wl.derive is not None:  # return traffic: derived from what the oracle's own prewarm translated
+        from oracle.pyoracle import Oracle, available
+        o = Oracle("reference" if available("reference") else "port")
+        for m, k, v in wl.maps:
+            assert o.update_batch(m, as_bytes(k), as_bytes(v)) == 0
+        tr = []
+        for prog, h, l in wl.prewarm:
+            pa = o.arena(h.shape[0] * 64 + 64)
+            pa[: h.shape[0] * 64] = h.reshape(-1)
+            o.run(prog, pa, l.copy(), wl.now0 - 1, stride=64)
+            tr.append(np.array(pa[: h.shape[0] * 64]))
+        wl.headers, wl.lens = wl.derive(tr)
+        o.free_arenas()
     arena, off16, stride = _arena(wl)
     steps = 1 if name == "nat_cold_64" else 3
     ref = _oracle_run(wl, arena, off16, stride, steps)
@@ -136,12 +153,14 @@ def test_million_frames_against_reference(name):
     _same(ref, gpu, f"{name}: reference oracle vs gpu (device-resident)")
 
 
-def test_dhcp_quarter_million_against_reference():
-    wl = W.dhcp(1 << 18, 0, 1, n_subs=1 << 16)
+@pytest.mark.parametrize("mode", ["device", "pinned"])
+def test_dhcp_config5_against_reference(mode):
+    """BASELINE config #5 at its full table size: 2^20 subscriber_pools entries, 99 % hits, 2^18 requests."""
+    wl = W.dhcp(1 << 18, 0, 1, n_subs=1 << 20)
     arena, off16, stride = _arena(wl)
     ref = _oracle_run(wl, arena, off16, stride, 1)
-    gpu = _gpu_run(wl, arena, off16, stride, 1, "pinned")
-    _same(ref, gpu, "dhcp: reference oracle vs gpu (pinned)")
+    gpu = _gpu_run(wl, arena, off16, stride, 1, mode)
+    _same(ref, gpu, f"dhcp (1 M subscriber_pools): reference oracle vs gpu ({mode})")
 
 
 def test_full_size_feed_paths_agree_and_conserve():
