@@ -918,8 +918,9 @@ static const char *const k_prog_names[] = {
     "nat44_hairpin_xdp",  // bpf/nat44.c:951-952
     "dhcp_fastpath_prog", // bpf/dhcp_fastpath.c:619-620
     "pipeline_up",        // antispoof_ingress -> nat44_egress -> qos_ingress_prog (pre-NAT key)
+    "pipeline_tc",        // antispoof_ingress -> qos_ingress_prog -> nat44_egress: the order of the reference's TC hooks
 };
-enum { P_ANTISPOOF, P_QOS_EG, P_QOS_IN, P_NAT_EG, P_NAT_IN, P_NAT_HAIRPIN, P_DHCP, P_PIPE_UP, P_COUNT };
+enum { P_ANTISPOOF, P_QOS_EG, P_QOS_IN, P_NAT_EG, P_NAT_IN, P_NAT_HAIRPIN, P_DHCP, P_PIPE_UP, P_PIPE_TC, P_COUNT };
 
 int bng_prog_id(bng_ctx *c, const char *name) {
     if (!c || !name) return -EINVAL;
@@ -939,6 +940,7 @@ static int dispatch(bng_ctx *c, int prog, const DevBatch &b) {
     case P_NAT_HAIRPIN: e = run_nat_hairpin_xdp(c->L, c->dev, b); break;
     case P_DHCP: e = run_dhcp_fastpath(c->L, c->dev, b); break;
     case P_PIPE_UP: e = run_pipeline_up(c->L, c->dev, b); break;
+    case P_PIPE_TC: e = run_pipeline_tc(c->L, c->dev, b); break;
     default: return -EINVAL;
     }
     if (e != cudaSuccess) return fail(c, -EIO, "launch %s: %s", k_prog_names[prog], cudaGetErrorString(e));
@@ -1299,6 +1301,100 @@ int bng_events_drain(bng_ctx *c, int map, void *buf, uint64_t cap_records, uint6
     if (n && buf) memcpy(buf, m->ev_pending.data(), n * m->ev_payload);
     if (n) m->ev_pending.erase(m->ev_pending.begin(), m->ev_pending.begin() + n * m->ev_payload);
     *n_out = n;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// snapshot / restore (device-table state for HA hand-over, reference pkg/ha)
+// A snapshot is a self-describing blob: header, then per map { name, kind, key size, value size, entry count,
+// keys, values } for every hash / array / LPM / statistics map (event rings are not state).  Restore clears
+// each map it finds in the blob and loads the entries through the ordinary update path, so derived state
+// (subscriber directory, the shared-memory image of the small maps) is rebuilt on the way and a snapshot
+// taken with one set of table capacities restores into another.
+// ---------------------------------------------------------------------------
+namespace {
+const char kSnapMagic[8] = {'B', 'N', 'G', 'S', 'N', 'A', 'P', '2'};
+struct SnapMapHdr {
+    char name[40];
+    u32 kind, key_size, value_size, pad;
+    u64 count;
+};
+} // namespace
+
+int64_t bng_snapshot(bng_ctx *c, void *buf, uint64_t cap) {
+    if (!c) return -EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    if (int fr = flush_staged_locked(c, -1)) return fr;
+    CU(c, cudaStreamSynchronize(c->L.stream));
+    std::vector<u8> out(kSnapMagic, kSnapMagic + 8);
+    u64 nmaps = 0;
+    size_t nmaps_at = out.size();
+    out.resize(out.size() + 8);
+    for (size_t mi = 0; mi < c->maps.size(); mi++) {
+        MapReg *m = &c->maps[mi];
+        if (m->kind == KIND_EVENT) continue;
+        u64 cnt = m->max_entries;
+        if (m->kind == KIND_HASH) {
+            u32 n32 = 0;
+            CU(c, cudaMemcpy(&n32, m->tbl->count, 4, cudaMemcpyDeviceToHost));
+            cnt = n32;
+        } else if (m->kind == KIND_LPM) {
+            cnt = m->lpm_host.size() / 3;
+        } else if (m->kind == KIND_STATS) {
+            cnt = 1;
+        }
+        std::vector<u8> keys((size_t)std::max<u64>(cnt, 1) * m->key_size), vals((size_t)std::max<u64>(cnt, 1) * m->value_size);
+        int64_t got = cnt ? map_dump_locked(c, m, keys.data(), vals.data(), cnt) : 0;
+        if (got < 0) return got;
+        SnapMapHdr h{};
+        snprintf(h.name, sizeof(h.name), "%s", m->name);
+        h.kind = (u32)m->kind, h.key_size = m->key_size, h.value_size = m->value_size, h.count = (u64)got;
+        out.insert(out.end(), (u8 *)&h, (u8 *)&h + sizeof(h));
+        out.insert(out.end(), keys.begin(), keys.begin() + (size_t)got * m->key_size);
+        out.insert(out.end(), vals.begin(), vals.begin() + (size_t)got * m->value_size);
+        nmaps++;
+    }
+    memcpy(&out[nmaps_at], &nmaps, 8);
+    if (buf && cap >= out.size()) memcpy(buf, out.data(), out.size());
+    return (int64_t)out.size(); // the size needed; nothing was copied when cap is smaller
+}
+
+int bng_restore(bng_ctx *c, const void *buf, uint64_t len) {
+    if (!c || !buf || len < 16 || memcmp(buf, kSnapMagic, 8)) return -EINVAL;
+    const u8 *p = (const u8 *)buf, *end = p + len;
+    u64 nmaps;
+    memcpy(&nmaps, p + 8, 8);
+    p += 16;
+    for (u64 k = 0; k < nmaps; k++) {
+        if (p + sizeof(SnapMapHdr) > end) return -EINVAL;
+        SnapMapHdr h;
+        memcpy(&h, p, sizeof(h));
+        p += sizeof(h);
+        h.name[sizeof(h.name) - 1] = 0;
+        const u64 kb = h.count * h.key_size, vb = h.count * h.value_size;
+        if (p + kb + vb > end) return -EINVAL;
+        int id = bng_map_id(c, h.name);
+        if (id >= 0) {
+            MapReg *m = get_map(c, id);
+            if (m->key_size != h.key_size || m->value_size != h.value_size) return fail(c, -EINVAL, "snapshot: %s has another layout", h.name);
+            if (m->kind == KIND_HASH) {
+                int r = bng_map_clear(c, id);
+                if (r) return r;
+            } else if (m->kind == KIND_LPM) {
+                std::lock_guard<std::mutex> g(c->mu);
+                cudaSetDevice(c->device);
+                m->lpm_host.clear();
+                int r = lpm_upload(c, m);
+                if (r) return r;
+            }
+            if (h.count) {
+                int r = bng_map_update_batch(c, id, p, p + kb, h.count, BNG_ANY);
+                if (r) return fail(c, r, "snapshot: loading %s failed", h.name);
+            }
+        }
+        p += kb + vb;
+    }
     return 0;
 }
 

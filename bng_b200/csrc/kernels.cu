@@ -32,6 +32,7 @@
 
 #define BLOCK 256
 #define MISS_FLAG 0x80000000u
+#define DEFER_FLAG 0x20000000u // pipeline_tc: nat44_egress runs in the ordered phase, after the token bucket passed the frame
 
 // device-side counters (Scratch::counters)
 enum { CNT_M = 0, CNT_NSEG = 1, CNT_DEFERRED = 2, CNT_MAXKEY = 3, CNT_WORK = 4 };
@@ -524,10 +525,12 @@ __global__ void __launch_bounds__(BLOCK) k_heads(const __grid_constant__ Grouped
 // The group key is the subscriber-directory slot (programs with a NAT stage) or the bucket's own slot.
 // ---------------------------------------------------------------------------
 #define DROP_FLAG 0x40000000u // staged value: nat44_egress dropped the frame (port exhaustion): no QoS stage
-#define IDX_MASK 0x3FFFFFFFu
+#define IDX_MASK 0x1FFFFFFFu
 #define RS_PER_THREAD 16
 
-template <bool NAT, bool QOS, bool EGRESS, int TEAM>
+// TC (pipeline_tc): the token bucket runs BEFORE the NAT stage: QoS walk first, then nat44_egress — hits and
+// new flows alike — for the frames it passed (DEFER_FLAG), with the parse-stage counters still to be counted.
+template <bool NAT, bool QOS, bool EGRESS, int TEAM, bool TC = false>
 __global__ void __launch_bounds__(TEAM, (TEAM == 128 ? 6 : 20)) k_resolve(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b,
                                                   const __grid_constant__ Grouped g, const u32 *seg, u32 *cnt) {
     constexpr int STAGE = TEAM * RS_PER_THREAD;
@@ -594,13 +597,26 @@ __global__ void __launch_bounds__(TEAM, (TEAM == 128 ? 6 : 20)) k_resolve(const 
             __syncthreads();
             const u32 n_here = s_cnt;
             const u32 nchunk = (n_here + 31) / 32;
-            // ---- new flows of this subscriber, strictly in index order ----
-            if (NAT && warp == 0 && sub) {
+            // ---- NAT stage of this subscriber's frames, strictly in index order: new flows (MISS_FLAG) and, in TC
+            //      order, every frame that waited for the token bucket (DEFER_FLAG) and was not dropped by it ----
+            auto nat_phase = [&]() {
+              if (warp == 0) {
                 for (u32 cb = 0; cb < nchunk; cb++) {
                     const u32 j = cb * 32 + lane;
                     const bool valid = j < n_here;
                     const u32 sv = valid ? s_sv[j] : 0;
-                    const bool is_miss = valid && (sv & MISS_FLAG);
+                    bool is_miss = valid && (sv & MISS_FLAG);
+                    bool fresh = false; // a deferred frame: the whole of nat44_egress is still to run
+                    if (TC && valid && (sv & DEFER_FLAG) && !(sv & DROP_FLAG)) {
+                        // :583-596 for a frame nobody has looked at yet: private source? allocation?
+                        const u8 *fp = frame_ptr(b, sv & IDX_MASK);
+                        if (is_private_ip(rd32(fp, 26))) {
+                            if (sub)
+                                is_miss = fresh = true;
+                            else
+                                bstats_add(bs, ST_NAT_PASSED, 1);
+                        }
+                    }
                     u32 mm = __ballot_sync(0xffffffffu, is_miss);
                     if (!mm) continue;
                     const u32 idx = sv & IDX_MASK, len = valid ? s_len[j] : 0;
@@ -623,14 +639,14 @@ __global__ void __launch_bounds__(TEAM, (TEAM == 128 ? 6 : 20)) k_resolve(const 
                     u32 todo = mm;
                     while (todo) {
                         // the longest prefix of the remaining new flows that does not interact: all at once
-                        const u32 took = nat_chunk_coop(c, bs, b, sub, is_miss && ((todo >> lane) & 1), idx, len, pend, lane);
+                        const u32 took = nat_chunk_coop(c, bs, b, sub, is_miss && ((todo >> lane) & 1), idx, len, pend, lane, fresh);
                         todo &= ~took;
                         if (lane == 0 && took) bstats_add(bs, ST_NAT_COOP, __popc(took));
                         if (!todo) break;
                         const u32 l = __ffs(todo) - 1; // ... then the frame that does, through the sequential code
                         todo &= todo - 1;
                         if (lane == l) {
-                            NatOut o = nat_egress_one<true>(c, bs, frame_ptr(b, idx), sub, len, frame_dlen(b, len), idx + b.base, b.now, &pend);
+                            NatOut o = nat_egress_one<true>(c, bs, frame_ptr(b, idx), sub, len, frame_dlen(b, len), idx + b.base, b.now, &pend, fresh);
                             if (o.verdict == TC_SHOT) {
                                 b.verdict[idx] = TC_SHOT;
                                 dropped = true;
@@ -643,7 +659,9 @@ __global__ void __launch_bounds__(TEAM, (TEAM == 128 ? 6 : 20)) k_resolve(const 
                         *(uint2 *)(pend.log_rec + r.rec_bytes - 8) = make_uint2(0xFFFFFFFFu, c.batch_seq);
                     if (dropped) s_sv[j] = sv | DROP_FLAG;
                 }
-            }
+              }
+            };
+            if (NAT && !TC && sub) nat_phase();
             if (NAT && QOS) __syncthreads();
             // ---- token bucket over the staged lengths ----
             if (QOS && slot) {
@@ -692,8 +710,13 @@ __global__ void __launch_bounds__(TEAM, (TEAM == 128 ? 6 : 20)) k_resolve(const 
                         dp++;
                         db += len;
                         b.verdict[idx] = TC_SHOT;
+                        if (TC) s_sv[j] = sv | DROP_FLAG; // never reaches the NAT stage
                     }
                 }
+            }
+            if (NAT && TC) { // the frames the bucket dropped are marked; everything else goes through nat44_egress now
+                __syncthreads();
+                nat_phase();
             }
             if (n_here < (u32)STAGE) break; // the group ended inside this sweep
             __syncthreads();                // ... else the staging buffers are reused
@@ -830,17 +853,17 @@ static cudaError_t group_by_key(Launcher &L, u32 n, u64 key_space, Grouped *out)
 
 // k_resolve walks one group per block and a batch of n frames can hold n groups: the grid is sized for n blocks,
 // capped at what the GPU holds at once (the blocks loop over the groups).
-template <bool NAT, bool QOS, bool EGRESS, int TEAM>
+template <bool NAT, bool QOS, bool EGRESS, int TEAM, bool TC = false>
 static void launch_resolve(Launcher &L, const DevCtx &c, const DevBatch &b, const Grouped &g, const char *name) {
-    int &per_sm = L.resolve_bps[(NAT ? 2 : 0) + (EGRESS ? 1 : 0)]; // resident blocks per SM of this instantiation
+    int &per_sm = L.resolve_bps[TC ? 4 : (NAT ? 2 : 0) + (QOS ? 0 : 1) + (EGRESS ? 1 : 0)]; // resident blocks per SM of this instantiation
     if (!per_sm) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resolve<NAT, QOS, EGRESS, TEAM>, TEAM, 0) != cudaSuccess || per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resolve<NAT, QOS, EGRESS, TEAM, TC>, TEAM, 0) != cudaSuccess || per_sm < 1)
             per_sm = 8;
     }
     long cap = (long)L.num_sms * per_sm, want = b.n ? b.n : 1;
     int grid = (int)(want < cap ? want : cap);
     prof_begin(L, name);
-    k_resolve<NAT, QOS, EGRESS, TEAM><<<grid, TEAM, 0, L.stream>>>(c, b, g, L.s.qslot, L.s.counters);
+    k_resolve<NAT, QOS, EGRESS, TEAM, TC><<<grid, TEAM, 0, L.stream>>>(c, b, g, L.s.qslot, L.s.counters);
     prof_end(L);
     L.launches++;
 }
@@ -888,5 +911,14 @@ cudaError_t run_pipeline_up(Launcher &L, const DevCtx &c, const DevBatch &b) {
     cudaError_t e = group_by_key(L, b.n, (u64)c.subdir.mask + 1, &g);
     if (e != cudaSuccess) return e;
     launch_resolve<true, true, false, 32>(L, c, b, g, "(k_resolve<true, true, false>)");
+    return cudaGetLastError();
+}
+
+cudaError_t run_pipeline_tc(Launcher &L, const DevCtx &c, const DevBatch &b) {
+    LAUNCH((k_pipe_classify<true, true, true>), b.n, CLASSIFY_BPS(true), c, b, L.s.key_a, L.s.val_a);
+    Grouped g;
+    cudaError_t e = group_by_key(L, b.n, (u64)c.subdir.mask + 1, &g);
+    if (e != cudaSuccess) return e;
+    launch_resolve<true, true, false, 32, true>(L, c, b, g, "(k_resolve<true, true, false, tc>)");
     return cudaGetLastError();
 }

@@ -27,7 +27,7 @@ struct Launcher {
     // per-context (= per-device) launch configuration, filled on first use: nothing here may be process-wide,
     // one process can hold contexts on several GPUs
     int dhcp_smem_set;  // cudaFuncAttributeMaxDynamicSharedMemorySize applied on this context's device
-    int resolve_bps[4]; // resident blocks per SM of the k_resolve instantiations
+    int resolve_bps[6]; // resident blocks per SM of the k_resolve instantiations
     int prof;
     ProfPending pend[32];
     int npend;
@@ -49,6 +49,7 @@ cudaError_t run_nat_egress(Launcher &L, const DevCtx &c, const DevBatch &b);
 cudaError_t run_nat_ingress(Launcher &L, const DevCtx &c, const DevBatch &b);
 cudaError_t run_nat_hairpin_xdp(Launcher &L, const DevCtx &c, const DevBatch &b);
 cudaError_t run_pipeline_up(Launcher &L, const DevCtx &c, const DevBatch &b);
+cudaError_t run_pipeline_tc(Launcher &L, const DevCtx &c, const DevBatch &b);
 cudaError_t run_dhcp_fastpath(Launcher &L, const DevCtx &c, const DevBatch &b);
 
 // header gather / scatter between a pinned host arena and a compact device copy (hostio.cu)

@@ -20,7 +20,12 @@
 
 // AS: run antispoof_ingress first; QOS: honour the qos_ingress bucket.  <false,false> is the
 // standalone nat44_egress classify.
-template <bool AS, bool QOS>
+// TC: the order the reference's own TC hooks give (pkg/antispoof/tc_linux.go:32-43, pkg/qos/tc_linux.go:44-55,
+// pkg/nat/tc_linux.go:37-66): antispoof -> qos_ingress -> nat44_egress.  A frame the token bucket drops never
+// reaches NAT, so whatever NAT would do to a frame with a rate-limited bucket — session counters, rewrite,
+// new flows, even the "no allocation" statistic — waits for the bucket's verdict: the frame goes to the ordered
+// phase with DEFER_FLAG and nat44_egress runs there, after token_bucket_check().
+template <bool AS, bool QOS, bool TC = false>
 __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
     k_pipe_classify(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b, u32 *skey, u32 *sval) {
     __shared__ SmallTabs st;
@@ -105,7 +110,8 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
         }
         __syncwarp();
         if (!QOS) qos_slot = DIR_NONE;
-        const bool priv = alive && is_private_ip(saddr); // only private sources are translated (:583-585)
+        const bool defer = TC && alive && qos_slot != DIR_NONE && !(qos_slot & DIR_QOS_UNLIMITED);
+        const bool priv = alive && !defer && is_private_ip(saddr); // only private sources are translated (:583-585)
         const bool has_sub = priv && nat_slot != DIR_NONE;
         if (priv && !has_sub) bstats_add(bs, ST_NAT_PASSED, 1); // no allocation: to userspace (:592-596)
         // L4 header in bounds and a translatable protocol (:608-653); fixed offsets need ihl = 5
@@ -187,6 +193,7 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
                 okey = dir_idx;
             }
             if (miss) oval |= MISS_FLAG;
+            if (defer) oval |= DEFER_FLAG;
         }
         if (act) {
             b.verdict[i] = (u8)v;

@@ -313,9 +313,9 @@ struct NatFlow {
     u8 is_hairpin;
     bool ok; // reaches the session lookup
 };
-template <bool COUNT>
+// count: bump the hairpin / ALG statistics and write the ALG log record (false when an earlier phase did it for this frame)
 __device__ __forceinline__ NatFlow nat_parse(const DevCtx &c, BlockStats &bs, const u8 *p, u32 dlen, u32 idx, u64 now,
-                                             const u8 *sub, u32 cfg_flags) {
+                                             const u8 *sub, u32 cfg_flags, const bool COUNT) {
     NatFlow f;
     f.ok = false;
     f.saddr = rd32(p, 26);
@@ -368,16 +368,17 @@ struct NatOut {
 //   RESOLVE=false (classify, frames with IPv4 options): everything up to the session lookup, the hit
 //     path, and the rewrite for hits.  A session miss is reported back.
 //   RESOLVE=true: full sequential semantics for one frame, executed by the
-//     subscriber's worker in frame-index order; counters that classify
-//     already bumped for this frame (hairpin) are not bumped again.
+//     subscriber's worker in frame-index order; `count_parse` says whether the
+//     parse-stage counters (hairpin, ALG) are still to be bumped (classify did
+//     it for frames it looked at; frames deferred past the QoS stage come fresh).
 template <bool RESOLVE>
 __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs, u8 *p, u8 *sub, u32 len, u32 dlen, u32 idx,
-                                                 u64 now, NatPend *pd = nullptr) {
+                                                 u64 now, NatPend *pd = nullptr, const bool count_parse = !RESOLVE) {
     NatOut o;
     o.verdict = TC_OK;
     o.miss = false;
     const u32 cfg_flags = *(const u32 *)c.nat_config;
-    const NatFlow f = nat_parse<!RESOLVE>(c, bs, p, dlen, idx, now, sub, cfg_flags);
+    const NatFlow f = nat_parse(c, bs, p, dlen, idx, now, sub, cfg_flags, count_parse);
     if (!f.ok) return o;
     const u32 saddr = f.saddr, daddr = f.daddr, proto = f.proto;
     const u16 sport = f.sport, dport = f.dport;
@@ -499,14 +500,14 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
 // Exhaustion never happens on the cooperative path: every proposed port is inside the block.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ u32 nat_chunk_coop(const DevCtx &c, BlockStats &bs, const DevBatch &b, u8 *sub, bool mine, u32 idx,
-                                              u32 len, NatPend &pend, u32 lane) {
+                                              u32 len, NatPend &pend, u32 lane, const bool count_parse = false) {
     const u32 cfg_flags = *(const u32 *)c.nat_config;
     if (cfg_flags & NATF_PARITY) return 0;
     const bool eim_on = (cfg_flags & NATF_EIM) != 0;
     u8 *p = mine ? frame_ptr(b, idx) : nullptr;
     NatFlow f;
     f.ok = false;
-    if (mine) f = nat_parse<false>(c, bs, p, frame_dlen(b, len), idx + b.base, b.now, sub, cfg_flags);
+    if (mine) f = nat_parse(c, bs, p, frame_dlen(b, len), idx + b.base, b.now, sub, cfg_flags, count_parse);
     const bool go = mine && f.ok; // (a frame classify flagged always parses; kept as a guard)
     u64 key[2] = {0, 0}, ek = 0;
     u8 *ses = nullptr, *m = nullptr;

@@ -22,7 +22,7 @@ ANY, NOEXIST, EXIST = 0, 1, 2
 
 PROGRAMS = (
     "antispoof_ingress", "qos_egress_prog", "qos_ingress_prog", "nat44_egress", "nat44_ingress",
-    "nat44_hairpin_xdp", "dhcp_fastpath_prog", "pipeline_up",
+    "nat44_hairpin_xdp", "dhcp_fastpath_prog", "pipeline_up", "pipeline_tc",
 )
 
 
@@ -80,6 +80,8 @@ def load_library() -> C.CDLL:
         "bng_comm_init": ([vp, vp, u32, u32], i32),
         "bng_sync_reduce": ([vp, vp], i32),
         "bng_sweep": ([vp, u64, C.POINTER(u64)], i32),
+        "bng_snapshot": ([vp, vp, u64], C.c_int64),
+        "bng_restore": ([vp, vp, u64], i32),
         "bng_lru_evictions": ([vp], u64),
         "bng_map_dump": ([vp, i32, vp, vp, u64], C.c_int64),
         "bng_map_clear": ([vp, i32], i32),
@@ -114,7 +116,7 @@ EXPORTED_SYMBOLS = (
     "bng_prog_run", "bng_sync", "bng_stream", "bng_events_drain", "bng_event_size", "bng_shard_of_mac",
     "bng_stats_device_ptr", "bng_launch_count", "bng_lru_overflow", "bng_events_lost", "bng_prof_enable",
     "bng_prof_read", "bng_host_alloc", "bng_host_free", "bng_map_update_staged", "bng_staged_info",
-    "bng_comm_unique_id", "bng_comm_init", "bng_sync_reduce", "bng_sweep", "bng_lru_evictions",
+    "bng_comm_unique_id", "bng_comm_init", "bng_sync_reduce", "bng_sweep", "bng_lru_evictions", "bng_snapshot", "bng_restore",
 )
 
 
@@ -300,6 +302,16 @@ class Dataplane:
 
     def sync(self):
         self._chk(self.lib.bng_sync(self.h), "sync")
+
+    def snapshot(self) -> bytes:
+        n = self._chk(self.lib.bng_snapshot(self.h, None, 0), "snapshot")
+        buf = C.create_string_buffer(n)
+        self._chk(self.lib.bng_snapshot(self.h, buf, n), "snapshot")
+        return buf.raw
+
+    def restore(self, blob: bytes):
+        buf = C.create_string_buffer(blob, len(blob))
+        self._chk(self.lib.bng_restore(self.h, buf, len(blob)), "restore")
 
     def sweep(self, now_ns: int) -> int:
         """Session expiry sweep at now_ns; returns the number of sessions removed."""

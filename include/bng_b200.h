@@ -167,6 +167,14 @@ int bng_comm_unique_id(void *id_out, uint64_t cap /* >= 128 */);
 int bng_comm_init(bng_ctx *ctx, const void *id, uint32_t rank, uint32_t world);
 int bng_sync_reduce(bng_ctx *ctx, uint64_t *totals_out /* [BNG_NUM_STATS] */);
 
+/* ---- snapshot / restore (table state for HA hand-over, reference pkg/ha) ----
+ * bng_snapshot() serialises every hash / array / LPM / statistics map into buf and returns the number of bytes
+ * the snapshot needs (call with cap 0 to size the buffer; nothing is written when cap is too small).
+ * bng_restore() replaces the contents of every map named in the blob; capacities may differ between the two
+ * contexts, layouts may not.  Event rings are not part of a snapshot. */
+int64_t bng_snapshot(bng_ctx *ctx, void *buf, uint64_t cap);
+int bng_restore(bng_ctx *ctx, const void *buf, uint64_t len);
+
 /* ---- diagnostics ---- */
 uint64_t bng_launch_count(bng_ctx *ctx);  /* kernels launched by this context so far */
 uint64_t bng_lru_overflow(bng_ctx *ctx);  /* inserts that found no victim to evict in a full LRU map (should stay 0) */

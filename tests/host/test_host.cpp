@@ -13,6 +13,7 @@
 #include "../../bng_b200/host/bng_dhcp_slow.hpp"
 #include "../../bng_b200/host/bng_host.hpp"
 #include "../../bng_b200/host/bng_nat_log.hpp"
+#include "../../bng_b200/host/bng_shard.hpp"
 
 using namespace bng;
 
@@ -622,6 +623,184 @@ static void test_nat_log_formats() {
     }
 }
 
+// ---- sharding: directory logic needs no device ----
+static uint32_t ipkey(uint8_t a, uint8_t b, uint8_t c, uint8_t d) { // the 4 address bytes as the maps hold them
+    uint8_t v[4] = {a, b, c, d};
+    uint32_t k;
+    memcpy(&k, v, 4);
+    return k;
+}
+
+static void test_shard_directory() {
+    shard::Directory dir(4, 1024, 1024);
+    for (uint32_t i = 0; i < 1000; i++) dir.Learn(0x020000000000ull + i, ipkey(100, 64, (uint8_t)(i >> 8), (uint8_t)i));
+    uint32_t per[4] = {0, 0, 0, 0};
+    for (uint32_t i = 0; i < 1000; i++) {
+        uint32_t s = dir.ShardOfMAC(0x020000000000ull + i);
+        CHECK(s < 4);
+        per[s]++;
+        CHECK_EQ(*dir.ShardOfIP(ipkey(100, 64, (uint8_t)(i >> 8), (uint8_t)i)), s); // the IP follows its MAC
+    }
+    for (int s = 0; s < 4; s++) CHECK(per[s] > 150);
+    CHECK(!dir.ShardOfIP(ipkey(10, 9, 9, 9)).has_value());
+    // port blocks by the AllocateNAT rule (pkg/nat/manager.go:433-434): subscriber k of a public IP owns
+    // [1024 + 1024 k, 1024 + 1024 (k + 1) - 1]
+    uint32_t pub = ipkey(203, 0, 113, 1);
+    for (uint32_t k = 0; k < 63; k++) dir.AddBlock(pub, (uint16_t)(1024 + 1024 * k), ipkey(100, 64, 0, (uint8_t)k));
+    for (uint32_t k = 0; k < 63; k++) {
+        uint32_t want = dir.ShardOfMAC(0x020000000000ull + k);
+        CHECK_EQ(*dir.ShardOfPublic(pub, (uint16_t)(1024 + 1024 * k)), want);
+        CHECK_EQ(*dir.ShardOfPublic(pub, (uint16_t)(1024 + 1024 * k + 1023)), want);
+    }
+    CHECK(!dir.ShardOfPublic(pub, 80).has_value());                // below the port range
+    CHECK(!dir.ShardOfPublic(ipkey(203, 0, 113, 2), 2000).has_value()); // unknown public address
+    dir.RemoveBlock(pub, 1024);
+    CHECK(!dir.ShardOfPublic(pub, 1500).has_value());
+    dir.Forget(0x020000000001ull);
+    CHECK(!dir.ShardOfIP(ipkey(100, 64, 0, 1)).has_value());
+    // routing classes of the reference's map names
+    CHECK(shard::RouteOf("subscriber_pools") == shard::Route::ByMAC);
+    CHECK(shard::RouteOf("qos_egress") == shard::Route::ByPrivateIP);
+    CHECK(shard::RouteOf("nat_reverse") == shard::Route::ByReverseKey);
+    CHECK(shard::RouteOf("ip_pools") == shard::Route::Replicated && shard::RouteOf("hairpin_ips") == shard::Route::Replicated);
+}
+
+static void put16be(uint8_t *p, uint16_t v) {
+    p[0] = (uint8_t)(v >> 8);
+    p[1] = (uint8_t)v;
+}
+// 64-byte Ethernet / IPv4 / UDP frame (checksums are updated incrementally by the programs: any start value does)
+static void udp_frame(uint8_t *f, uint64_t smac, uint64_t dmac, uint32_t sip, uint32_t dip, uint16_t sport, uint16_t dport) {
+    memset(f, 0, 64);
+    for (int i = 0; i < 6; i++) f[i] = (uint8_t)(dmac >> (8 * (5 - i))), f[6 + i] = (uint8_t)(smac >> (8 * (5 - i)));
+    f[12] = 0x08, f[14] = 0x45, f[22] = 64, f[23] = 17;
+    put16be(f + 16, 50);
+    memcpy(f + 26, &sip, 4);
+    memcpy(f + 30, &dip, 4);
+    put16be(f + 24, 0x1234);
+    put16be(f + 34, sport);
+    put16be(f + 36, dport);
+    put16be(f + 38, 30);
+    put16be(f + 40, 0x4321);
+}
+
+// Two shards (two contexts; on one device here): a flow's upstream frames land on its subscriber's shard by
+// source MAC, its replies on the same shard by (public address, port block), and only there are they translated.
+static void test_gpu_two_shards() {
+    const uint32_t world = 2, n_subs = 96;
+    std::vector<std::shared_ptr<Backend>> bes;
+    for (uint32_t r = 0; r < world; r++) {
+        bng_open_opts o;
+        memset(&o, 0, sizeof(o));
+        o.struct_size = sizeof(o);
+        o.device = -1;
+        o.max_subscribers = 1024, o.max_nat_sessions = 4096, o.max_eim_mappings = 4096, o.max_batch = 4096;
+        o.rank = r, o.world = world;
+        auto be = Backend::Open(&o);
+        CHECK(be->ctx != nullptr);
+        if (!be->ctx) return;
+        bes.push_back(be);
+    }
+    auto dir = std::make_shared<shard::Directory>(world, 1024, 1024);
+    shard::Router rt(bes, dir);
+    antispoof::Config ac{};
+    ac.DefaultMode = 1;
+    uint32_t zero = 0;
+    CHECK_EQ(rt.Update("antispoof_config", &zero, &ac), 0); // replicated
+    nat::NATConfig nc{};
+    nc.Flags = 0x0F;
+    nc.PortRangeStart = 1024, nc.PortRangeEnd = 65535, nc.DefaultPortsPerSub = 1024;
+    CHECK_EQ(rt.Update("nat_config_map", &zero, &nc), 0);
+    const uint32_t pub0 = ipkey(203, 0, 113, 0);
+    uint32_t owner_count[2] = {0, 0};
+    for (uint32_t i = 0; i < n_subs; i++) {
+        uint64_t mac = 0x020000000000ull + i;
+        uint32_t ip = ipkey(100, 64, 0, (uint8_t)i);
+        // nothing per-IP can be placed before the directory knows whose address it is
+        nat::SubscriberNAT sn{};
+        CHECK_EQ(rt.Update("subscriber_nat", &ip, &sn), -ENOENT);
+        dir->Learn(mac, ip);
+        antispoof::SubscriberBinding sb{};
+        sb.IPv4Addr = ip, sb.IPv4Valid = 1, sb.Mode = 1;
+        CHECK_EQ(rt.Update("subscriber_bindings", &mac, &sb, BNG_ANY, true), 0); // staged: applied at the batch boundary
+        uint32_t pub = pub0 + ((i / 63) << 24); // next public address after 63 blocks (last octet, wire order)
+        uint16_t ps = (uint16_t)(1024 + 1024 * (i % 63));
+        sn.Block.PublicIP = pub, sn.Block.PortStart = ps, sn.Block.PortEnd = (uint16_t)(ps + 1023), sn.Block.NextPort = ps;
+        sn.Block.SubscriberID = i + 1, sn.Block.BlockSizeLog2 = 10;
+        CHECK_EQ(rt.Update("subscriber_nat", &ip, &sn, BNG_ANY, true), 0);
+        dir->AddBlock(pub, ps, ip);
+        owner_count[dir->ShardOfMAC(mac)]++;
+    }
+    CHECK(owner_count[0] > 20 && owner_count[1] > 20);
+    // each entry lives on exactly one shard
+    for (uint32_t i = 0; i < n_subs; i++) {
+        uint32_t ip = ipkey(100, 64, 0, (uint8_t)i), own = dir->ShardOfMAC(0x020000000000ull + i);
+        nat::SubscriberNAT sn{};
+        for (uint32_t r = 0; r < world; r++) {
+            int rc = bng_map_lookup(bes[r]->ctx, bes[r]->Map("subscriber_nat"), &ip, &sn);
+            CHECK_EQ(rc, r == own ? 0 : -ENOENT);
+        }
+        CHECK_EQ(rt.Lookup("subscriber_nat", &ip, &sn), 0);
+    }
+    // ---- upstream: two frames per subscriber, steered by source MAC ----
+    const uint32_t n = 2 * n_subs;
+    std::vector<uint8_t> up(n * 64);
+    std::vector<std::vector<uint32_t>> mine(world);
+    for (uint32_t j = 0; j < n; j++) {
+        uint32_t i = j / 2;
+        udp_frame(&up[j * 64], 0x020000000000ull + i, 0x02fffffffffeull, ipkey(100, 64, 0, (uint8_t)i), ipkey(8, 8, 8, 8),
+                  (uint16_t)(4000 + (j & 1)), 53);
+        mine[dir->SteerUpstream(&up[j * 64], 64)].push_back(j);
+    }
+    int prog_up = bng_prog_id(bes[0]->ctx, "pipeline_up"), prog_in = bng_prog_id(bes[0]->ctx, "nat44_ingress");
+    std::vector<uint8_t> translated(n * 64);
+    for (uint32_t r = 0; r < world; r++) {
+        std::vector<uint8_t> a(mine[r].size() * 64), v(mine[r].size());
+        std::vector<uint32_t> len(mine[r].size(), 64);
+        for (size_t k = 0; k < mine[r].size(); k++) memcpy(&a[k * 64], &up[mine[r][k] * 64], 64);
+        bng_batch b{};
+        b.pkts = a.data(), b.len = len.data(), b.verdict = v.data(), b.n = (uint32_t)mine[r].size(), b.stride = 64;
+        b.now_ns = 1000000000ull, b.mem = BNG_MEM_HOST;
+        CHECK_EQ(bng_prog_run(bes[r]->ctx, prog_up, &b), 0);
+        for (size_t k = 0; k < mine[r].size(); k++) {
+            CHECK_EQ(v[k], 0);
+            memcpy(&translated[mine[r][k] * 64], &a[k * 64], 64);
+        }
+    }
+    uint64_t tot[BNG_NUM_STATS];
+    CHECK_EQ(rt.Totals(tot), 0);
+    CHECK_EQ(tot[0], (uint64_t)n);  // antispoof allowed: every frame found its binding on its shard
+    CHECK_EQ(tot[10], (uint64_t)n); // packets_snat
+    CHECK_EQ(tot[15], (uint64_t)n); // sessions_created: one per (subscriber, port)
+    // ---- downstream: the replies go to the owner by (public address, port block) ----
+    for (uint32_t j = 0; j < n; j++) {
+        const uint8_t *t = &translated[j * 64];
+        uint32_t nat_ip, i = j / 2, own = dir->ShardOfMAC(0x020000000000ull + i);
+        memcpy(&nat_ip, t + 26, 4);
+        CHECK(nat_ip != ipkey(100, 64, 0, (uint8_t)i)); // it was translated
+        uint8_t reply[64];
+        udp_frame(reply, 0x02fffffffffeull, 0x020000000000ull + i, ipkey(8, 8, 8, 8), nat_ip, 53, (uint16_t)((t[34] << 8) | t[35]));
+        CHECK_EQ(dir->SteerDownstream(reply, 64, 99), own);
+        for (uint32_t r = 0; r < world; r++) { // translated on the owner, untouched anywhere else
+            uint8_t fr[64], vd = 9;
+            uint32_t l = 64, daddr;
+            memcpy(fr, reply, 64);
+            bng_batch b{};
+            b.pkts = fr, b.len = &l, b.verdict = &vd, b.n = 1, b.stride = 64, b.now_ns = 2000000000ull, b.mem = BNG_MEM_HOST;
+            CHECK_EQ(bng_prog_run(bes[r]->ctx, prog_in, &b), 0);
+            memcpy(&daddr, fr + 30, 4);
+            if (r == own) {
+                CHECK_EQ(daddr, ipkey(100, 64, 0, (uint8_t)i));
+                CHECK_EQ((uint32_t)((fr[36] << 8) | fr[37]), 4000u + (j & 1));
+            } else {
+                CHECK(!memcmp(fr, reply, 64));
+            }
+        }
+    }
+    CHECK_EQ(rt.Totals(tot), 0);
+    CHECK_EQ(tot[11], (uint64_t)n); // packets_dnat
+}
+
 int main(int argc, char **argv) {
     std::string mode = argc > 1 ? argv[1] : "cpu";
     test_conversions();
@@ -632,7 +811,9 @@ int main(int argc, char **argv) {
     test_nat_allocator();
     test_qos_bookkeeping();
     test_antispoof_bookkeeping();
+    test_shard_directory();
     if (mode == "gpu") test_gpu_roundtrips();
+    if (mode == "gpu") test_gpu_two_shards();
     printf("%s: %d checks, %d failed\n", mode.c_str(), g_checks, g_fail);
     return g_fail ? 1 : 0;
 }

@@ -500,9 +500,9 @@ def dhcp_script(seed=0xD4C) -> Script:
 # ---------------------------------------------------------------------------
 # pipeline_up
 # ---------------------------------------------------------------------------
-def pipeline_script(seed=0x919E, n_subs=30, n=3000, flags=0x0F) -> Script:
+def pipeline_script(seed=0x919E, n_subs=30, n=3000, flags=0x0F, prog="pipeline_up") -> Script:
     r = rng(seed)
-    sc = Script("pipeline")
+    sc = Script("pipeline" if prog == "pipeline_up" else prog)
     keys, v = S.bindings(n_subs)
     v["mode"] = np.where(np.arange(n_subs) % 9 == 8, 3, 1)
     sc.update("subscriber_bindings", keys, v)
@@ -522,10 +522,10 @@ def pipeline_script(seed=0x919E, n_subs=30, n=3000, flags=0x0F) -> Script:
         hdr[sub_unknown, 8] ^= 0x55  # unknown source MAC
         l2 = np.where(lens == 64, S.imix_lengths(n, seed + b), lens)
         arena, off16 = S.pack_arena(hdr, l2)
-        sc.run("pipeline_up", arena, l2, t, off16=off16)
+        sc.run(prog, arena, l2, t, off16=off16)
         t += 3_000_000
     hdr, lens = nat_frames(r, n_subs, n, pubs, n_flow_ports=8)
-    sc.run("pipeline_up", fixed(hdr), lens, t + 10**9, stride=64)
+    sc.run(prog, fixed(hdr), lens, t + 10**9, stride=64)
     return sc
 
 
@@ -632,6 +632,7 @@ def ipopts_script(seed=0x0B75, n_subs=12, n=1600) -> Script:
     arena2, off2 = S.pack_arena(f2, lens2)
     sc.run("pipeline_up", arena2, lens2, t + 10**7, off16=off2)
     sc.run("pipeline_up", arena2, lens2, t + 10**7 + 10**6, off16=off2)
+    sc.run("pipeline_tc", arena2, lens2, t + 10**7 + 2 * 10**6, off16=off2)
     sc.run("antispoof_ingress", arena2, lens2, t + 2 * 10**7, off16=off2)
     sc.run("qos_ingress_prog", arena2, lens2, t + 3 * 10**7, off16=off2)
     sc.run("qos_egress_prog", arena2, lens2, t + 3 * 10**7, off16=off2, priority=np.zeros(n, np.uint32))
@@ -655,4 +656,7 @@ ALL_SCRIPTS = {
     "pipeline": pipeline_script,
     "pipeline_noeim": lambda: pipeline_script(seed=0x91A0, flags=0x06),
     "ipopts": ipopts_script,
+    # the order the reference's TC hooks give: antispoof -> qos_ingress -> nat44_egress (a frame the bucket drops never reaches NAT)
+    "pipeline_tc": lambda: pipeline_script(seed=0x91A7, prog="pipeline_tc"),
+    "pipeline_tc_noeim": lambda: pipeline_script(seed=0x91A9, flags=0x06, prog="pipeline_tc"),
 }

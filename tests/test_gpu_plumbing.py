@@ -132,3 +132,30 @@ def test_host_arena_alloc_free_cycles():
         assert int(view[-1]) == 7
         lib.bng_host_free(p)
     lib.bng_host_free(None)
+
+
+def test_snapshot_restores_into_a_context_of_another_size():
+    """bng_snapshot / bng_restore (HA hand-over): the state a pipeline scenario leaves behind is carried
+    into a fresh context with different table capacities; the second half of the traffic then behaves identically."""
+    import harness
+    import scenarios
+    sc = scenarios.pipeline_script()
+    runs = [i for i, st in enumerate(sc.steps) if st[0] == "run"]
+    cut = runs[2]  # state after two batches moves to the other context
+    first, second = harness.Script("a"), harness.Script("b")
+    first.steps, second.steps = sc.steps[:cut], sc.steps[cut:]
+    a = harness.GpuBackend()
+    try:
+        harness.run_script(a, first, tables=())
+        blob = a.dp.snapshot()
+        ra = harness.run_script(a, second)
+    finally:
+        a.close()
+    b = harness.GpuBackend(max_subscribers=1 << 12, max_nat_sessions=1 << 15, max_eim_mappings=1 << 13)
+    try:
+        b.dp.restore(blob)
+        rb = harness.run_script(b, second)
+    finally:
+        b.close()
+    harness.compare(ra, rb, "after the snapshot: original context vs restored context")
+    assert len(blob) > 10_000 and len(ra["tk_nat_sessions"]) > 100

@@ -20,7 +20,7 @@ def _stale(binary, deps):
 
 
 def build_host_test():
-    hdrs = [os.path.join(HOST, h) for h in ("bng_host.hpp", "bng_dhcp_slow.hpp", "bng_nat_log.hpp")] + \
+    hdrs = [os.path.join(HOST, h) for h in ("bng_host.hpp", "bng_dhcp_slow.hpp", "bng_nat_log.hpp", "bng_shard.hpp")] + \
         [os.path.join(ROOT, "include", "bng_b200.h")]
     lib = ["-L" + os.path.join(ROOT, "bng_b200"), "-lbng_b200"]
     if _stale(BIN, [SRC] + hdrs):

@@ -22,6 +22,7 @@ TARGETS = {  # program -> (scenario providing maps + seed frames, index of the r
     "nat44_ingress": "nat",
     "nat44_hairpin_xdp": "nat",
     "pipeline_up": "pipeline",
+    "pipeline_tc": "pipeline",
     "dhcp_fastpath_prog": "dhcp",
 }
 
