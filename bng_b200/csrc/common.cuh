@@ -138,8 +138,12 @@ __host__ __device__ __forceinline__ u32 ses_hi_of(u32 lo_off) { return lo_off ==
 #ifdef __CUDACC__
 // session->last_seen = now (bpf/nat44.c:677,881), once per flow and batch: `seen` is the epoch the caller
 // read with the probe, `epoch` the current batch's.
-__device__ __forceinline__ void ses_touch(u8 *ses, u64 now, u32 seen, u32 epoch) {
-    if (seen != epoch) {
+// With per-frame timestamps (stamped) the frames of a batch carry different values and the LAST frame's must
+// stay: the clock is monotonic, so that is the maximum.
+__device__ __forceinline__ void ses_touch(u8 *ses, u64 now, u32 seen, u32 epoch, bool stamped = false) {
+    if (stamped) {
+        atomicMax((unsigned long long *)(ses + SES_LAST_SEEN), (unsigned long long)now);
+    } else if (seen != epoch) {
         *(u64 *)(ses + SES_LAST_SEEN) = now;
         *(u16 *)(ses + SES_EPOCH) = (u16)epoch;
     }
@@ -261,6 +265,7 @@ struct DevBatch {
     // goes and can never reach into its neighbour.
     u32 cap;
     u64 arena_len; // bytes addressable from pkts (0 = unknown: no access may run past a frame's 16-byte chunks)
+    const u64 *nowv; // per-frame bpf_ktime_get_ns() (monotonic), or nullptr: `now` for every frame
 };
 // may the 64 bytes at p be read with 32-byte accesses?
 #define FRAME_WIDE_OK(b, p) ((((uintptr_t)(p)) & 31) == 0 && (u64)((p) - (b).pkts) + 64 <= (b).arena_len)
@@ -365,6 +370,48 @@ __device__ __forceinline__ bool tbl_evict_near(const Tbl &t, u32 home, u64 *stat
     atomicSub(t.count, 1u);
     if (stats) atomicAdd(&stats[ST_LRU_EVICT], 1ull);
     return true;
+}
+
+// tbl_find that also reports where an insert of k would go: *ins = index of the first tombstone on the probe path,
+// else of the EMPTY slot that ended it (0xFFFFFFFF: none seen).  A following tbl_claim_at() then costs one CAS
+// instead of a second walk.  SKIP_BUSY semantics (ordered phase: a key has one owner).
+template <int KW>
+__device__ __forceinline__ u8 *tbl_find_ins(const Tbl &t, const u64 *k, u32 *ins) {
+    *ins = 0xFFFFFFFFu;
+    if (k[0] >= K_BUSY) return nullptr;
+    u32 i = (u32)tbl_hash<KW>(k) & t.mask;
+    for (u32 probe = 0; probe <= t.mask; probe++) {
+        u8 *s = tbl_slot(t, i);
+        const u64 w0 = ld_vol64(s);
+        if (w0 == K_EMPTY) {
+            if (*ins == 0xFFFFFFFFu) *ins = i;
+            return nullptr;
+        }
+        if (w0 == K_TOMB && *ins == 0xFFFFFFFFu) *ins = i;
+        if (w0 == k[0]) {
+            bool eq = true;
+#pragma unroll
+            for (int j = 1; j < KW; j++) eq = eq && (((const u64 *)s)[j] == k[j]);
+            if (eq) return s;
+        }
+        i = (i + 1) & t.mask;
+    }
+    return nullptr;
+}
+// Claims slot `ins` (as reported by tbl_find_ins for a key that was absent) for k: EMPTY/TOMB -> BUSY with one
+// CAS, key words 1.. written; nullptr when somebody else took the slot meanwhile (the caller then walks again
+// with tbl_find_or_claim).  Live-entry accounting goes to *pending.
+template <int KW>
+__device__ __forceinline__ u8 *tbl_claim_at(const Tbl &t, u32 ins, const u64 *k, u32 *pending) {
+    if (ins == 0xFFFFFFFFu) return nullptr;
+    u8 *s = tbl_slot(t, ins);
+    const u64 w0 = ld_vol64(s);
+    if (w0 != K_EMPTY && w0 != K_TOMB) return nullptr;
+    if (atomicCAS((u64 *)s, w0, K_BUSY) != w0) return nullptr;
+#pragma unroll
+    for (int j = 1; j < KW; j++) ((u64 *)s)[j] = k[j];
+    ++*pending;
+    return s;
 }
 
 // Find-or-claim.  Returns the slot; *created says whether this call claimed
@@ -530,6 +577,7 @@ __device__ __forceinline__ u8 *ev_reserve(const DevCtx &c, const EvRing &r, u32 
 // are read the way the eBPF programs read them: little-endian loads of wire
 // bytes.  Even offsets are 2-byte aligned, so u16 accesses are always legal.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ u64 frame_now(const DevBatch &b, u32 i) { return b.nowv ? b.nowv[i] : b.now; }
 __device__ __forceinline__ u32 frame_dlen(const DevBatch &b, u32 len) { return (b.cap && len > b.cap) ? b.cap : len; }
 __device__ __forceinline__ u8 *frame_ptr(const DevBatch &b, u32 i) {
     return b.pkts + (b.off16 ? (size_t)b.off16[i] * 16 : (size_t)i * b.stride);
@@ -586,18 +634,46 @@ __device__ __forceinline__ void hdr_store_chunk(const Hdr64 &h, u8 *p, int c) {
 struct __align__(16) U256 {
     u32 w[8];
 };
+// L2 eviction priority of a 256-bit access (sm_100: LDG/STG.E.{EN,EF,EL}L2.256).  Frames stream through once:
+// evict-first keeps them from pushing the flow table's hot sectors (touched ~6 times per batch) out of the
+// 126 MB L2; the flow-table probe asks to stay (evict-last).
+enum { L2_NORMAL = 0, L2_FIRST = 1, L2_LAST = 2 };
+#ifndef FRAME_POLICY
+#define FRAME_POLICY L2_NORMAL
+#endif
+#ifndef SES_POLICY
+#define SES_POLICY L2_NORMAL
+#endif
+template <int POLICY = L2_NORMAL>
 __device__ __forceinline__ U256 ldg256(const void *p) {
     U256 r;
-    asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
-                 : "l"(p)
-                 : "memory");
+    if (POLICY == L2_FIRST)
+        asm volatile("ld.global.L2::evict_first.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+                     : "l"(p)
+                     : "memory");
+    else if (POLICY == L2_LAST)
+        asm volatile("ld.global.L2::evict_last.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+                     : "l"(p)
+                     : "memory");
+    else
+        asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+                     : "l"(p)
+                     : "memory");
     return r;
 }
+template <int POLICY = L2_NORMAL>
 __device__ __forceinline__ void stg256(void *p, const u32 *w) {
-    asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
-                 "r"(w[5]), "r"(w[6]), "r"(w[7])
-                 : "memory");
+    if (POLICY == L2_FIRST)
+        asm volatile("st.global.L2::evict_first.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                     "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                     : "memory");
+    else
+        asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
+                     "r"(w[5]), "r"(w[6]), "r"(w[7])
+                     : "memory");
 }
 // Frame header load: two 256-bit loads when the whole warp's frames allow it (32-byte aligned and 64
 // bytes inside the arena), 16-byte chunks otherwise.  `wide` must be warp-uniform.
@@ -606,8 +682,8 @@ __device__ __forceinline__ void hdr_load_wide(Hdr64 &h, const u8 *p, u32 len, bo
         U256 a, b;
 #pragma unroll
         for (int k = 0; k < 8; k++) a.w[k] = b.w[k] = 0;
-        if (len > 0) a = ldg256(p);
-        if (len > 32) b = ldg256(p + 32);
+        if (len > 0) a = ldg256<FRAME_POLICY>(p);
+        if (len > 32) b = ldg256<FRAME_POLICY>(p + 32);
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             h.w[k] = a.w[k];

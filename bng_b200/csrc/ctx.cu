@@ -61,6 +61,8 @@ struct bng_ctx {
     // staging for BNG_MEM_HOST batches
     u8 *hb_pkts = nullptr;
     u32 *hb_off = nullptr, *hb_len = nullptr, *hb_prio = nullptr;
+    u64 *hb_now = nullptr;
+    u64 *zc_now[2] = {nullptr, nullptr};
     u8 *hb_verdict = nullptr;
     size_t hb_arena = 0;
     u32 hb_n = 0;
@@ -456,12 +458,12 @@ int bng_close(bng_ctx *c) {
         for (void *p : c->allocs) cudaFree(p);
         Scratch &s = c->L.s;
         void *sp[] = {s.key_a, s.key_b, s.val_a, s.val_b, s.qslot, s.pflag, s.cub_tmp, s.counters,
-                      c->io_dev, c->hb_pkts, c->hb_off, c->hb_len, c->hb_prio, c->hb_verdict};
+                      c->io_dev, c->hb_pkts, c->hb_off, c->hb_len, c->hb_prio, c->hb_verdict, c->hb_now};
         for (void *p : sp)
             if (p) cudaFree(p);
         if (c->io_host) cudaFreeHost(c->io_host);
         for (int i = 0; i < 2; i++) {
-            void *zp[] = {c->zc_hdr[i], c->zc_verdict[i], c->zc_off[i], c->zc_len[i], c->zc_len0[i], c->zc_prio[i]};
+            void *zp[] = {c->zc_hdr[i], c->zc_verdict[i], c->zc_off[i], c->zc_len[i], c->zc_len0[i], c->zc_prio[i], c->zc_now[i]};
             for (void *p : zp)
                 if (p) cudaFree(p);
             if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
@@ -975,6 +977,7 @@ static int run_host_zero_copy(bng_ctx *c, int prog, bng_batch *bb, u8 *arena_dev
             CU(c, cudaMalloc((void **)&c->zc_len0[i], ZC_CHUNK * 4));
             CU(c, cudaMalloc((void **)&c->zc_prio[i], ZC_CHUNK * 4));
             CU(c, cudaMalloc((void **)&c->zc_verdict[i], ZC_CHUNK));
+            CU(c, cudaMalloc((void **)&c->zc_now[i], (size_t)ZC_CHUNK * 8));
         }
     }
     if (c->zc_hb < hb) {
@@ -997,6 +1000,8 @@ static int run_host_zero_copy(bng_ctx *c, int prog, bng_batch *bb, u8 *arena_dev
         CU(c, cudaMemcpyAsync(c->zc_len[buf], bb->len + base, (size_t)cn * 4, cudaMemcpyHostToDevice, c->s_in));
         if (bb->priority)
             CU(c, cudaMemcpyAsync(c->zc_prio[buf], bb->priority + base, (size_t)cn * 4, cudaMemcpyHostToDevice, c->s_in));
+        if (bb->now_ns_v)
+            CU(c, cudaMemcpyAsync(c->zc_now[buf], bb->now_ns_v + base, (size_t)cn * 8, cudaMemcpyHostToDevice, c->s_in));
         u8 *chunk_arena = bb->off16 ? arena_dev : arena_dev + (size_t)base * bb->stride;
         if (contiguous) {
             CU(c, cudaMemcpyAsync(c->zc_hdr[buf], (u8 *)bb->pkts + (size_t)base * hb, (size_t)cn * hb, cudaMemcpyHostToDevice,
@@ -1018,6 +1023,7 @@ static int run_host_zero_copy(bng_ctx *c, int prog, bng_batch *bb, u8 *arena_dev
         b.n = cn;
         b.stride = hb;
         b.now = bb->now_ns;
+        b.nowv = bb->now_ns_v ? c->zc_now[buf] : nullptr;
         b.base = base;
         b.cap = hb; // bounds checks never look past a compact slot (a no-op for whole frames: hostio.cu)
         b.arena_len = (u64)cn * hb;
@@ -1068,7 +1074,11 @@ int bng_prog_run(bng_ctx *c, int prog, bng_batch *bb) {
     // the caller's arena_bytes (16-byte units, possibly rounded up) says, and 0 means unknown
     b.arena_len = bb->off16 ? (bb->arena_bytes ? (u64)bb->arena_bytes * 16 - 15 : 0) : (u64)bb->n * bb->stride;
     b.cap = bb->off16 ? 0u : bb->stride; // a fixed-stride slot holds at most stride bytes of its frame
+    if (bb->mem == BNG_MEM_HOST && bb->now_ns_v) // the per-frame clock is monotonic (bpf_ktime_get_ns)
+        for (u32 i = 1; i < bb->n; i++)
+            if (bb->now_ns_v[i] < bb->now_ns_v[i - 1]) return fail(c, -EINVAL, "now_ns_v is not non-decreasing at frame %u", i);
     if (bb->mem == BNG_MEM_DEVICE) {
+        b.nowv = (const u64 *)bb->now_ns_v;
         b.pkts = (u8 *)bb->pkts;
         b.off16 = bb->off16;
         b.len = bb->len;
@@ -1099,7 +1109,7 @@ int bng_prog_run(bng_ctx *c, int prog, bng_batch *bb) {
         c->hb_arena = arena;
     }
     if (bb->n > c->hb_n) {
-        void **pp[] = {(void **)&c->hb_off, (void **)&c->hb_len, (void **)&c->hb_prio, (void **)&c->hb_verdict};
+        void **pp[] = {(void **)&c->hb_off, (void **)&c->hb_len, (void **)&c->hb_prio, (void **)&c->hb_verdict, (void **)&c->hb_now};
         for (void **p : pp) {
             if (*p) cudaFree(*p);
             *p = nullptr;
@@ -1109,12 +1119,15 @@ int bng_prog_run(bng_ctx *c, int prog, bng_batch *bb) {
         CU(c, cudaMalloc((void **)&c->hb_len, (size_t)bb->n * 4));
         CU(c, cudaMalloc((void **)&c->hb_prio, (size_t)bb->n * 4));
         CU(c, cudaMalloc((void **)&c->hb_verdict, (size_t)bb->n));
+        CU(c, cudaMalloc((void **)&c->hb_now, (size_t)bb->n * 8));
         c->hb_n = bb->n;
     }
     CU(c, cudaMemcpyAsync(c->hb_pkts, bb->pkts, arena, cudaMemcpyHostToDevice, st));
     if (bb->off16) CU(c, cudaMemcpyAsync(c->hb_off, bb->off16, (size_t)bb->n * 4, cudaMemcpyHostToDevice, st));
     CU(c, cudaMemcpyAsync(c->hb_len, bb->len, (size_t)bb->n * 4, cudaMemcpyHostToDevice, st));
     if (bb->priority) CU(c, cudaMemcpyAsync(c->hb_prio, bb->priority, (size_t)bb->n * 4, cudaMemcpyHostToDevice, st));
+    if (bb->now_ns_v) CU(c, cudaMemcpyAsync(c->hb_now, bb->now_ns_v, (size_t)bb->n * 8, cudaMemcpyHostToDevice, st));
+    b.nowv = bb->now_ns_v ? c->hb_now : nullptr;
     b.pkts = c->hb_pkts;
     b.off16 = bb->off16 ? c->hb_off : nullptr;
     b.len = c->hb_len;

@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(DH_TILE) k_dhcp_fastpath(const __grid_constant
             direct = l3 + (u32)(mine[l3] & 0x0f) * 4 + 8 + 240 + 64 > DH_SLOT;
         }
         const u32 l0 = len;
-        int v = dhcp_one(c, bs, direct ? g : mine, len, frame_dlen(b, l0), b.now);
+        int v = dhcp_one(c, bs, direct ? g : mine, len, frame_dlen(b, l0), frame_now(b, i));
         b.verdict[i] = (u8)v;
         if (len != l0) b.len[i] = len;
         // ---- stage out (every staged frame: a passed frame may have been rewritten, :769) ----

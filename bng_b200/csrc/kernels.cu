@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(BLOCK) k_antispoof(const __grid_constant__ Dev
             else if (w0 != K_EMPTY)
                 bv = bind_load(tbl_find<1, false>(c.bindings, &mk));
         }
-        if (act) b.verdict[i] = (u8)antispoof_eval(c, bs, h, len, i + b.base, b.now, bv, cfg, n_allowed);
+        if (act) b.verdict[i] = (u8)antispoof_eval(c, bs, h, len, i + b.base, frame_now(b, i), bv, cfg, n_allowed);
     }
     warp_stat_flush(bs, ST_AS_ALLOWED, n_allowed);
     bstats_flush(bs, c.stats);
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(BLOCK) k_nat_ingress(const __grid_constant__ D
         if (act) b.verdict[i] = TC_OK; // nat44_ingress never drops
         const bool ip4 = dlen >= 34 && h.b16(12) == ETH_P_IP_LE;
         if (ip4 && (h.b8(14) & 0x0f) != 5) { // options: fields are not at fixed offsets (rare)
-            nat_ingress_one(c, bs, p, len, dlen, b.now);
+            nat_ingress_one(c, bs, p, len, dlen, frame_now(b, i), b.nowv != nullptr);
             continue;
         }
         const u32 saddr = h.b32(26), daddr = h.b32(30), proto = h.b8(23);
@@ -185,8 +185,8 @@ __global__ void __launch_bounds__(BLOCK) k_nat_ingress(const __grid_constant__ D
         for (int k = 0; k < 8; k++) s1.w[k] = 0;
         if (have && ok[0] < K_BUSY) {
             u8 *s0 = tbl_slot(c.sessions, tbl_hash<2>(ok) & c.sessions.mask);
-            const U256 s = ldg256(s0);
-            s1 = ldg256(s0 + 32);
+            const U256 s = ldg256<SES_POLICY>(s0);
+            s1 = ldg256<SES_POLICY>(s0 + 32);
             const u64 w0 = (u64)s.w[0] | ((u64)s.w[1] << 32), w1 = (u64)s.w[2] | ((u64)s.w[3] << 32);
             seen = s.w[5] >> 16;
             if (w0 == ok[0] && w1 == ok[1]) {
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(BLOCK) k_nat_ingress(const __grid_constant__ D
                 n_passed++;
         }
         if (ses) {
-            ses_touch(ses, b.now, seen, c.epoch);
+            ses_touch(ses, frame_now(b, i), seen, c.epoch, b.nowv != nullptr);
             ses_count(ses, SES_IN_LO, len);
             if (proto == 6) { // :885-895; CLOSING(3) is absorbing, NEW(0) -> ESTABLISHED(1) on ack
                 const u32 tf = h.b8(47);
@@ -242,9 +242,9 @@ __global__ void __launch_bounds__(BLOCK) k_nat_ingress(const __grid_constant__ D
                 h.s16(36, csum_upd16(h.b16(36), dport, new_port));
             }
             if (wide) {
-                stg256(p, &h.w[0]);
+                stg256<FRAME_POLICY>(p, &h.w[0]);
                 if (proto == 6)
-                    stg256(p + 32, &h.w[8]);
+                    stg256<FRAME_POLICY>(p + 32, &h.w[8]);
                 else
                     hdr_store_chunk(h, p, 2);
             } else {
@@ -531,12 +531,14 @@ __global__ void __launch_bounds__(BLOCK) k_heads(const __grid_constant__ Grouped
 // TC (pipeline_tc): the token bucket runs BEFORE the NAT stage: QoS walk first, then nat44_egress — hits and
 // new flows alike — for the frames it passed (DEFER_FLAG), with the parse-stage counters still to be counted.
 template <bool NAT, bool QOS, bool EGRESS, int TEAM, bool TC = false>
-__global__ void __launch_bounds__(TEAM, (TEAM == 128 ? 6 : 20)) k_resolve(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b,
+#ifndef RESOLVE_MINB
+#define RESOLVE_MINB 20
+#endif
+__global__ void __launch_bounds__(TEAM, (TEAM == 128 ? 6 : RESOLVE_MINB)) k_resolve(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b,
                                                   const __grid_constant__ Grouped g, const u32 *seg, u32 *cnt) {
     constexpr int STAGE = TEAM * RS_PER_THREAD;
     __shared__ BlockStats bs;
     __shared__ u32 s_sv[STAGE], s_len[STAGE];
-    __shared__ u32 s_pass[STAGE / 32];
     __shared__ u32 s_cnt, s_next;
     bstats_init(bs);
     const u32 *skey, *sval;
@@ -544,7 +546,8 @@ __global__ void __launch_bounds__(TEAM, (TEAM == 128 ? 6 : 20)) k_resolve(const 
     const Tbl &qt = EGRESS ? c.qos_eg : c.qos_in;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 m = cnt[CNT_M], nseg = cnt[CNT_NSEG];
-    u64 pp = 0, pb = 0, dp = 0, db = 0; // per-thread partial QoS counters
+    u32 pp = 0, dp = 0; // per-thread partial QoS counters
+    u64 pb = 0, db = 0;
     NatPend pend;
     pend.ses = pend.rev = pend.eim = 0;
     pend.log_rec = nullptr;
@@ -646,7 +649,8 @@ __global__ void __launch_bounds__(TEAM, (TEAM == 128 ? 6 : 20)) k_resolve(const 
                         const u32 l = __ffs(todo) - 1; // ... then the frame that does, through the sequential code
                         todo &= todo - 1;
                         if (lane == l) {
-                            NatOut o = nat_egress_one<true>(c, bs, frame_ptr(b, idx), sub, len, frame_dlen(b, len), idx + b.base, b.now, &pend, fresh);
+                            NatOut o = nat_egress_one<true>(c, bs, frame_ptr(b, idx), sub, len, frame_dlen(b, len), idx + b.base, frame_now(b, idx), &pend, fresh,
+                                                                b.nowv != nullptr);
                             if (o.verdict == TC_SHOT) {
                                 b.verdict[idx] = TC_SHOT;
                                 dropped = true;
@@ -663,54 +667,60 @@ __global__ void __launch_bounds__(TEAM, (TEAM == 128 ? 6 : 20)) k_resolve(const 
             };
             if (NAT && !TC && sub) nat_phase();
             if (NAT && QOS) __syncthreads();
-            // ---- token bucket over the staged lengths ----
-            if (QOS && slot) {
-                if (warp == 0) {
-                    for (u32 cb = 0; cb < nchunk; cb++) {
-                        const u32 j = cb * 32 + lane;
-                        const bool elig = j < n_here && !(s_sv[j] & DROP_FLAG);
-                        const u32 len = elig ? s_len[j] : 0;
-                        u32 em = __ballot_sync(0xffffffffu, elig);
-                        bool pass = true;
-                        if (em && tb.rate_bps != 0) { // rate 0: unlimited, bucket untouched (bpf/qos_ratelimit.c:77-78)
-                            tb_refill(tb, b.now);
-                            const u32 tot = __reduce_add_sync(0xffffffffu, len);
-                            const u32 mn = __reduce_min_sync(0xffffffffu, elig ? len : 0xffffffffu);
-                            if (tb.tokens >= (u64)tot) { // the whole chunk fits
-                                tb.tokens -= tot;
-                            } else if (tb.tokens < (u64)mn) { // nothing in the chunk fits
-                                pass = false;
-                            } else { // mixed: frame by frame, uniform across the warp
-                                pass = false;
-                                while (em) {
-                                    const u32 l = __ffs(em) - 1;
-                                    em &= em - 1;
-                                    const u32 ll = __shfl_sync(0xffffffffu, len, l);
-                                    const bool ok = tb.tokens >= (u64)ll;
-                                    if (ok) tb.tokens -= ll;
-                                    if (lane == l) pass = ok;
-                                }
+            // ---- token bucket over the staged lengths; verdicts, priorities and statistics as the walk goes ----
+            if (QOS && slot && warp == 0) {
+                for (u32 cb = 0; cb < nchunk; cb++) {
+                    const u32 j = cb * 32 + lane;
+                    const u32 sv = j < n_here ? s_sv[j] : DROP_FLAG;
+                    const bool elig = !(sv & DROP_FLAG);
+                    const u32 len = elig ? s_len[j] : 0;
+                    u32 em = __ballot_sync(0xffffffffu, elig);
+                    if (!em) continue;
+                    bool pass = true;
+                    if (tb.rate_bps != 0 && b.nowv) {
+                        // a clock value per frame: token_bucket_check() frame by frame, refill included (:80-94)
+                        const u64 mynow = elig ? b.nowv[sv & IDX_MASK] : 0;
+                        pass = false;
+                        while (em) {
+                            const u32 l = __ffs(em) - 1;
+                            em &= em - 1;
+                            const u32 ll = __shfl_sync(0xffffffffu, len, l);
+                            const u64 tn = __shfl_sync(0xffffffffu, mynow, l);
+                            const bool ok = tb_step(tb, tn, ll);
+                            if (lane == l) pass = ok;
+                        }
+                    } else if (tb.rate_bps != 0) { // rate 0: unlimited, bucket untouched (bpf/qos_ratelimit.c:77-78)
+                        tb_refill(tb, b.now);
+                        const u32 tot = __reduce_add_sync(0xffffffffu, len);
+                        const u32 mn = __reduce_min_sync(0xffffffffu, elig ? len : 0xffffffffu);
+                        if (tb.tokens >= (u64)tot) { // the whole chunk fits
+                            tb.tokens -= tot;
+                        } else if (tb.tokens < (u64)mn) { // nothing in the chunk fits
+                            pass = false;
+                        } else { // mixed: frame by frame, uniform across the warp
+                            pass = false;
+                            while (em) {
+                                const u32 l = __ffs(em) - 1;
+                                em &= em - 1;
+                                const u32 ll = __shfl_sync(0xffffffffu, len, l);
+                                const bool ok = tb.tokens >= (u64)ll;
+                                if (ok) tb.tokens -= ll;
+                                if (lane == l) pass = ok;
                             }
                         }
-                        const u32 pm = __ballot_sync(0xffffffffu, pass);
-                        if (lane == 0) s_pass[cb] = pm;
                     }
-                }
-                __syncthreads();
-                // ---- verdicts, priorities, statistics ----
-                for (u32 j = tid; j < n_here; j += TEAM) {
-                    const u32 sv = s_sv[j];
-                    if (sv & DROP_FLAG) continue;
-                    const u32 idx = sv & IDX_MASK, len = s_len[j];
-                    if ((s_pass[j >> 5] >> (j & 31)) & 1) {
-                        pp++;
-                        pb += len;
-                        if (EGRESS && b.priority) b.priority[idx] = tb.prio;
-                    } else {
-                        dp++;
-                        db += len;
-                        b.verdict[idx] = TC_SHOT;
-                        if (TC) s_sv[j] = sv | DROP_FLAG; // never reaches the NAT stage
+                    if (elig) {
+                        const u32 idx = sv & IDX_MASK;
+                        if (pass) {
+                            pp++;
+                            pb += len;
+                            if (EGRESS && b.priority) b.priority[idx] = tb.prio;
+                        } else {
+                            dp++;
+                            db += len;
+                            b.verdict[idx] = TC_SHOT;
+                            if (TC) s_sv[j] = sv | DROP_FLAG; // never reaches the NAT stage
+                        }
                     }
                 }
             }
@@ -737,9 +747,9 @@ __global__ void __launch_bounds__(TEAM, (TEAM == 128 ? 6 : 20)) k_resolve(const 
         }
     }
     if (QOS) {
-        warp_stat_flush64(bs, ST_QOS_PASS_PKTS, pp);
+        warp_stat_flush(bs, ST_QOS_PASS_PKTS, pp);
         warp_stat_flush64(bs, ST_QOS_PASS_BYTES, pb);
-        warp_stat_flush64(bs, ST_QOS_DROP_PKTS, dp);
+        warp_stat_flush(bs, ST_QOS_DROP_PKTS, dp);
         warp_stat_flush64(bs, ST_QOS_DROP_BYTES, db);
     }
     bstats_flush(bs, c.stats);

@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
         const bool act = i < b.n;
         const u32 len = act ? b.len[i] : 0;      // skb->len: byte counters, token bucket
         const u32 dlen = frame_dlen(b, len);     // data_end - data: every bounds check
+        const u64 now = act ? frame_now(b, i) : 0; // bpf_ktime_get_ns() while this frame runs
         u8 *p = act ? frame_ptr(b, i) : b.pkts;
         const bool wide = __all_sync(0xffffffffu, !act || FRAME_WIDE_OK(b, p));
         Hdr64 h;
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
         if (AS && dlen >= 14) bv.s = ldg256(bslot0);
         if (ip4) {
             d0 = *(const ulonglong2 *)tbl_slot(c.subdir, di);
-            s0 = ldg256(sslot0);
+            s0 = ldg256<SES_POLICY>(sslot0);
         }
         const u64 kw0 = (u64)s0.w[0] | ((u64)s0.w[1] << 32), kw1 = (u64)s0.w[2] | ((u64)s0.w[3] << 32);
 
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
             __syncwarp();
             bv.has = bind != nullptr;
             if (bind && bind != bslot0) bv.s = ldg256(bind); // found on a later probe
-            v = antispoof_eval(c, bs, h, dlen, i + b.base, b.now, bv, as_cfg, n_allowed);
+            v = antispoof_eval(c, bs, h, dlen, i + b.base, now, bv, as_cfg, n_allowed);
             __syncwarp();
         }
         const bool alive = act && v != TC_SHOT && ip4;
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
             if (ax >= 0) { // ALG traffic goes to userspace untranslated (:615-642)
                 bstats_add(bs, ST_NAT_ALG, 1);
                 const u8 *sub = tbl_slot(c.sub_nat, nat_slot);
-                nat_log(c, i + b.base, b.now, 7, *(const u32 *)(sub + 32), saddr, 0, sport, 0, daddr, dport, (u8)proto, st.alg_type[ax]);
+                nat_log(c, i + b.base, now, 7, *(const u32 *)(sub + 32), saddr, 0, sport, 0, daddr, dport, (u8)proto, st.alg_type[ax]);
                 go = false;
             }
         }
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
             if (ses != sslot0) tr = *(const uint2 *)(ses + SES_NAT_IP); // found on a later probe
             const u32 nat_ip = tr.x;
             const u16 nat_port = (u16)tr.y;
-            ses_touch(ses, b.now, tr.y >> 16, epoch);
+            ses_touch(ses, now, tr.y >> 16, epoch, b.nowv != nullptr);
             ses_count(ses, SES_OUT_LO, len);
             h.s32(26, nat_ip);
             h.s16(24, csum_upd32(h.b16(24), saddr, nat_ip));
@@ -161,9 +162,9 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
                 h.s16(36, csum_upd16(h.b16(36), sport, nat_port));
             }
             if (wide) { // whole sectors: bytes 0-31 (the Ethernet header goes back unchanged), then 32-63 or 32-47
-                stg256(p, &h.w[0]);
+                stg256<FRAME_POLICY>(p, &h.w[0]);
                 if (proto == 6)
-                    stg256(p + 32, &h.w[8]);
+                    stg256<FRAME_POLICY>(p + 32, &h.w[8]);
                 else
                     hdr_store_chunk(h, p, 2);
             } else {
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
 
         // ---- IPv4 options: fields are not at fixed offsets, take the generic path (rare) ----
         if (has_sub && !ihl5) {
-            NatOut o = nat_egress_one<false>(c, bs, p, tbl_slot(c.sub_nat, nat_slot), len, dlen, i + b.base, b.now);
+            NatOut o = nat_egress_one<false>(c, bs, p, tbl_slot(c.sub_nat, nat_slot), len, dlen, i + b.base, now, nullptr, true, b.nowv != nullptr);
             v = o.verdict;
             miss = o.miss;
         }

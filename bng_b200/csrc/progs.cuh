@@ -373,7 +373,8 @@ struct NatOut {
 //     it for frames it looked at; frames deferred past the QoS stage come fresh).
 template <bool RESOLVE>
 __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs, u8 *p, u8 *sub, u32 len, u32 dlen, u32 idx,
-                                                 u64 now, NatPend *pd = nullptr, const bool count_parse = !RESOLVE) {
+                                                 u64 now, NatPend *pd = nullptr, const bool count_parse = !RESOLVE,
+                                                 const bool stamped = false) {
     NatOut o;
     o.verdict = TC_OK;
     o.miss = false;
@@ -392,7 +393,7 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
         const u32 tr = *(const volatile u32 *)(ses + SES_NAT_PORT);
         nat_ip = *(const u32 *)(ses + SES_NAT_IP);
         nat_port = (u16)tr;
-        ses_touch(ses, now, tr >> 16, c.epoch);
+        ses_touch(ses, now, tr >> 16, c.epoch, stamped);
         ses_count(ses, SES_OUT_LO, len);
     } else {
         if (!RESOLVE) {
@@ -505,18 +506,52 @@ __device__ __forceinline__ u32 nat_chunk_coop(const DevCtx &c, BlockStats &bs, c
     if (cfg_flags & NATF_PARITY) return 0;
     const bool eim_on = (cfg_flags & NATF_EIM) != 0;
     u8 *p = mine ? frame_ptr(b, idx) : nullptr;
+    const u64 now = mine ? frame_now(b, idx) : 0;
+    const bool stamped = b.nowv != nullptr;
+    const u32 dlen = frame_dlen(b, len);
+    // ---- parse.  The common frame (ihl = 5, classify has already vetted it: not ALG traffic, L4 header in bounds)
+    //      comes in with two 256-bit loads and is rewritten in registers, like classify does; anything else takes
+    //      the byte-wise parse of the sequential code ----
     NatFlow f;
     f.ok = false;
-    if (mine) f = nat_parse(c, bs, p, frame_dlen(b, len), idx + b.base, b.now, sub, cfg_flags, count_parse);
-    const bool go = mine && f.ok; // (a frame classify flagged always parses; kept as a guard)
+    Hdr64 h;
+    bool fast = false, wide = false;
+    if (mine && !count_parse) {
+        wide = FRAME_WIDE_OK(b, p);
+        if (wide) {
+            const U256 a0 = ldg256(p), a1 = ldg256(p + 32);
+#pragma unroll
+            for (int k = 0; k < 8; k++) h.w[k] = a0.w[k], h.w[8 + k] = a1.w[k];
+        } else {
+            hdr_load(h, p, dlen < 64 ? dlen : 64);
+        }
+        const u32 proto = h.b8(23);
+        fast = dlen >= 34 && h.b16(12) == ETH_P_IP_LE && (h.b8(14) & 0x0f) == 5 &&
+               (proto == 6 ? dlen >= 54u : ((proto == 17 || proto == 1) && dlen >= 42u));
+        if (fast) {
+            f.saddr = h.b32(26), f.daddr = h.b32(30), f.proto = proto, f.l4 = 34;
+            f.sport = proto == 1 ? h.b16(38) : h.b16(34);
+            f.dport = proto == 1 ? (u16)0 : h.b16(36);
+            f.is_hairpin = 0;
+            if (cfg_flags & NATF_HAIRPIN) {
+                u64 hk = f.daddr;
+                if (tbl_find<1, false>(c.hairpin, &hk)) f.is_hairpin = 1;
+            }
+            f.ok = true;
+        }
+    }
+    if (mine && !fast) f = nat_parse(c, bs, p, dlen, idx + b.base, now, sub, cfg_flags, count_parse);
+    const bool go = mine && f.ok;
+    // ---- probes: where the flow's entries are, or would go ----
     u64 key[2] = {0, 0}, ek = 0;
     u8 *ses = nullptr, *m = nullptr;
+    u32 ses_ins = 0xFFFFFFFFu, eim_ins = 0xFFFFFFFFu, rev_ins = 0xFFFFFFFFu;
     if (go) {
         key[0] = (u64)f.saddr | ((u64)f.daddr << 32);
         key[1] = (u64)f.sport | ((u64)f.dport << 16) | ((u64)f.proto << 32);
         ek = (u64)f.saddr | ((u64)f.sport << 32) | ((u64)f.proto << 48);
-        ses = tbl_find<2, true, true>(c.sessions, key);
-        if (!ses && eim_on) m = tbl_find<1, true, true>(c.eim, &ek);
+        ses = tbl_find_ins<2>(c.sessions, key, &ses_ins);
+        if (!ses && eim_on) m = tbl_find_ins<1>(c.eim, &ek, &eim_ins);
     }
     const bool create = go && !ses;          // needs a session
     const bool alloc = create && !m;         // ... and a port (EIM: a new mapping)
@@ -543,28 +578,33 @@ __device__ __forceinline__ u32 nat_chunk_coop(const DevCtx &c, BlockStats &bs, c
         if (next > 0xFFFFu) all_clash = true;
         port = next + __popc(amask & below);
         if (alloc && port > port_end) clash = true; // the counter wraps here: that frame goes through the sequential code
-        const u64 ck = (u64)f.saddr | ((u64)port << 32) | ((u64)f.proto << 48);
-        if (alloc && !all_clash && tbl_find<1, true, true>(c.eim, &ck)) clash = true; // candidate taken (:450-459)
-        if (eim_on) { // ... or about to be: an endpoint an earlier lane creates whose network-order port reads as my candidate
-            for (u32 j = 0; j < 32; j++) {
-                const u64 o = __shfl_sync(0xffffffffu, ek, j);
-                if (alloc && j < lane && ((amask >> j) & 1) && o == ck) clash = true;
-            }
-        }
     }
-    // translation of every creating lane, and its nat_reverse key: an earlier flow of the chunk must not own it
-    // (a port handed out twice after the counter wrapped; :740 is BPF_ANY, the later frame has to win)
+    // translation of every creating lane, and its nat_reverse key
     u32 nat_ip = 0;
     u16 nat_port = 0;
     u64 rk[2] = {0, 0};
+    u8 *rev = nullptr;
     if (create) {
         nat_ip = m ? *(const u32 *)(m + 8) : pub_ip;
         nat_port = m ? bswap16(*(const u16 *)(m + 12)) : bswap16((u16)port);
         rk[0] = (u64)f.daddr | ((u64)nat_ip << 32);
         rk[1] = (u64)f.dport | ((u64)nat_port << 16) | ((u64)f.proto << 32);
     }
+    // second round of probes, in flight together: is the proposed port taken (:450-459)?  does the reverse key exist
+    // already (:740 is BPF_ANY: then it is overwritten in place)?
+    const u64 ck = (u64)f.saddr | ((u64)port << 32) | ((u64)f.proto << 48);
+    if (alloc && !clash && !all_clash && tbl_find<1, true, true>(c.eim, &ck)) clash = true;
+    if (create && !clash && !all_clash) rev = tbl_find_ins<2>(c.reverse, rk, &rev_ins);
+    if (nalloc && eim_on) { // ... or about to be taken: an endpoint an earlier lane creates whose network-order port reads as my candidate
+        for (u32 j = 0; j < 32; j++) {
+            const u64 o = __shfl_sync(0xffffffffu, ek, j);
+            if (alloc && j < lane && ((amask >> j) & 1) && o == ck) clash = true;
+        }
+    }
     const u32 ncreate = __popc(cmask);
     if (ncreate) {
+        // an earlier flow of the chunk must not own the same nat_reverse key (a port handed out twice after the
+        // counter wrapped: the later frame has to win)
         const u32 r0 = __match_any_sync(0xffffffffu, create ? rk[0] : (u64)lane | (1ull << 63));
         const u32 r1 = __match_any_sync(0xffffffffu, create ? rk[1] : (u64)lane | (1ull << 63));
         if (create && (r0 & r1 & cmask & below)) clash = true;
@@ -594,21 +634,46 @@ __device__ __forceinline__ u32 nat_chunk_coop(const DevCtx &c, BlockStats &bs, c
             const u32 tr = *(const volatile u32 *)(ses + SES_NAT_PORT);
             nat_ip = *(const u32 *)(ses + SES_NAT_IP);
             nat_port = (u16)tr;
-            ses_touch(ses, b.now, tr >> 16, c.epoch);
+            ses_touch(ses, now, tr >> 16, c.epoch, stamped);
             ses_count(ses, SES_OUT_LO, len);
         } else {
-            if (m) { // existing endpoint mapping (:482-487)
-                *(u64 *)(m + 24) = b.now;
+            // the three claims first, so that their atomics are in flight together
+            bool created;
+            u8 *nm = nullptr, *ns, *rs = rev;
+            if (!m && eim_on) nm = tbl_claim_at<1>(c.eim, eim_ins, &ek, &pend.eim);
+            ns = tbl_claim_at<2>(c.sessions, ses_ins, key, &pend.ses);
+            bool rs_new = false;
+            if (!rs) {
+                rs = tbl_claim_at<2>(c.reverse, rev_ins, rk, &pend.rev);
+                rs_new = rs != nullptr;
+            }
+            // (a slot another subscriber's worker took in the meantime: walk again)
+            bool nm_new = nm != nullptr, ns_new = ns != nullptr;
+            if (!m && eim_on && !nm) {
+                nm = tbl_find_or_claim<1, true>(c.eim, &ek, &created, &pend.eim, c.stats);
+                nm_new = nm && created;
+            }
+            if (!ns) {
+                ns = tbl_find_or_claim<2, true>(c.sessions, key, &created, &pend.ses, c.stats);
+                ns_new = ns && created;
+            }
+            if (!rs) {
+                rs = tbl_find_or_claim<2, true>(c.reverse, rk, &created, &pend.rev, c.stats);
+                rs_new = rs && created;
+            }
+            if (m) { // existing endpoint mapping (:482-487); two lanes may share it: the later frame's clock stays
+                if (stamped)
+                    atomicMax((unsigned long long *)(m + 24), (unsigned long long)now);
+                else
+                    *(u64 *)(m + 24) = now;
                 atomicAdd((u32 *)(m + 32), 1u);
                 n_hit = 1;
             } else if (eim_on) { // new mapping (:495-517)
-                bool created;
-                u8 *nm = tbl_find_or_claim<1, true>(c.eim, &ek, &created, &pend.eim, c.stats);
-                if (nm && created) {
+                if (nm && nm_new) {
                     *(u32 *)(nm + 8) = pub_ip;
                     *(u32 *)(nm + 12) = port;
-                    *(u64 *)(nm + 16) = b.now;
-                    *(u64 *)(nm + 24) = b.now;
+                    *(u64 *)(nm + 16) = now;
+                    *(u64 *)(nm + 24) = now;
                     *(u32 *)(nm + 32) = 1;
                     *(u32 *)(nm + 36) = 0;
                     tbl_publish<false>(nm, ek);
@@ -617,27 +682,57 @@ __device__ __forceinline__ u32 nat_chunk_coop(const DevCtx &c, BlockStats &bs, c
                 }
                 n_miss = 1;
             }
-            bool created;
-            u8 *ns = tbl_find_or_claim<2, true>(c.sessions, key, &created, &pend.ses, c.stats);
             if (ns) {
-                nat_ses_fill(ns, nat_ip, nat_port, f.sport, f.saddr, f.daddr, f.dport, f.proto, f.is_hairpin, len, b.now, c.epoch);
-                if (created) tbl_publish<false>(ns, key[0]);
+                nat_ses_fill(ns, nat_ip, nat_port, f.sport, f.saddr, f.daddr, f.dport, f.proto, f.is_hairpin, len, now, c.epoch);
+                if (ns_new) tbl_publish<false>(ns, key[0]);
             } else {
                 bstats_add(bs, ST_LRU_OVERFLOW, 1);
             }
-            u8 *rs = tbl_find_or_claim<2, true>(c.reverse, rk, &created, &pend.rev, c.stats);
             if (rs) {
                 *(u64 *)(rs + 16) = key[0];
                 *(u64 *)(rs + 24) = key[1];
-                if (created) tbl_publish<false>(rs, rk[0]);
+                if (rs_new) tbl_publish<false>(rs, rk[0]);
             } else {
                 bstats_add(bs, ST_LRU_OVERFLOW, 1);
             }
             n_created = 1;
-            nat_log(c, idx + b.base, b.now, 1, sub_id, f.saddr, nat_ip, f.sport, nat_port, f.daddr, f.dport, (u8)f.proto, f.is_hairpin,
+            nat_log(c, idx + b.base, now, 1, sub_id, f.saddr, nat_ip, f.sport, nat_port, f.daddr, f.dport, (u8)f.proto, f.is_hairpin,
                     &pend);
         }
-        nat_snat_rewrite(p, f.l4, f.proto, f.saddr, nat_ip, nat_port);
+        if (fast) { // :752-798 on the header in registers, whole sectors back (as classify does for hits)
+            h.s32(26, nat_ip);
+            h.s16(24, csum_upd32(h.b16(24), f.saddr, nat_ip));
+            if (f.proto == 6) {
+                h.s16(34, nat_port);
+                u16 ck2 = csum_upd32(h.b16(50), f.saddr, nat_ip);
+                h.s16(50, csum_upd16(ck2, f.sport, nat_port));
+            } else if (f.proto == 17) {
+                h.s16(34, nat_port);
+                u16 ck2 = h.b16(40);
+                if (ck2 != 0) {
+                    ck2 = csum_upd32(ck2, f.saddr, nat_ip);
+                    ck2 = csum_upd16(ck2, f.sport, nat_port);
+                    if (ck2 == 0) ck2 = 0xffff;
+                    h.s16(40, ck2);
+                }
+            } else {
+                h.s16(38, nat_port);
+                h.s16(36, csum_upd16(h.b16(36), f.sport, nat_port));
+            }
+            if (wide) {
+                stg256(p, &h.w[0]);
+                if (f.proto == 6)
+                    stg256(p + 32, &h.w[8]);
+                else
+                    hdr_store_chunk(h, p, 2);
+            } else {
+                hdr_store_chunk(h, p, 1);
+                hdr_store_chunk(h, p, 2);
+                if (f.proto == 6) hdr_store_chunk(h, p, 3);
+            }
+        } else {
+            nat_snat_rewrite(p, f.l4, f.proto, f.saddr, nat_ip, nat_port);
+        }
         n_snat = 1;
     }
     const u32 t_created = __reduce_add_sync(0xffffffffu, n_created), t_hit = __reduce_add_sync(0xffffffffu, n_hit),
@@ -657,7 +752,7 @@ __device__ __forceinline__ u32 nat_chunk_coop(const DevCtx &c, BlockStats &bs, c
 
 // nat44_ingress, :805-948.  Every update is commutative (or made so with a
 // CAS on the state byte), so this is a classify-only program.
-__device__ __forceinline__ int nat_ingress_one(const DevCtx &c, BlockStats &bs, u8 *p, u32 len, u32 dlen, u64 now) {
+__device__ __forceinline__ int nat_ingress_one(const DevCtx &c, BlockStats &bs, u8 *p, u32 len, u32 dlen, u64 now, bool stamped = false) {
     if (dlen < 14) return TC_OK;
     if (rd16(p, 12) != ETH_P_IP_LE) return TC_OK;
     if (dlen < 34) return TC_OK;
@@ -703,7 +798,7 @@ __device__ __forceinline__ int nat_ingress_one(const DevCtx &c, BlockStats &bs, 
             bstats_add(bs, ST_NAT_PASSED, 1);
         return TC_OK;
     }
-    ses_touch(ses, now, *(const volatile u16 *)(ses + SES_EPOCH), c.epoch);
+    ses_touch(ses, now, *(const volatile u16 *)(ses + SES_EPOCH), c.epoch, stamped);
     ses_count(ses, SES_IN_LO, len);
     if (proto == 6) { // :885-895; CLOSING(3) is absorbing, NEW(0)->ESTABLISHED(1) on ack
         u32 tf = p[l4 + 13];

@@ -45,7 +45,7 @@ class Batch(C.Structure):
     _fields_ = [
         ("pkts", C.c_void_p), ("off16", C.c_void_p), ("len", C.c_void_p), ("verdict", C.c_void_p),
         ("priority", C.c_void_p), ("n", C.c_uint32), ("stride", C.c_uint32), ("now_ns", C.c_uint64),
-        ("mem", C.c_uint32), ("arena_bytes", C.c_uint32),
+        ("mem", C.c_uint32), ("arena_bytes", C.c_uint32), ("now_ns_v", C.c_void_p),
     ]
 
 
@@ -272,7 +272,7 @@ class Dataplane:
         return i
 
     def run(self, prog, pkts, lens, now_ns: int, off16=None, stride: int = 0, priority=None, verdict=None,
-            mem: int = MEM_HOST, arena_bytes: int | None = None):
+            mem: int = MEM_HOST, arena_bytes: int | None = None, now_v=None):
         """Run a program over a batch, in place.  Host arrays (numpy) with ``mem=MEM_HOST`` return
         synchronised; device buffers (torch tensors / raw pointers) with ``mem=MEM_DEVICE`` are queued on
         the context's stream (call :meth:`sync`).  Returns the verdict array/tensor."""
@@ -294,6 +294,7 @@ class Dataplane:
         b.stride = stride
         b.now_ns = now_ns
         b.mem = mem
+        b.now_ns_v = _ptr(now_v)
         if arena_bytes is None:
             arena_bytes = int(pkts.nbytes) if isinstance(pkts, np.ndarray) else int(pkts.numel() * pkts.element_size())
         b.arena_bytes = (arena_bytes + 15) // 16

@@ -193,7 +193,7 @@ def qos(n: int, rank=0, world=1, n_subs=10_000, seed=0xB2000006, egress=False) -
     return w
 
 
-def dhcp(n: int, rank=0, world=1, n_subs=1 << 20, seed=0xB2000005, frame_len=362) -> Workload:
+def dhcp(n: int, rank=0, world=1, n_subs=1_000_000, seed=0xB2000005, frame_len=362) -> Workload:
     """Config #5: 1 M subscriber_pools entries over 64 ip_pools (/18, both DNS set => 50 B of options),
     362 B requests (BOOTP 320 B), 80 % REQUEST / 20 % DISCOVER, option 53 first; 99 % known MAC (XDP_TX),
     1 % unknown (XDP_PASS)."""
@@ -280,7 +280,7 @@ def build(name: str, n: int, rank: int = 0, world: int = 1, subs_scale: int = 1)
     if name in ("qos_64", "qos_egress_64"):
         return qos(n, rank, world, n_subs=10_000 * k, egress=name == "qos_egress_64")
     if name == "dhcp":
-        return dhcp(n, rank, world, n_subs=(1 << 20) * k)
+        return dhcp(n, rank, world, n_subs=1_000_000 * k)
     raise KeyError(name)
 
 

@@ -82,7 +82,11 @@ typedef struct bng_map_info {
  * off16 is NULL; every frame's storage must be readable and writable up to the
  * next multiple of 16 bytes.  Frames are applied in index order: the result is
  * bit-identical to running the reference program on frame 0, then 1, ...
- * with bpf_ktime_get_ns() returning now_ns throughout the batch. */
+ * with bpf_ktime_get_ns() returning now_ns throughout the batch — or, when
+ * now_ns_v is given, now_ns_v[i] while frame i runs (the reference reads the
+ * clock per packet: bpf/nat44.c:669, bpf/qos_ratelimit.c:80).  Per-frame
+ * timestamps must be what that clock gives: monotonic, i.e. non-decreasing in
+ * index order and from batch to batch (-EINVAL when a host array is not). */
 typedef struct bng_batch {
     void *pkts;            /* arena base */
     const uint32_t *off16; /* [n] frame offsets in 16-byte units, or NULL */
@@ -94,6 +98,7 @@ typedef struct bng_batch {
     uint64_t now_ns;       /* bpf_ktime_get_ns() for this batch */
     uint32_t mem;          /* BNG_MEM_DEVICE or BNG_MEM_HOST */
     uint32_t arena_bytes;  /* size of the arena in 16-byte units (needed for BNG_MEM_HOST copies) */
+    const uint64_t *now_ns_v; /* [n] per-frame bpf_ktime_get_ns(), or NULL (same memory space as the other arrays) */
 } bng_batch;
 
 /* ---- lifecycle (replaces ebpf.LoadCollectionSpec/NewCollection/Collection.Close,

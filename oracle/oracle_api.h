@@ -60,6 +60,7 @@ typedef struct ora_batch {
     uint32_t n;
     uint32_t stride;
     uint64_t now_ns;
+    const uint64_t *now_v; /* optional: bpf_ktime_get_ns() per frame ([n]); NULL = now_ns for the whole batch */
 } ora_batch;
 
 const char *ora_impl(void); /* "reference" or "port" */

@@ -34,6 +34,7 @@ class _Batch(C.Structure):
         ("n", C.c_uint32),
         ("stride", C.c_uint32),
         ("now_ns", C.c_uint64),
+        ("now_v", C.c_void_p),
     ]
 
 
@@ -186,7 +187,7 @@ class Oracle:
         return out
 
     def run(self, prog: str, pkts: np.ndarray, lens: np.ndarray, now_ns: int, off16=None, stride: int = 0,
-            priority=None):
+            priority=None, now_v=None):
         """Run ``prog`` over the batch IN PLACE (pkts, lens and priority are modified).
 
         Returns the verdict array (uint8[n]).
@@ -216,6 +217,11 @@ class Oracle:
         b.n = n
         b.stride = stride
         b.now_ns = now_ns
+        if now_v is not None:
+            assert now_v.dtype == np.uint64 and now_v.flags.c_contiguous and now_v.shape[0] == n
+            b.now_v = now_v.ctypes.data
+        else:
+            b.now_v = None
         r = self.lib.ora_prog_run(pid, C.byref(b))
         if r:
             raise RuntimeError(f"ora_prog_run({prog}) = {r}")

@@ -563,6 +563,7 @@ int ora_prog_run(int prog, ora_batch *b) {
     ora_prog_fn fn = prog < g_nprogs ? g_progs[prog].fn : NULL;
     for (uint32_t i = 0; i < b->n; i++) {
         ora_pkt p;
+        if (b->now_v) g_now = b->now_v[i];
         p.data = b->pkts + (b->off16 ? (size_t)b->off16[i] * 16 : (size_t)i * b->stride);
         p.len = b->len[i];
         p.priority = b->priority ? b->priority[i] : 0;

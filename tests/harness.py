@@ -60,12 +60,14 @@ class Script:
         self.steps.append(("lookup", m, as_bytes(np.asarray(key)).reshape(-1).copy()))
         return self
 
-    def run(self, prog, arena, lens, now_ns, off16=None, stride=0, priority=None):
+    def run(self, prog, arena, lens, now_ns, off16=None, stride=0, priority=None, now_v=None):
+        """now_v: bpf_ktime_get_ns() per frame (u64[n], non-decreasing) instead of one value for the batch."""
         if off16 is None and stride == 0:
             stride = 64
         self.steps.append(("run", prog, arena.copy(), lens.astype(np.uint32).copy(), int(now_ns),
                            None if off16 is None else off16.astype(np.uint32).copy(), int(stride),
-                           None if priority is None else priority.astype(np.uint32).copy()))
+                           None if priority is None else priority.astype(np.uint32).copy(),
+                           None if now_v is None else np.ascontiguousarray(now_v, dtype=np.uint64).copy()))
         return self
 
     def drain(self):
@@ -101,10 +103,10 @@ class OracleBackend:
     def lookup(self, m, k):
         return self.o.lookup(m, k)
 
-    def run(self, prog, arena, lens, now, off16, stride, prio):
+    def run(self, prog, arena, lens, now, off16, stride, prio, now_v=None):
         oa = self.o.arena(len(arena) + 64)
         oa[:len(arena)] = arena
-        v = self.o.run(prog, oa, lens, now, off16=off16, stride=stride, priority=prio)
+        v = self.o.run(prog, oa, lens, now, off16=off16, stride=stride, priority=prio, now_v=now_v)
         arena[:] = oa[:len(arena)]
         self.o.free_arenas()
         return v
@@ -148,9 +150,9 @@ class GpuBackend:
     def lookup(self, m, k):
         return self.dp.lookup(m, k)
 
-    def run(self, prog, arena, lens, now, off16, stride, prio):
+    def run(self, prog, arena, lens, now, off16, stride, prio, now_v=None):
         if not getattr(self, "pinned", False):
-            return self.dp.run(prog, arena, lens, now, off16=off16, stride=stride, priority=prio)
+            return self.dp.run(prog, arena, lens, now, off16=off16, stride=stride, priority=prio, now_v=now_v)
         # pinned host buffers: exercises the zero-copy gather/scatter path of BNG_MEM_HOST
         import torch
         from bng_b200 import MEM_HOST
@@ -167,8 +169,9 @@ class GpuBackend:
                 to = None if off16 is None else torch.from_numpy(off16.view(np.int32).copy()).pin_memory()
                 tp = None if prio is None else torch.from_numpy(prio.view(np.int32).copy()).pin_memory()
                 tv = torch.zeros(len(lens), dtype=torch.uint8).pin_memory()
+                tn = None if now_v is None else torch.from_numpy(now_v.view(np.int64).copy()).pin_memory()
                 self.dp.run(prog, int(p), tl, now, off16=to, stride=stride, priority=tp, verdict=tv, mem=MEM_HOST,
-                            arena_bytes=arena.nbytes)
+                            arena_bytes=arena.nbytes, now_v=tn)
                 arena[:] = view
             finally:
                 lib.bng_host_free(p)
@@ -181,8 +184,9 @@ class GpuBackend:
         to = None if off16 is None else torch.from_numpy(off16.view(np.int32).copy()).pin_memory()
         tp = None if prio is None else torch.from_numpy(prio.view(np.int32).copy()).pin_memory()
         tv = torch.zeros(len(lens), dtype=torch.uint8).pin_memory()
+        tn = None if now_v is None else torch.from_numpy(now_v.view(np.int64).copy()).pin_memory()
         self.dp.run(prog, ta, tl, now, off16=to, stride=stride, priority=tp, verdict=tv, mem=MEM_HOST,
-                    arena_bytes=arena.nbytes)
+                    arena_bytes=arena.nbytes, now_v=tn)
         arena[:] = ta.numpy()
         lens[:] = tl.numpy().view(np.uint32)
         if prio is not None:
@@ -223,12 +227,12 @@ def run_script(be, script: Script, tables=TABLES) -> dict:
             if st[0] == "run_from":
                 d = st[2](res)
                 prog, arena, lens, now = st[1], d["arena"], d["lens"].astype(np.uint32), int(d["now_ns"])
-                off16, stride, prio = d.get("off16"), int(d.get("stride", 0)), d.get("priority")
+                off16, stride, prio, now_v = d.get("off16"), int(d.get("stride", 0)), d.get("priority"), d.get("now_v")
             else:
-                _, prog, arena, lens, now, off16, stride, prio = st
+                _, prog, arena, lens, now, off16, stride, prio, now_v = st
             a, l = arena.copy(), lens.copy()
             p = None if prio is None else prio.copy()
-            v = be.run(prog, a, l, now, off16, stride, p)
+            v = be.run(prog, a, l, now, off16, stride, p, now_v) if now_v is not None else be.run(prog, a, l, now, off16, stride, p)
             res[tag + "_verdict"] = np.asarray(v).copy()
             res[tag + "_frames"] = a
             res[tag + "_len"] = l

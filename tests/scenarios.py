@@ -640,6 +640,89 @@ def ipopts_script(seed=0x0B75, n_subs=12, n=1600) -> Script:
     return sc
 
 
+
+# ---------------------------------------------------------------------------
+# a clock value per frame (the reference calls bpf_ktime_get_ns() per packet: bpf/nat44.c:669, bpf/qos_ratelimit.c:80)
+# ---------------------------------------------------------------------------
+def ticks_script(seed=0x71C5, n_subs=24, n=3000) -> Script:
+    """Every program with per-frame timestamps: token buckets refill BETWEEN the frames of a batch (a frame that
+    found the bucket empty passes a few microseconds later), sessions / mappings / log records carry their own
+    frame's time, the lease check of the DHCP fast path too."""
+    r = rng(seed)
+    sc = Script("ticks")
+    keys, v = S.bindings(n_subs)
+    sc.update("subscriber_bindings", keys, v)
+    cfg = np.zeros(1, L.antispoof_config)
+    cfg["default_mode"], cfg["log_violations"] = 1, 1
+    sc.update1("antispoof_config", np.uint32(0), cfg)
+    pubs = nat_maps(sc, n_subs, 64, 0x0F)
+    qk, qv = S.qos_buckets(n_subs)
+    qv["burst_bytes"] = np.minimum(qv["burst_bytes"], 6000)  # small bursts: the refill between frames decides
+    qv["tokens"] = qv["burst_bytes"] // 2
+    qv["rate_bps"] = np.where(qv["rate_bps"] > 0, np.minimum(qv["rate_bps"], 1_000_000 * (1 + np.arange(n_subs) % 5)), 0)
+    sc.update("qos_ingress", qk, qv)
+    sc.update("qos_egress", qk, qv)
+    t = 20 * 10**9
+    first_nat = None
+    for b in range(3):
+        hdr, lens = nat_frames(r, n_subs, n, pubs, n_flow_ports=3 + 2 * b)
+        spoof = r.integers(0, 25, n) == 0
+        hdr[spoof, 27] ^= 0x08
+        l2 = np.where(lens == 64, S.imix_lengths(n, seed + b), lens)
+        arena, off16 = S.pack_arena(hdr, l2)
+        now_v = (t + np.cumsum(r.integers(0, 40_000, n))).astype(np.uint64)  # 0..40 us between frames, repeats included
+        prog = ("pipeline_up", "nat44_egress", "pipeline_tc")[b]
+        if prog == "nat44_egress":
+            first_nat = len(sc.steps)
+        sc.run(prog, arena, l2, int(now_v[0]), off16=off16, now_v=now_v)
+        sc.run("qos_ingress_prog", arena, l2, int(now_v[-1]), off16=off16, now_v=(now_v + np.uint64(10**6)))
+        sc.run("qos_egress_prog", arena, l2, int(now_v[-1]), off16=off16, now_v=(now_v + np.uint64(2 * 10**6)),
+               priority=np.zeros(n, np.uint32))
+        sc.run("antispoof_ingress", arena, l2, int(now_v[-1]), off16=off16, now_v=(now_v + np.uint64(3 * 10**6)))
+        t = int(now_v[-1]) + 5 * 10**6
+
+    def replies(res):
+        out_a = res[f"s{first_nat:03d}_frames"]
+        st = sc.steps[first_nat]
+        off16, lens = st[5], st[3]
+        fr = np.stack([out_a[int(o) * 16: int(o) * 16 + 64] for o in off16])
+        keep = (res[f"s{first_nat:03d}_verdict"] == 0) & (lens >= 64) & (fr[:, 12] == 0x08) & ((fr[:, 14] & 0x0F) == 5)
+        fr = fr[keep][:1200]
+        out = fr.copy()
+        out[:, 26:30], out[:, 30:34] = fr[:, 30:34], fr[:, 26:30]
+        tcpudp = (fr[:, 23] == 6) | (fr[:, 23] == 17)
+        out[tcpudp, 34:36], out[tcpudp, 36:38] = fr[tcpudp, 36:38], fr[tcpudp, 34:36]
+        out[fr[:, 23] == 6, 47] = 0x10
+        rr = rng(seed + 99)
+        nv = (t + np.cumsum(rr.integers(0, 9_000, len(out)))).astype(np.uint64)
+        return {"arena": out.reshape(-1), "lens": np.full(len(out), 64, np.uint32), "now_ns": int(nv[0]), "stride": 64, "now_v": nv}
+
+    sc.run_from("nat44_ingress", replies)
+    # DHCP: leases that expire WHILE the batch runs
+    macs = S.sub_mac_key(np.arange(16))
+    pa = np.zeros(16, L.pool_assignment)
+    pa["pool_id"], pa["allocated_ip"], pa["client_class"] = 1, S.ip_bytes(np.uint32(0x0A000010) + np.arange(16)), 1
+    pa["lease_expiry"] = 100 + np.arange(16) % 4  # seconds
+    sc.update("subscriber_pools", macs, pa)
+    pools = np.zeros(1, L.ip_pool)
+    pools["network"], pools["prefix_len"], pools["gateway"] = S.ip_bytes(np.uint32(0x0A000000)), 24, S.ip_bytes(np.uint32(0x0A000001))
+    pools["dns_primary"], pools["lease_time"] = S.ip_bytes(np.uint32(0x08080808)), 600
+    sc.update("ip_pools", np.ones(1, "<u4"), pools)
+    dcfg = np.zeros(1, L.dhcp_server_config)
+    dcfg["server_mac"], dcfg["server_ip"] = [[2, 0xAA, 0xBB, 0xCC, 0xDD, 1]], [[10, 0, 0, 1]]
+    sc.update1("server_config", np.uint32(0), dcfg)
+    F = [dhcp_frame(macs[i % 16], msg_type=3) for i in range(400)]
+    lens = np.array([len(f) for f in F], np.uint32)
+    width = int(((lens.max() + 15) // 16) * 16)
+    hd = np.zeros((len(F), width), np.uint8)
+    for i, f in enumerate(F):
+        hd[i, :len(f)] = f
+    arena, off16 = S.pack_arena(hd, lens)
+    nv = (99 * 10**9 + np.arange(400, dtype=np.uint64) * np.uint64(15 * 10**6))  # 99.0 s .. 105 s
+    sc.run("dhcp_fastpath_prog", arena, lens, int(nv[0]), off16=off16, now_v=nv)
+    return sc
+
+
 ALL_SCRIPTS = {
     "antispoof": antispoof_script,
     "qos": qos_script,
@@ -656,6 +739,7 @@ ALL_SCRIPTS = {
     "pipeline": pipeline_script,
     "pipeline_noeim": lambda: pipeline_script(seed=0x91A0, flags=0x06),
     "ipopts": ipopts_script,
+    "ticks": ticks_script,
     # the order the reference's TC hooks give: antispoof -> qos_ingress -> nat44_egress (a frame the bucket drops never reaches NAT)
     "pipeline_tc": lambda: pipeline_script(seed=0x91A7, prog="pipeline_tc"),
     "pipeline_tc_noeim": lambda: pipeline_script(seed=0x91A9, flags=0x06, prog="pipeline_tc"),

@@ -155,8 +155,8 @@ def test_million_frames_against_reference(name):
 
 @pytest.mark.parametrize("mode", ["device", "pinned"])
 def test_dhcp_config5_against_reference(mode):
-    """BASELINE config #5 at its full table size: 2^20 subscriber_pools entries, 99 % hits, 2^18 requests."""
-    wl = W.dhcp(1 << 18, 0, 1, n_subs=1 << 20)
+    """BASELINE config #5 at its full table size: 1 000 000 subscriber_pools entries (the map's max_entries), 99 % hits, 2^18 requests."""
+    wl = W.dhcp(1 << 18, 0, 1, n_subs=1_000_000)  # the reference map holds MAX_SUBSCRIBERS = 1e6 (bpf/maps.h)
     arena, off16, stride = _arena(wl)
     ref = _oracle_run(wl, arena, off16, stride, 1)
     gpu = _gpu_run(wl, arena, off16, stride, 1, mode)

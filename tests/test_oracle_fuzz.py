@@ -70,7 +70,7 @@ def base_maps_and_frames(scenario: str):
     sc = scenarios.ALL_SCRIPTS[scenario]()
     updates = [st for st in sc.steps if st[0] == "update"]
     run = next(st for st in sc.steps if st[0] == "run")
-    _, _, arena, lens, now, off16, stride, _ = run
+    _, _, arena, lens, now, off16, stride, _, _ = run
     if off16 is None:
         frames = arena.reshape(-1, stride)[: len(lens)]
         return updates, frames, lens, now, stride

@@ -46,7 +46,7 @@ for SEED in SEEDS:
     runs = [(si, st) for si, st in enumerate(sc.steps) if st[0] == "run"]
     for si, st in runs:
         tag = f"s{si:03d}"
-        _, prog, arena, lens, now, off16, stride, prio = st
+        _, prog, arena, lens, now, off16, stride, prio, _ = st
         vw, vg = want[tag + "_verdict"], got[tag + "_verdict"]
         fw = want[tag + "_frames"].reshape(-1, stride)
         fg = got[tag + "_frames"].reshape(-1, stride)
