@@ -400,9 +400,9 @@ __device__ __forceinline__ u8 *tbl_find_ins(const Tbl &t, const u64 *k, u32 *ins
 }
 // Claims slot `ins` (as reported by tbl_find_ins for a key that was absent) for k: EMPTY/TOMB -> BUSY with one
 // CAS, key words 1.. written; nullptr when somebody else took the slot meanwhile (the caller then walks again
-// with tbl_find_or_claim).  Live-entry accounting goes to *pending.
+// with tbl_find_or_claim).  The caller has already reserved the entry in t.count (tbl_reserve).
 template <int KW>
-__device__ __forceinline__ u8 *tbl_claim_at(const Tbl &t, u32 ins, const u64 *k, u32 *pending) {
+__device__ __forceinline__ u8 *tbl_claim_at(const Tbl &t, u32 ins, const u64 *k) {
     if (ins == 0xFFFFFFFFu) return nullptr;
     u8 *s = tbl_slot(t, ins);
     const u64 w0 = ld_vol64(s);
@@ -410,8 +410,20 @@ __device__ __forceinline__ u8 *tbl_claim_at(const Tbl &t, u32 ins, const u64 *k,
     if (atomicCAS((u64 *)s, w0, K_BUSY) != w0) return nullptr;
 #pragma unroll
     for (int j = 1; j < KW; j++) ((u64 *)s)[j] = k[j];
-    ++*pending;
     return s;
+}
+// Reserves room for n new entries: true when they fit under max_entries (t.count then includes them; give back
+// what is not used with tbl_unreserve).  One atomic for a whole chunk of inserts, and exact: the count can never
+// overshoot max_entries, however many warps insert at once.
+__device__ __forceinline__ bool tbl_reserve(const Tbl &t, u32 n) {
+    if (atomicAdd(t.count, n) + n > t.max_entries) {
+        atomicSub(t.count, n);
+        return false;
+    }
+    return true;
+}
+__device__ __forceinline__ void tbl_unreserve(const Tbl &t, u32 n) {
+    if (n) atomicSub(t.count, n);
 }
 
 // Find-or-claim.  Returns the slot; *created says whether this call claimed
@@ -423,7 +435,8 @@ __device__ __forceinline__ u8 *tbl_claim_at(const Tbl &t, u32 ins, const u64 *k,
 // atomic per warp instead of one per insert, which on a million-insert batch is the difference
 // between a same-address atomic storm and none).  The max_entries check is then approximate by at
 // most the inserts in flight, which only matters for the LRU maps at the very edge of capacity.
-template <int KW, bool SKIP_BUSY = false>
+// RESERVED: the caller holds a reservation for the entry (tbl_reserve): no accounting, no max_entries check here.
+template <int KW, bool SKIP_BUSY = false, bool RESERVED = false>
 __device__ __forceinline__ u8 *tbl_find_or_claim(const Tbl &t, const u64 *k, bool *created, u32 *pending = nullptr,
                                                  u64 *stats = nullptr) {
     *created = false;
@@ -449,7 +462,8 @@ __device__ __forceinline__ u8 *tbl_find_or_claim(const Tbl &t, const u64 *k, boo
             u32 target = tomb >= 0 ? (u32)tomb : i;
             u64 expect = tomb >= 0 ? K_TOMB : K_EMPTY;
             u8 *ts = tbl_slot(t, target);
-            if (pending) {
+            if (RESERVED) {
+            } else if (pending) {
                 if (*(volatile u32 *)t.count + *pending >= t.max_entries && !(t.lru && tbl_evict_near(t, home, stats))) return nullptr;
             } else if (atomicAdd(t.count, 1u) >= t.max_entries) {
                 if (!(t.lru && tbl_evict_near(t, home, stats))) { // (the victim's count goes, ours stays)
@@ -466,7 +480,7 @@ __device__ __forceinline__ u8 *tbl_find_or_claim(const Tbl &t, const u64 *k, boo
                 return ts;
             }
             // lost the race for that slot: undo the reservation and look again
-            if (!pending) atomicSub(t.count, 1u);
+            if (!pending && !RESERVED) atomicSub(t.count, 1u);
             if (tomb >= 0) {
                 tomb = -1;
                 i = (u32)tbl_hash<KW>(k) & t.mask;

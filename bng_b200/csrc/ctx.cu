@@ -15,7 +15,9 @@
 #include <algorithm>
 #include <mutex>
 #include <string>
+#include <string_view>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/bng_b200.h"
@@ -82,6 +84,12 @@ struct bng_ctx {
     };
     std::vector<Staged> staged;
     u64 staged_total = 0, staged_errors = 0, staged_flushes = 0;
+    u64 rebuilds = 0; // flow-table rebuilds (tombstone compaction) so far
+    bool small_dirty = false; // a map feeding the SmallTabs image changed since the image was built
+    // grow-only scratch of map dumps (no cudaMalloc / cudaFree per call)
+    u8 *dump_k = nullptr, *dump_v = nullptr;
+    u32 *dump_c = nullptr;
+    size_t dump_kb = 0, dump_vb = 0;
     // multi-GPU reconciliation (bng_comm_init / bng_sync_reduce)
     ncclComm_t comm = nullptr;
     u32 comm_rank = 0, comm_world = 1;
@@ -319,7 +327,7 @@ int flush_staged_locked(bng_ctx *c, int only_map) {
         int first = 0;
         u64 nerr = 0;
         int r = hash_cmd(c, m, TOP_UPDATE, k2.data(), v2.data(), uniq, BNG_ANY, &first, &nerr);
-        if (!r && feeds_small_tabs_p(m)) r = small_refresh_p(c);
+        if (!r && feeds_small_tabs_p(m)) c->small_dirty = true;
         c->staged_errors += nerr;
         c->staged_total -= q.n;
         c->staged_flushes++;
@@ -458,7 +466,7 @@ int bng_close(bng_ctx *c) {
         for (void *p : c->allocs) cudaFree(p);
         Scratch &s = c->L.s;
         void *sp[] = {s.key_a, s.key_b, s.val_a, s.val_b, s.qslot, s.pflag, s.cub_tmp, s.counters,
-                      c->io_dev, c->hb_pkts, c->hb_off, c->hb_len, c->hb_prio, c->hb_verdict, c->hb_now};
+                      c->io_dev, c->hb_pkts, c->hb_off, c->hb_len, c->hb_prio, c->hb_verdict, c->hb_now, c->dump_k, c->dump_v, c->dump_c};
         for (void *p : sp)
             if (p) cudaFree(p);
         if (c->io_host) cudaFreeHost(c->io_host);
@@ -652,9 +660,33 @@ int bng_map_update_batch(bng_ctx *c, int map, const void *keys, const void *valu
     if (int fr = flush_staged_locked(c, map)) return fr; // staged Puts of this map come first
     switch (m->kind) {
     case KIND_HASH: {
-        int first = 0;
-        int r = hash_cmd(c, m, TOP_UPDATE, keys, (void *)values, n, (u32)flags, &first);
-        if (!r && feeds_small_tabs(m)) r = small_refresh(c);
+        // The reference applies the entries of a batch one after the other; one kernel launch applies them
+        // concurrently, which is only the same thing when no key occurs twice.  The batch is therefore cut
+        // wherever a key repeats (usually nowhere) and the pieces run in order.
+        int first = 0, r = 0;
+        const u32 ks = m->key_size;
+        u64 seg = 0;
+        if (n > 1) {
+            std::unordered_set<std::string_view> seen;
+            seen.reserve((size_t)n * 2);
+            for (u64 i = 0; i < n && !r; i++) {
+                std::string_view kv((const char *)keys + i * ks, ks);
+                if (!seen.insert(kv).second) { // key seen in this piece: run the piece, start the next one here
+                    int f2 = 0;
+                    r = hash_cmd(c, m, TOP_UPDATE, (const u8 *)keys + seg * ks, (u8 *)values + seg * m->value_size, i - seg, (u32)flags, &f2);
+                    if (f2 && !first) first = f2;
+                    seg = i;
+                    seen.clear();
+                    seen.insert(kv);
+                }
+            }
+        }
+        if (!r) {
+            int f2 = 0;
+            r = hash_cmd(c, m, TOP_UPDATE, (const u8 *)keys + seg * ks, (u8 *)values + seg * m->value_size, n - seg, (u32)flags, &f2);
+            if (f2 && !first) first = f2;
+        }
+        if (!r && feeds_small_tabs(m)) c->small_dirty = true; // the image is rebuilt once, at the next batch boundary
         return r ? r : first;
     }
     case KIND_ARRAY:
@@ -668,7 +700,8 @@ int bng_map_update_batch(bng_ctx *c, int map, const void *keys, const void *valu
                                   c->L.stream));
         }
         CU(c, cudaStreamSynchronize(c->L.stream));
-        return feeds_small_tabs(m) ? small_refresh(c) : 0;
+        if (feeds_small_tabs(m)) c->small_dirty = true;
+        return 0;
     case KIND_LPM:
         for (u64 i = 0; i < n; i++) {
             const u32 *k = (const u32 *)((const u8 *)keys + i * 8);
@@ -746,7 +779,7 @@ int bng_map_delete(bng_ctx *c, int map, const void *key) {
     if (m->kind == KIND_HASH) {
         int first = 0;
         int r = hash_cmd(c, m, TOP_DELETE, key, nullptr, 1, 0, &first);
-        if (!r && !first && feeds_small_tabs(m)) r = small_refresh(c);
+        if (!r && !first && feeds_small_tabs(m)) c->small_dirty = true;
         return r ? r : first;
     }
     if (m->kind == KIND_LPM) {
@@ -782,7 +815,8 @@ int bng_map_clear(bng_ctx *c, int map) {
     if (m->tbl == &c->dev.sub_nat || m->tbl == &c->dev.qos_in)
         CU(c, run_dir_clear_half(c->L, c->dev.subdir, m->tbl == &c->dev.sub_nat ? 1 : 2));
     CU(c, cudaStreamSynchronize(c->L.stream));
-    return feeds_small_tabs(m) ? small_refresh(c) : 0;
+    if (feeds_small_tabs(m)) c->small_dirty = true;
+    return 0;
 }
 
 int64_t bng_map_dump(bng_ctx *c, int map, void *keys_out, void *values_out, uint64_t cap) {
@@ -797,6 +831,7 @@ int64_t bng_map_dump(bng_ctx *c, int map, void *keys_out, void *values_out, uint
 // Rebuilds the SmallTabs image from the authoritative device state of
 // antispoof_config, nat_config_map, alg_ports and hairpin_ips and uploads it.
 static int small_refresh(bng_ctx *c) {
+    c->small_dirty = false;
     SmallTabs *im = new SmallTabs();
     memset(im, 0, sizeof(*im));
     for (u32 i = 0; i < HP_SLOTS; i++) im->hp_hash[i] = HP_EMPTY;
@@ -880,31 +915,32 @@ static int64_t map_dump_locked(bng_ctx *c, MapReg *m, void *keys_out, void *valu
     if (m->kind != KIND_HASH) return -EINVAL;
     if (cap == 0) return 0;
     const Tbl &t = *m->tbl;
-    u8 *dk = nullptr, *dv = nullptr;
-    u32 *dc = nullptr;
-    CU(c, cudaMalloc((void **)&dk, cap * t.key_size));
-    cudaError_t e2 = cudaMalloc((void **)&dv, cap * t.value_size);
-    cudaError_t e3 = cudaMalloc((void **)&dc, 16);
+    if (cap * t.key_size > c->dump_kb || cap * t.value_size > c->dump_vb || !c->dump_c) {
+        if (c->dump_k) cudaFree(c->dump_k);
+        if (c->dump_v) cudaFree(c->dump_v);
+        c->dump_k = c->dump_v = nullptr;
+        c->dump_kb = c->dump_vb = 0;
+        size_t kb = std::max<size_t>(cap * t.key_size, 1 << 16), vb = std::max<size_t>(cap * t.value_size, 1 << 16);
+        if (cudaMalloc((void **)&c->dump_k, kb) != cudaSuccess || cudaMalloc((void **)&c->dump_v, vb) != cudaSuccess)
+            return fail(c, -ENOMEM, "dump: out of device memory");
+        if (!c->dump_c && cudaMalloc((void **)&c->dump_c, 16) != cudaSuccess) return fail(c, -ENOMEM, "dump: out of device memory");
+        c->dump_kb = kb, c->dump_vb = vb;
+    }
+    u8 *dk = c->dump_k, *dv = c->dump_v;
+    u32 *dc = c->dump_c;
     int rc = 0;
     u32 cnt = 0;
-    if (e2 != cudaSuccess || e3 != cudaSuccess) {
-        rc = fail(c, -ENOMEM, "dump: out of device memory");
-    } else {
-        cudaMemsetAsync(dc, 0, 16, c->L.stream);
-        cudaError_t e = run_table_dump(c->L, t, dk, dv, dc, cap);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(&cnt, dc, 4, cudaMemcpyDeviceToHost, c->L.stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->L.stream);
-        if (e == cudaSuccess && cnt) {
-            u64 n = std::min<u64>(cnt, cap);
-            e = cudaMemcpy(keys_out, dk, n * t.key_size, cudaMemcpyDeviceToHost);
-            if (e == cudaSuccess) e = cudaMemcpy(values_out, dv, n * t.value_size, cudaMemcpyDeviceToHost);
-            cnt = (u32)n;
-        }
-        if (e != cudaSuccess) rc = fail(c, -EIO, "dump: %s", cudaGetErrorString(e));
+    cudaMemsetAsync(dc, 0, 16, c->L.stream);
+    cudaError_t e = run_table_dump(c->L, t, dk, dv, dc, cap);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&cnt, dc, 4, cudaMemcpyDeviceToHost, c->L.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->L.stream);
+    if (e == cudaSuccess && cnt) {
+        u64 n = std::min<u64>(cnt, cap);
+        e = cudaMemcpy(keys_out, dk, n * t.key_size, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(values_out, dv, n * t.value_size, cudaMemcpyDeviceToHost);
+        cnt = (u32)n;
     }
-    cudaFree(dk);
-    if (dv) cudaFree(dv);
-    if (dc) cudaFree(dc);
+    if (e != cudaSuccess) rc = fail(c, -EIO, "dump: %s", cudaGetErrorString(e));
     return rc ? rc : (int64_t)cnt;
 }
 
@@ -1063,6 +1099,7 @@ int bng_prog_run(bng_ctx *c, int prog, bng_batch *bb) {
     int r = ensure_scratch(c, bb->n);
     if (r) return r;
     if ((r = flush_staged_locked(c, -1)) != 0) return r; // the batch boundary: staged upserts become visible
+    if (c->small_dirty && (r = small_refresh_p(c)) != 0) return r; // ... and the shared-memory image of the small maps is rebuilt
     c->dev.batch_seq++;
     c->dev.epoch = c->dev.batch_seq % 65535u + 1; // what a session hit stamps next to last_seen (common.cuh)
     if (c->dev.epoch == 1 && c->dev.batch_seq > 1) CU(c, run_epoch_reset(c->L, c->dev.sessions)); // the 16-bit stamp wraps
@@ -1234,6 +1271,39 @@ int bng_sync_reduce(bng_ctx *c, uint64_t *totals_out) {
 
 void *bng_stream(bng_ctx *c) { return c ? (void *)c->L.stream : nullptr; }
 
+// Rebuilds a hash table in place (same capacity): what deletes, expiry and eviction left as tombstones is gone and
+// every probe chain is as short as the load factor allows.  Only for tables nothing else indexes by slot number
+// (the NAT flow tables; subscriber_nat / qos_ingress slots are referenced by the subscriber directory).
+static int table_rebuild_locked(bng_ctx *c, Tbl *t) {
+    Tbl nw = *t;
+    nw.lru = LRU_NONE;
+    nw.max_entries = nw.mask; // the copy must never refuse or evict
+    size_t bytes = ((size_t)t->mask + 1) * t->slot_bytes;
+    CU(c, cudaMalloc((void **)&nw.slots, bytes));
+    u32 *cnt = nullptr;
+    cudaError_t e = cudaMalloc((void **)&cnt, 16);
+    if (e != cudaSuccess) {
+        cudaFree(nw.slots);
+        return fail(c, -ENOMEM, "rebuild: out of device memory");
+    }
+    nw.count = cnt;
+    e = cudaMemsetAsync(nw.slots, 0xFF, bytes, c->L.stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(cnt, 0, 16, c->L.stream);
+    if (e == cudaSuccess) e = run_table_rebuild(c->L, *t, nw);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->L.stream);
+    cudaFree(cnt);
+    if (e != cudaSuccess) {
+        cudaFree(nw.slots);
+        return fail(c, -EIO, "rebuild: %s", cudaGetErrorString(e));
+    }
+    for (auto &p : c->allocs)
+        if (p == t->slots) p = nw.slots;
+    cudaFree(t->slots);
+    t->slots = nw.slots;
+    c->rebuilds++;
+    return 0;
+}
+
 // Session expiry sweep (sweep.cu): removes every nat_sessions entry idle for longer than the timeout of its
 // protocol / TCP state at now_ns, with its nat_reverse entry, its EIM reference, the subscriber's active-session
 // count; counts sessions_expired and logs NAT_LOG_SESSION_DELETE.  A batch of its own between program runs.
@@ -1247,13 +1317,19 @@ int bng_sweep(bng_ctx *c, uint64_t now_ns, uint64_t *expired_out) {
     c->dev.epoch = c->dev.batch_seq % 65535u + 1;
     if (c->dev.epoch == 1 && c->dev.batch_seq > 1) CU(c, run_epoch_reset(c->L, c->dev.sessions));
     u32 *cnt = c->L.s.counters + 8; // scratch words 8.. are free between program runs
-    CU(c, cudaMemsetAsync(cnt, 0, 4, c->L.stream));
+    CU(c, cudaMemsetAsync(cnt, 0, 8, c->L.stream));
     CU(c, run_nat_sweep(c->L, c->dev, now_ns, cnt));
-    u32 n = 0;
-    CU(c, cudaMemcpyAsync(&n, cnt, 4, cudaMemcpyDeviceToHost, c->L.stream));
+    u32 n[2] = {0, 0};
+    CU(c, cudaMemcpyAsync(n, cnt, 8, cudaMemcpyDeviceToHost, c->L.stream));
     CU(c, cudaStreamSynchronize(c->L.stream));
     prof_collect(c->L);
-    if (expired_out) *expired_out = n;
+    if (expired_out) *expired_out = n[0];
+    // a quarter of nat_sessions' slots are tombstones: rebuild the three flow tables (they churn together)
+    if (n[1] > (c->dev.sessions.mask + 1) / 4) {
+        if ((r = table_rebuild_locked(c, &c->dev.sessions)) != 0) return r;
+        if ((r = table_rebuild_locked(c, &c->dev.reverse)) != 0) return r;
+        if ((r = table_rebuild_locked(c, &c->dev.eim)) != 0) return r;
+    }
     return 0;
 }
 
@@ -1463,6 +1539,7 @@ static uint64_t read_stat(bng_ctx *c, int idx) {
 }
 uint64_t bng_lru_overflow(bng_ctx *c) { return read_stat(c, ST_LRU_OVERFLOW); }
 uint64_t bng_lru_evictions(bng_ctx *c) { return read_stat(c, ST_LRU_EVICT); }
+uint64_t bng_table_rebuilds(bng_ctx *c) { return c ? c->rebuilds : 0; }
 uint64_t bng_events_lost(bng_ctx *c) { return read_stat(c, ST_EV_LOST_SPOOF) + read_stat(c, ST_EV_LOST_NATLOG); }
 
 } // extern "C"

@@ -273,16 +273,12 @@ __device__ __forceinline__ int dhcp_one(const DevCtx &c, BlockStats &bs, u8 *p, 
     return XDP_TX_;
 }
 
-// A request is up to ~350 bytes that the program reads sparsely and rewrites almost entirely (L2 headers,
-// BOOTP fixed part, 192 zeroed bytes, options), so frames are staged through shared memory with the TMA: every
-// thread bulk-copies its frame in (cp.async.bulk, completion on an mbarrier), runs the program on the
-// shared-memory copy, and bulk-stores it back.  HBM sees two streaming passes per frame instead of scattered
-// 1-16 byte accesses.
-// Every thread owns its staging slot AND its mbarrier: there is no block-wide barrier anywhere in the loop, so
-// the warps of an SM drift apart and one warp's loads, another's program and a third's stores overlap (with one
-// barrier per block — round 1 — the three phases of a tile ran strictly one after the other: 0.49 of the HBM
-// roofline at 25 % occupancy).  A thread only has to wait for its own store to have READ its slot before the
-// next load overwrites it.
+// Tile kernel (one mbarrier per block; per-thread barriers without any block-wide synchronisation were measured
+// in round 2 and are SLOWER: 1.19 vs 0.96 ms per 2^22 requests): a request is up to ~350 bytes that the program reads sparsely and rewrites almost
+// entirely (L2 headers, BOOTP fixed part, 192 zeroed bytes, options), so frames are staged through
+// shared memory with the TMA: every thread bulk-copies its frame (cp.async.bulk, completion on an
+// mbarrier), runs the program on the shared-memory copy, and bulk-stores it back.  HBM sees two
+// streaming passes per frame instead of scattered 1-16 byte accesses.
 #define DH_TILE 128
 // Bytes staged per frame, also the slot stride in shared memory.  400 = 16 x 25: a multiple of 16 (bulk
 // copies) whose word stride (100) spreads same-offset accesses of the 32 lanes over 8 banks; 384 or 448
@@ -290,20 +286,24 @@ __device__ __forceinline__ int dhcp_one(const DevCtx &c, BlockStats &bs, u8 *p, 
 #define DH_SLOT 400
 
 __global__ void __launch_bounds__(DH_TILE) k_dhcp_fastpath(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b) {
-    extern __shared__ __align__(128) u8 stage[]; // DH_TILE * DH_SLOT, then DH_TILE mbarriers
+    extern __shared__ __align__(128) u8 stage[]; // DH_TILE * DH_SLOT
     __shared__ BlockStats bs;
+    __shared__ u64 bar;
     bstats_init(bs);
-    u64 *bars = (u64 *)(stage + (size_t)DH_TILE * DH_SLOT);
-    const u32 bar_a = (u32)__cvta_generic_to_shared(&bars[threadIdx.x]);
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const u32 bar_a = (u32)__cvta_generic_to_shared(&bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(DH_TILE));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     u8 *mine = stage + (size_t)threadIdx.x * DH_SLOT;
     const u32 mine_a = (u32)__cvta_generic_to_shared(mine);
     u32 phase = 0;
-    for (u32 i = blockIdx.x * DH_TILE + threadIdx.x; i < b.n; i += gridDim.x * DH_TILE) {
-        u32 len = b.len[i];
-        u8 *g = frame_ptr(b, i);
+    for (u32 base = blockIdx.x * DH_TILE; base < b.n; base += gridDim.x * DH_TILE) {
+        const u32 i = base + threadIdx.x;
+        const bool act = i < b.n;
+        u32 len = act ? b.len[i] : 0;
+        u8 *g = act ? frame_ptr(b, i) : b.pkts;
         const u32 present = frame_dlen(b, len);
         u32 nbytes = ((present < DH_SLOT ? present : DH_SLOT) + 15u) & ~15u;
         if (nbytes > DH_SLOT) nbytes = DH_SLOT;
@@ -313,21 +313,23 @@ __global__ void __launch_bounds__(DH_TILE) k_dhcp_fastpath(const __grid_constant
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(mine_a),
                          "l"(g), "r"(nbytes), "r"(bar_a)
                          : "memory");
-            u32 done = 0;
-            while (!done) {
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\t"
-                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                    "selp.u32 %0, 1, 0, p;\n\t}"
-                    : "=r"(done)
-                    : "r"(bar_a), "r"(phase)
-                    : "memory");
-            }
-            phase ^= 1;
+        } else {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a) : "memory");
         }
+        u32 done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar_a), "r"(phase)
+                : "memory");
+        }
+        phase ^= 1;
         // ---- the program, on the staged copy ----
         bool direct = false; // the program would reach past the staged bytes: run it on the frame itself
-        if (present > DH_SLOT) {
+        if (act && present > DH_SLOT) {
             u32 et = rd16(mine, 12), l3 = 14;
             if (et == 0x0081u || et == 0xA888u) {
                 l3 = 18;
@@ -335,24 +337,27 @@ __global__ void __launch_bounds__(DH_TILE) k_dhcp_fastpath(const __grid_constant
             }
             direct = l3 + (u32)(mine[l3] & 0x0f) * 4 + 8 + 240 + 64 > DH_SLOT;
         }
-        const u32 l0 = len;
-        int v = dhcp_one(c, bs, direct ? g : mine, len, frame_dlen(b, l0), frame_now(b, i));
-        b.verdict[i] = (u8)v;
-        if (len != l0) b.len[i] = len;
+        if (act) {
+            const u32 l0 = len;
+            int v = dhcp_one(c, bs, direct ? g : mine, len, frame_dlen(b, l0), frame_now(b, i));
+            b.verdict[i] = (u8)v;
+            if (len != l0) b.len[i] = len;
+        }
+        if (direct) nbytes = 0;
         // ---- stage out (every staged frame: a passed frame may have been rewritten, :769) ----
-        if (nbytes && !direct) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (nbytes) {
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(mine_a), "r"(nbytes) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // my slot is reused by my next frame
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // the slot is reused by the next tile
         }
+        __syncthreads();
     }
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     bstats_flush(bs, c.stats);
 }
 
 cudaError_t run_dhcp_fastpath(Launcher &L, const DevCtx &c, const DevBatch &b) {
-    const int smem = DH_TILE * DH_SLOT + DH_TILE * 8;
+    const int smem = DH_TILE * DH_SLOT;
     if (!L.dhcp_smem_set) { // function attributes are per device: set on the device this context runs on
         cudaError_t e = cudaFuncSetAttribute(k_dhcp_fastpath, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;

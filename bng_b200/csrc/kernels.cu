@@ -549,7 +549,6 @@ __global__ void __launch_bounds__(TEAM, (TEAM == 128 ? 6 : RESOLVE_MINB)) k_reso
     u32 pp = 0, dp = 0; // per-thread partial QoS counters
     u64 pb = 0, db = 0;
     NatPend pend;
-    pend.ses = pend.rev = pend.eim = 0;
     pend.log_rec = nullptr;
     pend.logged = false;
     // groups are handed out dynamically (fat and thin groups mix: a static stride leaves blocks idle at the end)
@@ -736,15 +735,6 @@ __global__ void __launch_bounds__(TEAM, (TEAM == 128 ? 6 : RESOLVE_MINB)) k_reso
             *(u64 *)(slot + 24) = tb.last_update;
         }
         __syncthreads();
-    }
-    if (NAT && warp == 0) { // live-entry counts of the flow tables: one global atomic per block and table
-        u32 a = __reduce_add_sync(0xffffffffu, pend.ses), r2 = __reduce_add_sync(0xffffffffu, pend.rev),
-            e = __reduce_add_sync(0xffffffffu, pend.eim);
-        if (lane == 0) {
-            if (a) atomicAdd(c.sessions.count, a);
-            if (r2) atomicAdd(c.reverse.count, r2);
-            if (e) atomicAdd(c.eim.count, e);
-        }
     }
     if (QOS) {
         warp_stat_flush(bs, ST_QOS_PASS_PKTS, pp);

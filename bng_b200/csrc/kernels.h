@@ -65,6 +65,7 @@ cudaError_t run_table_op(Launcher &L, const Tbl &t, int op, const u8 *keys, u8 *
                          const Tbl &dir, int dir_role);
 cudaError_t run_dir_clear_half(Launcher &L, const Tbl &dir, int role);
 cudaError_t run_epoch_reset(Launcher &L, const Tbl &sessions);
+cudaError_t run_table_rebuild(Launcher &L, const Tbl &old_table, const Tbl &empty_table);
 // session expiry sweep (sweep.cu); n_expired: device counter, incremented by the number of sessions removed
-cudaError_t run_nat_sweep(Launcher &L, const DevCtx &c, u64 now, u32 *n_expired);
+cudaError_t run_nat_sweep(Launcher &L, const DevCtx &c, u64 now, u32 *n_expired /* [0] expired, [1] tombstones seen */);
 cudaError_t run_table_dump(Launcher &L, const Tbl &t, u8 *keys_out, u8 *vals_out, u32 *count_out, u64 cap);

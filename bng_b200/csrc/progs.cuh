@@ -206,11 +206,9 @@ __device__ __forceinline__ bool is_private_ip(u32 ip_le) { // bpf/nat44.c:340-36
     return false;
 }
 
-// Batched accounting of the ordered NAT phase (one per lane, reduced per warp by k_resolve):
-// live-entry deltas of the three flow tables, and the log record reserved for this frame.
+// Per-lane state of the ordered NAT phase: the log record reserved for this frame.
 struct NatPend {
-    u32 ses, rev, eim; // inserts not yet added to the tables' counts
-    u8 *log_rec;       // staged nat_log_rb record reserved for this frame (nullptr: ring full)
+    u8 *log_rec; // staged nat_log_rb record reserved for this frame (nullptr: ring full)
     bool logged;
 };
 
@@ -311,13 +309,16 @@ struct NatFlow {
     u32 saddr, daddr, proto, l4;
     u16 sport, dport;
     u8 is_hairpin;
-    bool ok; // reaches the session lookup
+    bool ok;     // reaches the session lookup
+    bool alg;    // stopped at an ALG trigger (:615-642); alg_type then says which
+    u8 alg_type;
 };
 // count: bump the hairpin / ALG statistics and write the ALG log record (false when an earlier phase did it for this frame)
 __device__ __forceinline__ NatFlow nat_parse(const DevCtx &c, BlockStats &bs, const u8 *p, u32 dlen, u32 idx, u64 now,
                                              const u8 *sub, u32 cfg_flags, const bool COUNT) {
     NatFlow f;
-    f.ok = false;
+    f.ok = f.alg = false;
+    f.alg_type = 0;
     f.saddr = rd32(p, 26);
     f.daddr = rd32(p, 30);
     f.proto = p[23];
@@ -333,6 +334,8 @@ __device__ __forceinline__ NatFlow nat_parse(const DevCtx &c, BlockStats &bs, co
             u64 ak = ((u32)bswap16(f.dport) << 16) | f.proto;
             const u8 *alg = tbl_find<1, false>(c.alg, &ak);
             if (alg) { // ALG traffic goes to userspace untranslated (:615-642)
+                f.alg = true;
+                f.alg_type = alg[8 + 3];
                 if (COUNT) {
                     bstats_add(bs, ST_NAT_ALG, 1);
                     nat_log(c, idx, now, 7, *(const u32 *)(sub + 32), f.saddr, 0, f.sport, 0, f.daddr, f.dport, (u8)f.proto,
@@ -416,7 +419,7 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
                     bstats_add(bs, ST_NAT_EXHAUST, 1);
                 } else {
                     bool created;
-                    m = tbl_find_or_claim<1, true>(c.eim, &ek, &created, pd ? &pd->eim : nullptr, c.stats);
+                    m = tbl_find_or_claim<1, true>(c.eim, &ek, &created, nullptr, c.stats);
                     if (m && created) {
                         *(u32 *)(m + 8) = pub_ip;
                         *(u32 *)(m + 12) = ext; // external_port (host order) + zero pad
@@ -453,7 +456,7 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
             nat_port = bswap16(ap);
         }
         bool created;
-        u8 *ns = tbl_find_or_claim<2, true>(c.sessions, key, &created, pd ? &pd->ses : nullptr, c.stats); // BPF_ANY (:730)
+        u8 *ns = tbl_find_or_claim<2, true>(c.sessions, key, &created, nullptr, c.stats); // BPF_ANY (:730)
         if (ns) {
             nat_ses_fill(ns, nat_ip, nat_port, sport, saddr, daddr, dport, proto, f.is_hairpin, len, now, c.epoch);
             if (created) tbl_publish<false>(ns, key[0]);
@@ -463,7 +466,7 @@ __device__ __forceinline__ NatOut nat_egress_one(const DevCtx &c, BlockStats &bs
         u64 rk[2];
         rk[0] = (u64)daddr | ((u64)nat_ip << 32);
         rk[1] = (u64)dport | ((u64)nat_port << 16) | ((u64)proto << 32);
-        u8 *rs = tbl_find_or_claim<2, true>(c.reverse, rk, &created, pd ? &pd->rev : nullptr, c.stats); // BPF_ANY (:740)
+        u8 *rs = tbl_find_or_claim<2, true>(c.reverse, rk, &created, nullptr, c.stats); // BPF_ANY (:740)
         if (rs) {
             *(u64 *)(rs + 16) = key[0];
             *(u64 *)(rs + 24) = key[1];
@@ -513,7 +516,7 @@ __device__ __forceinline__ u32 nat_chunk_coop(const DevCtx &c, BlockStats &bs, c
     //      comes in with two 256-bit loads and is rewritten in registers, like classify does; anything else takes
     //      the byte-wise parse of the sequential code ----
     NatFlow f;
-    f.ok = false;
+    f.ok = f.alg = false;
     Hdr64 h;
     bool fast = false, wide = false;
     if (mine && !count_parse) {
@@ -540,7 +543,8 @@ __device__ __forceinline__ u32 nat_chunk_coop(const DevCtx &c, BlockStats &bs, c
             f.ok = true;
         }
     }
-    if (mine && !fast) f = nat_parse(c, bs, p, dlen, idx + b.base, now, sub, cfg_flags, count_parse);
+    // (nothing is counted here: a frame that is not in the committed prefix comes back and is parsed again)
+    if (mine && !fast) f = nat_parse(c, bs, p, dlen, idx + b.base, now, sub, cfg_flags, false);
     const bool go = mine && f.ok;
     // ---- probes: where the flow's entries are, or would go ----
     u64 key[2] = {0, 0}, ek = 0;
@@ -608,11 +612,6 @@ __device__ __forceinline__ u32 nat_chunk_coop(const DevCtx &c, BlockStats &bs, c
         const u32 r0 = __match_any_sync(0xffffffffu, create ? rk[0] : (u64)lane | (1ull << 63));
         const u32 r1 = __match_any_sync(0xffffffffu, create ? rk[1] : (u64)lane | (1ull << 63));
         if (create && (r0 & r1 & cmask & below)) clash = true;
-        const u32 room = 64 + ncreate;
-        if (*(volatile u32 *)c.sessions.count + pend.ses + room >= c.sessions.max_entries ||
-            *(volatile u32 *)c.reverse.count + pend.rev + room >= c.reverse.max_entries ||
-            (eim_on && *(volatile u32 *)c.eim.count + pend.eim + room >= c.eim.max_entries))
-            all_clash = true;
     }
     if (__any_sync(0xffffffffu, all_clash)) return 0;
     // the prefix: every frame of this call below the first one that interacts with an earlier frame
@@ -621,13 +620,38 @@ __device__ __forceinline__ u32 nat_chunk_coop(const DevCtx &c, BlockStats &bs, c
     if (!take) return 0;
     const bool in = (take >> lane) & 1;
     const u32 nalloc_take = __popc(amask & take);
+    // room for what the prefix creates, reserved exactly (a table at max_entries sends the chunk to the sequential
+    // code, which evicts); surplus — a nat_reverse key that existed, a slot found again — is given back below
+    const u32 n_ses = __popc(cmask & take), n_eim = eim_on ? nalloc_take : 0;
+    u32 res_ok = 1;
+    if (lane == 0 && n_ses) {
+        if (!tbl_reserve(c.sessions, n_ses)) {
+            res_ok = 0;
+        } else if (!tbl_reserve(c.reverse, n_ses)) {
+            tbl_unreserve(c.sessions, n_ses);
+            res_ok = 0;
+        } else if (n_eim && !tbl_reserve(c.eim, n_eim)) {
+            tbl_unreserve(c.sessions, n_ses);
+            tbl_unreserve(c.reverse, n_ses);
+            res_ok = 0;
+        }
+    }
+    if (!__shfl_sync(0xffffffffu, res_ok, 0)) return 0;
 
     // ---- commit: nothing below depends on another lane of the chunk ----
     if (nalloc_take && lane == 0) {
         const u32 nn = next + nalloc_take;
         *(volatile u32 *)(sub + 16) = nn > port_end ? port_start : nn;
     }
-    u32 n_hit = 0, n_miss = 0, n_created = 0, n_snat = 0;
+    u32 n_hit = 0, n_miss = 0, n_created = 0, n_snat = 0, back_ses = 0, back_rev = 0, back_eim = 0;
+    if (mine && in && count_parse) { // parse-stage counters of a frame nobody has counted yet (TC order)
+        if (f.alg) {
+            bstats_add(bs, ST_NAT_ALG, 1);
+            nat_log(c, idx + b.base, now, 7, *(const u32 *)(sub + 32), f.saddr, 0, f.sport, 0, f.daddr, f.dport, (u8)f.proto, f.alg_type);
+        } else if (f.ok && f.is_hairpin) {
+            bstats_add(bs, ST_NAT_HAIRPIN, 1);
+        }
+    }
     if (go && in) {
         const u32 sub_id = *(const u32 *)(sub + 32);
         if (ses) { // created earlier in this batch (or by a previous chunk): the hit path, :674-680
@@ -640,27 +664,28 @@ __device__ __forceinline__ u32 nat_chunk_coop(const DevCtx &c, BlockStats &bs, c
             // the three claims first, so that their atomics are in flight together
             bool created;
             u8 *nm = nullptr, *ns, *rs = rev;
-            if (!m && eim_on) nm = tbl_claim_at<1>(c.eim, eim_ins, &ek, &pend.eim);
-            ns = tbl_claim_at<2>(c.sessions, ses_ins, key, &pend.ses);
+            if (!m && eim_on) nm = tbl_claim_at<1>(c.eim, eim_ins, &ek);
+            ns = tbl_claim_at<2>(c.sessions, ses_ins, key);
             bool rs_new = false;
             if (!rs) {
-                rs = tbl_claim_at<2>(c.reverse, rev_ins, rk, &pend.rev);
+                rs = tbl_claim_at<2>(c.reverse, rev_ins, rk);
                 rs_new = rs != nullptr;
             }
             // (a slot another subscriber's worker took in the meantime: walk again)
             bool nm_new = nm != nullptr, ns_new = ns != nullptr;
             if (!m && eim_on && !nm) {
-                nm = tbl_find_or_claim<1, true>(c.eim, &ek, &created, &pend.eim, c.stats);
+                nm = tbl_find_or_claim<1, true, true>(c.eim, &ek, &created);
                 nm_new = nm && created;
             }
             if (!ns) {
-                ns = tbl_find_or_claim<2, true>(c.sessions, key, &created, &pend.ses, c.stats);
+                ns = tbl_find_or_claim<2, true, true>(c.sessions, key, &created);
                 ns_new = ns && created;
             }
             if (!rs) {
-                rs = tbl_find_or_claim<2, true>(c.reverse, rk, &created, &pend.rev, c.stats);
+                rs = tbl_find_or_claim<2, true, true>(c.reverse, rk, &created);
                 rs_new = rs && created;
             }
+            back_ses = !ns_new, back_rev = !rs_new, back_eim = (!m && eim_on && !nm_new);
             if (m) { // existing endpoint mapping (:482-487); two lanes may share it: the later frame's clock stays
                 if (stamped)
                     atomicMax((unsigned long long *)(m + 24), (unsigned long long)now);
@@ -737,7 +762,12 @@ __device__ __forceinline__ u32 nat_chunk_coop(const DevCtx &c, BlockStats &bs, c
     }
     const u32 t_created = __reduce_add_sync(0xffffffffu, n_created), t_hit = __reduce_add_sync(0xffffffffu, n_hit),
               t_miss = __reduce_add_sync(0xffffffffu, n_miss), t_snat = __reduce_add_sync(0xffffffffu, n_snat);
+    const u32 b_ses = __reduce_add_sync(0xffffffffu, back_ses), b_rev = __reduce_add_sync(0xffffffffu, back_rev),
+              b_eim = __reduce_add_sync(0xffffffffu, back_eim);
     if (lane == 0) {
+        tbl_unreserve(c.sessions, b_ses);
+        tbl_unreserve(c.reverse, b_rev);
+        tbl_unreserve(c.eim, b_eim);
         if (t_created) {
             atomicAdd((u64 *)(sub + 40), (u64)t_created);
             atomicAdd((u64 *)(sub + 48), (u64)t_created);

@@ -30,12 +30,15 @@ __global__ void __launch_bounds__(256) k_nat_sweep(const __grid_constant__ DevCt
     bstats_init(bs);
     const Tbl &t = c.sessions;
     const u64 slots = (u64)t.mask + 1;
-    u32 mine = 0;
+    u32 mine = 0, tombs = 0;
     for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < slots; i += (u64)gridDim.x * blockDim.x) {
         u8 *s = t.slots + i * t.slot_bytes;
         const U256 s0 = ldg256(s);
         const u64 k0 = (u64)s0.w[0] | ((u64)s0.w[1] << 32), k1 = (u64)s0.w[2] | ((u64)s0.w[3] << 32);
-        if (k0 >= K_BUSY) continue;
+        if (k0 >= K_BUSY) {
+            tombs += k0 == K_TOMB;
+            continue;
+        }
         const U256 s1 = ldg256(s + 32); // last_seen 8 | orig_ip 4 | state word 4 | orig_port 2 ...
         const u64 last_seen = (u64)s1.w[0] | ((u64)s1.w[1] << 32);
         const u32 state = s1.w[3] & 0xff, proto = (s1.w[3] >> 8) & 0xff;
@@ -43,6 +46,7 @@ __global__ void __launch_bounds__(256) k_nat_sweep(const __grid_constant__ DevCt
         if (atomicCAS((u64 *)s, k0, K_TOMB) != k0) continue; // somebody else removed it
         atomicSub(t.count, 1u);
         mine++;
+        tombs++;
         const u32 nat_ip = s0.w[4], nat_port = s0.w[5] & 0xffff;
         const u32 orig_ip = s1.w[2], orig_port = s1.w[4] & 0xffff;
         const u32 dest_ip = *(const u32 *)(s + SES_DEST_IP), dest_port = *(const u16 *)(s + SES_DEST_PORT);
@@ -83,10 +87,13 @@ __global__ void __launch_bounds__(256) k_nat_sweep(const __grid_constant__ DevCt
         // sweep records carry the marker 0xFFFFFFFE instead of a frame index: the drain orders them by content
         nat_log(c, 0xFFFFFFFEu, now, 2, sub_id, orig_ip, nat_ip, (u16)orig_port, (u16)nat_port, dest_ip, (u16)dest_port, (u8)proto, 0);
     }
-    u32 tot = __reduce_add_sync(0xffffffffu, mine);
-    if ((threadIdx.x & 31) == 0 && tot) {
-        bstats_add(bs, ST_NAT_EXPIRED, tot);
-        atomicAdd(n_expired, tot);
+    u32 tot = __reduce_add_sync(0xffffffffu, mine), tt = __reduce_add_sync(0xffffffffu, tombs);
+    if ((threadIdx.x & 31) == 0) {
+        if (tot) {
+            bstats_add(bs, ST_NAT_EXPIRED, tot);
+            atomicAdd(n_expired, tot);
+        }
+        if (tt) atomicAdd(n_expired + 1, tt);
     }
     bstats_flush(bs, c.stats);
 }

@@ -160,6 +160,37 @@ cudaError_t run_table_op(Launcher &L, const Tbl &t, int op, const u8 *keys, u8 *
     return cudaGetLastError();
 }
 
+// Re-inserts every live entry of `o` into the empty table `nw` (same geometry): tombstones left behind by
+// deletes, expiry and eviction lengthen every probe chain until the table is rebuilt.
+template <int KW>
+__global__ void k_table_rebuild(const __grid_constant__ Tbl o, const __grid_constant__ Tbl nw) {
+    u64 slots = (u64)o.mask + 1;
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < slots; i += (u64)gridDim.x * blockDim.x) {
+        const u8 *s = o.slots + i * o.slot_bytes;
+        u64 kw[KW];
+        kw[0] = *(const u64 *)s;
+        if (kw[0] >= K_BUSY) continue;
+#pragma unroll
+        for (int j = 1; j < KW; j++) kw[j] = ((const u64 *)s)[j];
+        bool created;
+        u8 *d = tbl_find_or_claim<KW>(nw, kw, &created);
+        if (!d || !created) continue; // cannot happen: same capacity, distinct keys
+        for (u32 z = 8 * KW; z < o.slot_bytes; z += 8) *(u64 *)(d + z) = *(const u64 *)(s + z);
+        tbl_publish(d, kw[0]);
+    }
+}
+
+cudaError_t run_table_rebuild(Launcher &L, const Tbl &o, const Tbl &nw) {
+    if (o.key_size <= 8)
+        k_table_rebuild<1><<<L.num_sms * 8, 256, 0, L.stream>>>(o, nw);
+    else if (o.key_size == 16)
+        k_table_rebuild<2><<<L.num_sms * 8, 256, 0, L.stream>>>(o, nw);
+    else
+        k_table_rebuild<4><<<L.num_sms * 8, 256, 0, L.stream>>>(o, nw);
+    L.launches++;
+    return cudaGetLastError();
+}
+
 cudaError_t run_dir_clear_half(Launcher &L, const Tbl &dir, int role) {
     k_dir_clear_half<<<L.num_sms * 4, 256, 0, L.stream>>>(dir, role);
     L.launches++;

@@ -83,6 +83,7 @@ def load_library() -> C.CDLL:
         "bng_snapshot": ([vp, vp, u64], C.c_int64),
         "bng_restore": ([vp, vp, u64], i32),
         "bng_lru_evictions": ([vp], u64),
+        "bng_table_rebuilds": ([vp], u64),
         "bng_map_dump": ([vp, i32, vp, vp, u64], C.c_int64),
         "bng_map_clear": ([vp, i32], i32),
         "bng_prog_id": ([vp, C.c_char_p], i32),
@@ -116,7 +117,7 @@ EXPORTED_SYMBOLS = (
     "bng_prog_run", "bng_sync", "bng_stream", "bng_events_drain", "bng_event_size", "bng_shard_of_mac",
     "bng_stats_device_ptr", "bng_launch_count", "bng_lru_overflow", "bng_events_lost", "bng_prof_enable",
     "bng_prof_read", "bng_host_alloc", "bng_host_free", "bng_map_update_staged", "bng_staged_info",
-    "bng_comm_unique_id", "bng_comm_init", "bng_sync_reduce", "bng_sweep", "bng_lru_evictions", "bng_snapshot", "bng_restore",
+    "bng_comm_unique_id", "bng_comm_init", "bng_sync_reduce", "bng_sweep", "bng_lru_evictions", "bng_snapshot", "bng_restore", "bng_table_rebuilds",
 )
 
 
@@ -319,6 +320,10 @@ class Dataplane:
         n = C.c_uint64(0)
         self._chk(self.lib.bng_sweep(self.h, now_ns, C.byref(n)), "sweep")
         return n.value
+
+    @property
+    def table_rebuilds(self) -> int:
+        return self.lib.bng_table_rebuilds(self.h)
 
     @property
     def lru_evictions(self) -> int:

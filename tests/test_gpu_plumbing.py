@@ -159,3 +159,26 @@ def test_snapshot_restores_into_a_context_of_another_size():
         b.close()
     harness.compare(ra, rb, "after the snapshot: original context vs restored context")
     assert len(blob) > 10_000 and len(ra["tk_nat_sessions"]) > 100
+
+
+def test_update_batch_with_repeated_keys_applies_in_order():
+    """bpf(2) semantics inside one bng_map_update_batch: entries take effect one after the other — the last value of a
+    repeated key stays (BPF_ANY), its second occurrence fails under BPF_NOEXIST."""
+    dp = _dp()
+    try:
+        keys, v = S.bindings(8)
+        k = np.concatenate([keys[:4], keys[:4], keys[4:]])
+        vv = np.concatenate([v[:4], v[4:8], v[4:]])  # second occurrence of keys 0..3 carries other values
+        assert dp.update_batch("subscriber_bindings", k, vv) == 0
+        for i in range(4):
+            assert bytes(dp.lookup("subscriber_bindings", keys[i])) == bytes(L.as_bytes(v[4 + i:5 + i])[0])
+        assert dp.map_info("subscriber_bindings")["count"] == 8
+        import errno
+        assert dp.update_batch("subscriber_bindings", k, vv, 1) == -errno.EEXIST  # NOEXIST: everything exists by now
+        dp.clear("subscriber_bindings")
+        assert dp.update_batch("subscriber_bindings", k, vv, 1) == -errno.EEXIST  # ... and the repeats clash with themselves
+        assert dp.map_info("subscriber_bindings")["count"] == 8
+        for i in range(4):  # the FIRST occurrence won under NOEXIST
+            assert bytes(dp.lookup("subscriber_bindings", keys[i])) == bytes(L.as_bytes(v[i:i + 1])[0])
+    finally:
+        dp.close()

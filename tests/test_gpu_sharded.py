@@ -40,6 +40,8 @@ def _oracle(wl, steps):
         pa = o.arena(h.shape[0] * 64 + 64)
         pa[: h.shape[0] * 64] = h.reshape(-1)
         o.run(prog, pa, l.copy(), wl.now0 - 1, stride=64)
+    for m in ("spoof_events", "nat_log_rb"):
+        o.drain(m)  # the log consumer has caught up before the batches under test (ONE ring here, one per shard there)
     outs = []
     for s in range(steps):
         oa = o.arena(wl.n * 64 + 64)
@@ -88,6 +90,8 @@ def test_union_of_shards_equals_unsharded_reference(world):
                 assert dp.update_batch(m, kb, vb) == 0, m
             mine_w = warm_shard == rank
             dp.run("nat44_egress", warm_h[mine_w].reshape(-1).copy(), warm_l[mine_w].copy(), wl.now0 - 1, stride=64)
+            for m in ("spoof_events", "nat_log_rb"):
+                dp.drain(m)
             mine = np.nonzero(frame_shard == rank)[0]  # index order is kept inside a shard
             for s in range(steps):
                 a = wl.headers[mine].reshape(-1).copy()
