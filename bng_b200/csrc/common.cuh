@@ -57,6 +57,7 @@ struct Tbl {
     u8 *slots;
     u32 *count;      // live entries
     u32 mask;        // capacity - 1 (capacity is a power of two)
+    u32 home_mask;   // hash -> home slot: mask, or mask & ~1 for tables whose lookups fetch the home PAIR of slots at once
     u32 slot_bytes;  // multiple of 32
     u32 voff;        // value offset inside the slot
     u32 max_entries; // the reference map's max_entries
@@ -324,7 +325,7 @@ __device__ __forceinline__ u64 ld_vol64(const u8 *p) { return *(volatile const u
 template <int KW, bool VOL, bool SKIP_BUSY = false>
 __device__ __forceinline__ u8 *tbl_find(const Tbl &t, const u64 *k) {
     if (k[0] >= K_BUSY) return nullptr;
-    u32 i = (u32)tbl_hash<KW>(k) & t.mask;
+    u32 i = (u32)tbl_hash<KW>(k) & t.home_mask;
     for (u32 probe = 0; probe <= t.mask; probe++) {
         u8 *s = tbl_slot(t, i);
         u64 w0 = VOL ? ld_vol64(s) : *(const u64 *)s;
@@ -353,23 +354,29 @@ __device__ __forceinline__ u8 *tbl_find(const Tbl &t, const u64 *k) {
 // entries the kernel evicted underneath it (stale-reverse path, bpf/nat44.c:871-876).
 __device__ __forceinline__ bool tbl_evict_near(const Tbl &t, u32 home, u64 *stats) {
     const u32 mode = t.lru & 0xff, ts_off = t.lru >> 8;
-    u8 *best = nullptr;
-    u64 best_ts = ~0ull, best_w = 0;
-    for (u32 j = 0; j < LRU_WINDOW; j++) {
-        u8 *s = t.slots + (size_t)((home + j) & t.mask) * t.slot_bytes;
-        const u64 w0 = *(volatile const u64 *)s;
-        if (w0 >= K_BUSY) continue;
-        const u64 ts = mode == LRU_TS ? *(volatile const u64 *)(s + ts_off) : j;
-        if (ts < best_ts) {
-            best_ts = ts;
-            best = s;
-            best_w = w0;
+    // Many workers insert at once when a batch brings more new flows than the table holds: a victim may be taken by
+    // somebody else between the scan and the CAS, and a window may hold no live entry at all.  Try again, moving on.
+    for (u32 attempt = 0; attempt < 16; attempt++) {
+        u8 *best = nullptr;
+        u64 best_ts = ~0ull, best_w = 0;
+        for (u32 j = 0; j < LRU_WINDOW; j++) {
+            u8 *s = t.slots + (size_t)((home + (attempt >> 1) * LRU_WINDOW + j) & t.mask) * t.slot_bytes;
+            const u64 w0 = *(volatile const u64 *)s;
+            if (w0 >= K_BUSY) continue;
+            const u64 ts = mode == LRU_TS ? *(volatile const u64 *)(s + ts_off) : j;
+            if (ts < best_ts) {
+                best_ts = ts;
+                best = s;
+                best_w = w0;
+            }
+        }
+        if (best && atomicCAS((u64 *)best, best_w, K_TOMB) == best_w) {
+            atomicSub(t.count, 1u);
+            if (stats) atomicAdd(&stats[ST_LRU_EVICT], 1ull);
+            return true;
         }
     }
-    if (!best || atomicCAS((u64 *)best, best_w, K_TOMB) != best_w) return false;
-    atomicSub(t.count, 1u);
-    if (stats) atomicAdd(&stats[ST_LRU_EVICT], 1ull);
-    return true;
+    return false;
 }
 
 // tbl_find that also reports where an insert of k would go: *ins = index of the first tombstone on the probe path,
@@ -379,7 +386,7 @@ template <int KW>
 __device__ __forceinline__ u8 *tbl_find_ins(const Tbl &t, const u64 *k, u32 *ins) {
     *ins = 0xFFFFFFFFu;
     if (k[0] >= K_BUSY) return nullptr;
-    u32 i = (u32)tbl_hash<KW>(k) & t.mask;
+    u32 i = (u32)tbl_hash<KW>(k) & t.home_mask;
     for (u32 probe = 0; probe <= t.mask; probe++) {
         u8 *s = tbl_slot(t, i);
         const u64 w0 = ld_vol64(s);
@@ -405,9 +412,8 @@ template <int KW>
 __device__ __forceinline__ u8 *tbl_claim_at(const Tbl &t, u32 ins, const u64 *k) {
     if (ins == 0xFFFFFFFFu) return nullptr;
     u8 *s = tbl_slot(t, ins);
-    const u64 w0 = ld_vol64(s);
-    if (w0 != K_EMPTY && w0 != K_TOMB) return nullptr;
-    if (atomicCAS((u64 *)s, w0, K_BUSY) != w0) return nullptr;
+    const u64 got = atomicCAS((u64 *)s, K_EMPTY, K_BUSY); // (the slot was EMPTY a moment ago, more often than a tombstone)
+    if (got != K_EMPTY && !(got == K_TOMB && atomicCAS((u64 *)s, K_TOMB, K_BUSY) == K_TOMB)) return nullptr;
 #pragma unroll
     for (int j = 1; j < KW; j++) ((u64 *)s)[j] = k[j];
     return s;
@@ -441,7 +447,7 @@ __device__ __forceinline__ u8 *tbl_find_or_claim(const Tbl &t, const u64 *k, boo
                                                  u64 *stats = nullptr) {
     *created = false;
     if (k[0] >= K_BUSY) return nullptr;
-    const u32 home = (u32)tbl_hash<KW>(k) & t.mask;
+    const u32 home = (u32)tbl_hash<KW>(k) & t.home_mask;
     u32 i = home;
     int tomb = -1;
     for (u32 probe = 0; probe <= t.mask;) {
@@ -483,7 +489,7 @@ __device__ __forceinline__ u8 *tbl_find_or_claim(const Tbl &t, const u64 *k, boo
             if (!pending && !RESERVED) atomicSub(t.count, 1u);
             if (tomb >= 0) {
                 tomb = -1;
-                i = (u32)tbl_hash<KW>(k) & t.mask;
+                i = (u32)tbl_hash<KW>(k) & t.home_mask;
                 probe = 0;
             }
             continue; // re-examine the same slot (it may now hold our key)
@@ -711,6 +717,8 @@ __device__ __forceinline__ void hdr_load_wide(Hdr64 &h, const u8 *p, u32 len, bo
 // MAC bytes [off, off+6) as the reference's big-endian u64 key
 // (bpf/antispoof.c:122-129, bpf/dhcp_fastpath.c:175-182).
 __device__ __forceinline__ u64 mac_key(const Hdr64 &h, u32 off) {
+    if (off == 6) // the source MAC: bytes 6-7 are the high half of word 1, bytes 8-11 word 2; two byte permutes
+        return ((u64)__byte_perm(h.w[1], 0, 0x4423) << 32) | __byte_perm(h.w[2], 0, 0x0123);
     u64 k = 0;
 #pragma unroll
     for (int i = 0; i < 6; i++) k = (k << 8) | h.b8(off + i);

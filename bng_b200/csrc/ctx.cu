@@ -139,9 +139,10 @@ int dev_alloc(bng_ctx *c, void **p, size_t bytes, int fill) {
 }
 
 int make_table(bng_ctx *c, Tbl *t, u32 key_size, u32 value_size, u32 voff, u32 max_entries, u32 vlayout = 0,
-               u32 slot_bytes = 0) {
-    u32 cap = pow2_at_least(std::max<u64>(64, (u64)max_entries * 2));
+               u32 slot_bytes = 0, u32 sparsity = 2) {
+    u32 cap = pow2_at_least(std::max<u64>(64, (u64)max_entries * sparsity));
     t->mask = cap - 1;
+    t->home_mask = cap - 1;
     t->voff = voff;
     t->key_size = key_size;
     t->value_size = value_size;
@@ -538,7 +539,10 @@ bng_ctx *bng_open(const bng_open_opts *o) {
     u32 max_vlan = std::min<u32>(100000u, std::max<u32>(max_subs, 64));
     DevCtx &d = c->dev;
 
-    OPEN_R(make_table(c, &d.bindings, 8, 24, 8, max_subs));
+    // subscriber_bindings: 32-byte slots, L2-resident; sparse (8 slots per subscriber) and probed a PAIR of slots at a
+    // time, so that a second, dependent probe — which stalls its whole warp — is needed by ~0.1 % of the lookups
+    OPEN_R(make_table(c, &d.bindings, 8, 24, 8, max_subs, 0, 0, 8));
+    d.bindings.home_mask = d.bindings.mask & ~1u;
     OPEN_R(make_table(c, &d.qos_eg, 4, 32, 16, max_subs, VL_QOS));
     OPEN_R(make_table(c, &d.qos_in, 4, 32, 16, max_subs, VL_QOS));
     OPEN_R(make_table(c, &d.sub_nat, 4, 64, 8, max_subs));
@@ -558,6 +562,7 @@ bng_ctx *bng_open(const bng_open_opts *o) {
     // subscriber directory: 16-byte slots, as many as the per-subscriber maps have, room for both maps' keys
     OPEN_R(make_table(c, &d.subdir, 4, 8, 8, max_subs, 0, 16));
     d.subdir.max_entries = std::min<u64>(2ull * max_subs, d.subdir.mask);
+    d.subdir.home_mask = d.subdir.mask & ~1u; // classify fetches the home pair (32 bytes) in one load
     OPEN_R(make_lpm(c, &d.ranges_v4, 256));
     OPEN_R(make_lpm(c, &d.priv_ranges, 64));
     OPEN_R(dev_alloc(c, (void **)&d.as_config, 16, 0));

@@ -55,35 +55,82 @@ __device__ __forceinline__ void grouped_select(const Grouped &g, const u32 *cnt,
 // ---------------------------------------------------------------------------
 // antispoof_ingress
 // ---------------------------------------------------------------------------
+// AS_UNROLL frames per thread and trip: their headers are requested together, then their binding probes, then the
+// verdicts: two dependent round trips serve AS_UNROLL frames instead of one.
+#ifndef AS_UNROLL
+#define AS_UNROLL 1
+#endif
+#ifndef AS_FULL_HEADER
+#define AS_FULL_HEADER 0
+#endif
 __global__ void __launch_bounds__(BLOCK) k_antispoof(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b) {
     __shared__ BlockStats bs;
     bstats_init(bs);
     u32 cfg = *(const u16 *)c.as_config;
-    u32 n_allowed = 0;
+    AsCnt cn = {0, 0, 0, 0};
     const u32 lane = threadIdx.x & 31;
     // warp-uniform trip count: the warp decides together whether its frames allow 256-bit loads
-    for (u32 base = blockIdx.x * BLOCK + (threadIdx.x & ~31u); base < b.n; base += gridDim.x * BLOCK) {
-        const u32 i = base + lane;
-        const bool act = i < b.n;
-        const u32 len = act ? frame_dlen(b, b.len[i]) : 0; // antispoof only bounds-checks: the bytes present
-        const u8 *p = act ? frame_ptr(b, i) : b.pkts;
-        Hdr64 h;
-        hdr_load_wide(h, p, len, __all_sync(0xffffffffu, !act || FRAME_WIDE_OK(b, p)));
-        u64 mk = mac_key(h, 6);
-        // first probe = the whole 32-byte slot (key + binding); later probes only on a collision
-        BindVal bv;
-        bv.has = false;
-        if (len >= 14) {
-            bv.s = ldg256(tbl_slot(c.bindings, tbl_hash<1>(&mk) & c.bindings.mask));
-            const u64 w0 = (u64)bv.s.w[0] | ((u64)bv.s.w[1] << 32);
-            if (w0 == mk)
-                bv.has = true;
-            else if (w0 != K_EMPTY)
-                bv = bind_load(tbl_find<1, false>(c.bindings, &mk));
+    for (u32 base = (blockIdx.x * BLOCK + (threadIdx.x & ~31u)) * AS_UNROLL; base < b.n; base += gridDim.x * BLOCK * AS_UNROLL) {
+        Hdr64 h[AS_UNROLL];
+        u32 len[AS_UNROLL], idx[AS_UNROLL];
+        bool act[AS_UNROLL];
+#pragma unroll
+        for (int u = 0; u < AS_UNROLL; u++) {
+            idx[u] = base + u * 32 + lane;
+            act[u] = idx[u] < b.n;
+            len[u] = act[u] ? frame_dlen(b, b.len[idx[u]]) : 0; // antispoof only bounds-checks: the bytes present
         }
-        if (act) b.verdict[i] = (u8)antispoof_eval(c, bs, h, len, i + b.base, frame_now(b, i), bv, cfg, n_allowed);
+        // antispoof_ingress reads the Ethernet header and the IPv4 source address (bytes 26-29): the first 32-byte
+        // sector of the frame.  Only an IPv6 frame needs more (its source address ends at byte 37).
+        const u8 *fp[AS_UNROLL];
+#pragma unroll
+        for (int u = 0; u < AS_UNROLL; u++) {
+            fp[u] = act[u] ? frame_ptr(b, idx[u]) : b.pkts;
+            const bool wide = __all_sync(0xffffffffu, !act[u] || FRAME_WIDE_OK(b, fp[u]));
+#if AS_FULL_HEADER
+            hdr_load_wide(h[u], fp[u], len[u] < 38 ? len[u] : 38, wide);
+#else
+            hdr_load_wide(h[u], fp[u], len[u] < 32 ? len[u] : 32, wide);
+#endif
+        }
+#if !AS_FULL_HEADER
+#pragma unroll
+        for (int u = 0; u < AS_UNROLL; u++)
+            if (len[u] > 32 && h[u].b16(12) == ETH_P_IPV6_LE) hdr_load(h[u], fp[u], len[u] < 48 ? len[u] : 48);
+#endif
+        // first probe = the home PAIR of 32-byte slots (key + binding each), both in flight at once; a third slot
+        // is needed by ~0.1 % of the lookups (the table is sparse)
+        BindVal bv[AS_UNROLL];
+        U256 s1[AS_UNROLL];
+        u64 mk[AS_UNROLL];
+        u32 hi[AS_UNROLL];
+#pragma unroll
+        for (int u = 0; u < AS_UNROLL; u++) {
+            mk[u] = mac_key(h[u], 6);
+            bv[u].has = false;
+            hi[u] = tbl_hash<1>(&mk[u]) & c.bindings.home_mask;
+            if (len[u] >= 14) {
+                bv[u].s = ldg256(tbl_slot(c.bindings, hi[u]));
+                s1[u] = ldg256(tbl_slot(c.bindings, hi[u] + 1));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < AS_UNROLL; u++) {
+            if (len[u] >= 14) {
+                const u64 w0 = (u64)bv[u].s.w[0] | ((u64)bv[u].s.w[1] << 32), w1 = (u64)s1[u].w[0] | ((u64)s1[u].w[1] << 32);
+                if (w0 == mk[u]) {
+                    bv[u].has = true;
+                } else if (w0 != K_EMPTY && w1 == mk[u]) {
+                    bv[u].has = true;
+                    bv[u].s = s1[u];
+                } else if (w0 != K_EMPTY && w1 != K_EMPTY) {
+                    bv[u] = bind_load(tbl_finish<1>(c.bindings, &mk[u], hi[u] + 1, w1, true));
+                }
+            }
+            if (act[u]) b.verdict[idx[u]] = (u8)antispoof_eval(c, h[u], len[u], idx[u] + b.base, frame_now(b, idx[u]), bv[u], cfg, cn);
+        }
     }
-    warp_stat_flush(bs, ST_AS_ALLOWED, n_allowed);
+    ascnt_flush(bs, cn);
     bstats_flush(bs, c.stats);
 }
 
@@ -526,7 +573,62 @@ __global__ void __launch_bounds__(BLOCK) k_heads(const __grid_constant__ Grouped
 // ---------------------------------------------------------------------------
 #define DROP_FLAG 0x40000000u // staged value: nat44_egress dropped the frame (port exhaustion): no QoS stage
 #define IDX_MASK 0x1FFFFFFFu
-#define RS_PER_THREAD 16
+#ifndef RS_PER_THREAD
+#define RS_PER_THREAD 8
+#endif
+
+// The NAT stage of one 32-frame chunk that holds new flows (mm: their lanes), kept out of line: the steady state
+// never calls it, and its registers (the frame header, three table probes, the translation) must not cost the
+// staging loop and the token-bucket walk theirs.  Returns true for a frame nat44_egress dropped (port exhaustion).
+// The sequential nat44_egress of one frame, out of line (rare; keeps its registers and code out of the walk).
+static __device__ __noinline__ int nat_egress_seq(const DevCtx &c, BlockStats &bs, const DevBatch &b, u8 *sub, u32 idx, u32 len, NatPend *pend,
+                                                 bool fresh) {
+    NatOut o = nat_egress_one<true>(c, bs, frame_ptr(b, idx), sub, len, frame_dlen(b, len), idx + b.base, frame_now(b, idx), pend, fresh,
+                                    b.nowv != nullptr);
+    return o.verdict;
+}
+
+__device__ __forceinline__ bool resolve_nat_chunk(const DevCtx &c, const DevBatch &b, BlockStats &bs, u8 *sub, u32 idx, u32 len,
+                                                      bool is_miss, bool fresh, u32 mm, u32 lane) {
+    NatPend pend;
+    // one nat_log_rb reservation for all new flows of this chunk (every one of them
+    // logs at most one record; a slot left unused is tagged invalid for the drain)
+    const EvRing &r = c.natlog_ev;
+    u32 nrec = __popc(mm), basepos = 0;
+    if (lane == 0) basepos = atomicAdd(r.count, nrec);
+    basepos = __shfl_sync(0xffffffffu, basepos, 0);
+    if (lane == 0 && basepos + nrec > r.cap) { // staging ring full: the tail of the chunk has no slot
+        u32 over = basepos >= r.cap ? nrec : basepos + nrec - r.cap;
+        atomicSub(r.count, over);
+        atomicAdd(&c.stats[r.lost_stat], (u64)over);
+    }
+    const u32 rpos = basepos + __popc(mm & ((1u << lane) - 1));
+    pend.log_rec = (is_miss && rpos < r.cap) ? r.buf + (size_t)rpos * r.rec_bytes : nullptr;
+    pend.logged = false;
+    if (pend.log_rec) *(uint2 *)(pend.log_rec + r.rec_bytes - 8) = make_uint2(idx + b.base, c.batch_seq);
+    bool dropped = false;
+    u32 todo = mm;
+    while (todo) {
+        // the longest prefix of the remaining new flows that does not interact: all at once
+        const u32 took = nat_chunk_coop(c, bs, b, sub, is_miss && ((todo >> lane) & 1), idx, len, pend, lane, fresh);
+        todo &= ~took;
+        if (lane == 0 && took) bstats_add(bs, ST_NAT_COOP, __popc(took));
+        if (!todo) break;
+        const u32 l = __ffs(todo) - 1; // ... then the frame that does, through the sequential code
+        todo &= todo - 1;
+        if (lane == l) {
+            if (nat_egress_seq(c, bs, b, sub, idx, len, &pend, fresh) == TC_SHOT) {
+                b.verdict[idx] = TC_SHOT;
+                dropped = true;
+            }
+            bstats_add(bs, ST_NAT_SEQ, 1);
+        }
+        __syncwarp();
+    }
+    if (is_miss && !pend.logged && pend.log_rec) // e.g. the session was created earlier in this batch
+        *(uint2 *)(pend.log_rec + r.rec_bytes - 8) = make_uint2(0xFFFFFFFFu, c.batch_seq);
+    return dropped;
+}
 
 // TC (pipeline_tc): the token bucket runs BEFORE the NAT stage: QoS walk first, then nat44_egress — hits and
 // new flows alike — for the frames it passed (DEFER_FLAG), with the parse-stage counters still to be counted.
@@ -548,9 +650,6 @@ __global__ void __launch_bounds__(TEAM, (TEAM == 128 ? 6 : RESOLVE_MINB)) k_reso
     const u32 m = cnt[CNT_M], nseg = cnt[CNT_NSEG];
     u32 pp = 0, dp = 0; // per-thread partial QoS counters
     u64 pb = 0, db = 0;
-    NatPend pend;
-    pend.log_rec = nullptr;
-    pend.logged = false;
     // groups are handed out dynamically (fat and thin groups mix: a static stride leaves blocks idle at the end)
     for (;;) {
         if (tid == 0) s_next = atomicAdd(&cnt[CNT_WORK], 1u);
@@ -619,48 +718,9 @@ __global__ void __launch_bounds__(TEAM, (TEAM == 128 ? 6 : RESOLVE_MINB)) k_reso
                                 bstats_add(bs, ST_NAT_PASSED, 1);
                         }
                     }
-                    u32 mm = __ballot_sync(0xffffffffu, is_miss);
-                    if (!mm) continue;
-                    const u32 idx = sv & IDX_MASK, len = valid ? s_len[j] : 0;
-                    // one nat_log_rb reservation for all new flows of this chunk (every one of them
-                    // logs at most one record; a slot left unused is tagged invalid for the drain)
-                    const EvRing &r = c.natlog_ev;
-                    u32 nrec = __popc(mm), basepos = 0;
-                    if (lane == 0) basepos = atomicAdd(r.count, nrec);
-                    basepos = __shfl_sync(0xffffffffu, basepos, 0);
-                    if (lane == 0 && basepos + nrec > r.cap) { // staging ring full: the tail of the chunk has no slot
-                        u32 over = basepos >= r.cap ? nrec : basepos + nrec - r.cap;
-                        atomicSub(r.count, over);
-                        atomicAdd(&c.stats[r.lost_stat], (u64)over);
-                    }
-                    const u32 rpos = basepos + __popc(mm & ((1u << lane) - 1));
-                    pend.log_rec = (is_miss && rpos < r.cap) ? r.buf + (size_t)rpos * r.rec_bytes : nullptr;
-                    pend.logged = false;
-                    if (pend.log_rec) *(uint2 *)(pend.log_rec + r.rec_bytes - 8) = make_uint2(idx + b.base, c.batch_seq);
-                    bool dropped = false;
-                    u32 todo = mm;
-                    while (todo) {
-                        // the longest prefix of the remaining new flows that does not interact: all at once
-                        const u32 took = nat_chunk_coop(c, bs, b, sub, is_miss && ((todo >> lane) & 1), idx, len, pend, lane, fresh);
-                        todo &= ~took;
-                        if (lane == 0 && took) bstats_add(bs, ST_NAT_COOP, __popc(took));
-                        if (!todo) break;
-                        const u32 l = __ffs(todo) - 1; // ... then the frame that does, through the sequential code
-                        todo &= todo - 1;
-                        if (lane == l) {
-                            NatOut o = nat_egress_one<true>(c, bs, frame_ptr(b, idx), sub, len, frame_dlen(b, len), idx + b.base, frame_now(b, idx), &pend, fresh,
-                                                                b.nowv != nullptr);
-                            if (o.verdict == TC_SHOT) {
-                                b.verdict[idx] = TC_SHOT;
-                                dropped = true;
-                            }
-                            bstats_add(bs, ST_NAT_SEQ, 1);
-                        }
-                        __syncwarp();
-                    }
-                    if (is_miss && !pend.logged && pend.log_rec) // e.g. the session was created earlier in this batch
-                        *(uint2 *)(pend.log_rec + r.rec_bytes - 8) = make_uint2(0xFFFFFFFFu, c.batch_seq);
-                    if (dropped) s_sv[j] = sv | DROP_FLAG;
+                    const u32 mm = __ballot_sync(0xffffffffu, is_miss);
+                    if (!mm) continue; // (the steady state: nothing to create, the call below never happens)
+                    if (resolve_nat_chunk(c, b, bs, sub, sv & IDX_MASK, valid ? s_len[j] : 0, is_miss, fresh, mm, lane)) s_sv[j] = sv | DROP_FLAG;
                 }
               }
             };

@@ -16,7 +16,14 @@
 #pragma once
 
 // Resident blocks per SM each instantiation is compiled for (registers: 65536 / (256 x blocks)).
-#define CLASSIFY_BPS(AS) ((AS) ? 4 : 5)
+#ifndef CLASSIFY_BLOCKS
+#define CLASSIFY_BLOCKS 4
+#endif
+#define CLASSIFY_BPS(AS) ((AS) ? CLASSIFY_BLOCKS : 5)
+// CLASSIFY_PAIR: fetch the home PAIR of slots of the bindings table / subscriber directory with the first probe
+#ifndef CLASSIFY_PAIR
+#define CLASSIFY_PAIR 1
+#endif
 
 // AS: run antispoof_ingress first; QOS: honour the qos_ingress bucket.  <false,false> is the
 // standalone nat44_egress classify.
@@ -37,7 +44,8 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
     const u32 as_cfg = st.as_cfg, nflags = st.nat_flags;
     const u32 lane = threadIdx.x & 31;
     const u32 epoch = c.epoch;
-    u32 n_allowed = 0, n_snat = 0, n_qpass = 0;
+    AsCnt cn = {0, 0, 0, 0};
+    u32 n_snat = 0, n_qpass = 0;
     u64 n_qbytes = 0;
     // warp-uniform trip count: every lane stays in the loop, inactive lanes are predicated off
     for (u32 base = blockIdx.x * BLOCK + (threadIdx.x & ~31u); base < b.n; base += gridDim.x * BLOCK) {
@@ -56,9 +64,9 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
         const u32 saddr = h.b32(26), daddr = h.b32(30), proto = h.b8(23);
         const bool ihl5 = (h.b8(14) & 0x0f) == 5;
         u64 mk = mac_key(h, 6);
-        const u32 bi = tbl_hash<1>(&mk) & c.bindings.mask;
+        const u32 bi = tbl_hash<1>(&mk) & c.bindings.home_mask;
         u64 sk = saddr;
-        const u32 di = tbl_hash<1>(&sk) & c.subdir.mask;
+        const u32 di = tbl_hash<1>(&sk) & c.subdir.home_mask; // even: the home pair is one aligned 32-byte load
         u16 sport, dport;
         if (proto == 1) {
             sport = h.b16(38); // echo id stands in for the source port (bpf/nat44.c:647-649)
@@ -72,16 +80,27 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
         key[1] = (u64)sport | ((u64)dport << 16) | ((u64)proto << 32);
         const u32 hi = tbl_hash<2>(key) & c.sessions.mask;
         // whole 32-byte sectors per probe: the binding slot, and the flow slot's key + translation + counters
+        // the L2-resident per-subscriber tables are probed a PAIR of slots at a time (a dependent second probe stalls
+        // the whole warp; with sparse tables a third slot is needed by ~0.1 % of the lookups)
         BindVal bv;
-        U256 s0;
-        bv.s.w[0] = bv.s.w[1] = s0.w[0] = s0.w[1] = 0xFFFFFFFFu; // K_EMPTY
+        U256 s0, b1, d0;
+        bv.s.w[0] = bv.s.w[1] = b1.w[0] = b1.w[1] = s0.w[0] = s0.w[1] = 0xFFFFFFFFu; // K_EMPTY
         s0.w[2] = s0.w[3] = 0;
-        ulonglong2 d0 = make_ulonglong2(K_EMPTY, ~0ull);
+#pragma unroll
+        for (int k = 0; k < 8; k++) d0.w[k] = 0xFFFFFFFFu;
         const u8 *bslot0 = tbl_slot(c.bindings, bi);
         u8 *sslot0 = tbl_slot(c.sessions, hi);
-        if (AS && dlen >= 14) bv.s = ldg256(bslot0);
+        if (AS && dlen >= 14) {
+            bv.s = ldg256(bslot0);
+            if (CLASSIFY_PAIR) b1 = ldg256(bslot0 + 32);
+        }
         if (ip4) {
-            d0 = *(const ulonglong2 *)tbl_slot(c.subdir, di);
+            if (CLASSIFY_PAIR) {
+                d0 = ldg256(tbl_slot(c.subdir, di));
+            } else {
+                const uint4 q = *(const uint4 *)tbl_slot(c.subdir, di);
+                d0.w[0] = q.x, d0.w[1] = q.y, d0.w[2] = q.z, d0.w[3] = q.w;
+            }
             s0 = ldg256<SES_POLICY>(sslot0);
         }
         const u64 kw0 = (u64)s0.w[0] | ((u64)s0.w[1] << 32), kw1 = (u64)s0.w[2] | ((u64)s0.w[3] << 32);
@@ -89,11 +108,27 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
         // ---- phase 2: antispoof_ingress ----
         int v = TC_OK;
         if (AS) {
-            const u8 *bind = dlen >= 14 ? tbl_finish<1>(c.bindings, &mk, bi, (u64)bv.s.w[0] | ((u64)bv.s.w[1] << 32), true) : nullptr;
+            const u8 *bind = nullptr;
+            if (dlen >= 14 && mk < K_BUSY) {
+                const u64 w0 = (u64)bv.s.w[0] | ((u64)bv.s.w[1] << 32), w1 = (u64)b1.w[0] | ((u64)b1.w[1] << 32);
+                if (w0 == mk) {
+                    bind = bslot0;
+                } else if (w0 != K_EMPTY) {
+                    if (!CLASSIFY_PAIR) {
+                        bind = tbl_finish<1>(c.bindings, &mk, bi, w0, true);
+                        if (bind) bv.s = ldg256(bind);
+                    } else if (w1 == mk) {
+                        bind = bslot0 + 32;
+                        bv.s = b1;
+                    } else if (w1 != K_EMPTY) {
+                        bind = tbl_finish<1>(c.bindings, &mk, bi + 1, w1, true); // third slot and beyond (rare)
+                        if (bind) bv.s = ldg256(bind);
+                    }
+                }
+            }
             __syncwarp();
             bv.has = bind != nullptr;
-            if (bind && bind != bslot0) bv.s = ldg256(bind); // found on a later probe
-            v = antispoof_eval(c, bs, h, dlen, i + b.base, now, bv, as_cfg, n_allowed);
+            v = antispoof_eval(c, h, dlen, i + b.base, now, bv, as_cfg, cn);
             __syncwarp();
         }
         const bool alive = act && v != TC_SHOT && ip4;
@@ -101,12 +136,21 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
         // ---- phase 3: the subscriber directory: does this address own a NAT block / a bucket? ----
         u32 nat_slot = DIR_NONE, qos_slot = DIR_NONE, dir_idx = 0;
         if (alive) {
-            const u8 *de = tbl_finish<1>(c.subdir, &sk, di, d0.x, true);
-            if (de) {
-                const u64 w = de == tbl_slot(c.subdir, di) ? d0.y : *(const u64 *)(de + 8);
-                nat_slot = (u32)w;
-                qos_slot = (u32)(w >> 32);
-                dir_idx = (u32)((de - c.subdir.slots) >> 4);
+            const u64 k0 = (u64)d0.w[0] | ((u64)d0.w[1] << 32), k1 = (u64)d0.w[4] | ((u64)d0.w[5] << 32);
+            if (k0 == sk) {
+                nat_slot = d0.w[2], qos_slot = d0.w[3], dir_idx = di;
+            } else if (k0 != K_EMPTY) {
+                if (CLASSIFY_PAIR && k1 == sk) {
+                    nat_slot = d0.w[6], qos_slot = d0.w[7], dir_idx = di + 1;
+                } else if (!CLASSIFY_PAIR || k1 != K_EMPTY) { // third slot and beyond (rare)
+                    const u8 *de = CLASSIFY_PAIR ? tbl_finish<1>(c.subdir, &sk, di + 1, k1, true) : tbl_finish<1>(c.subdir, &sk, di, k0, true);
+                    if (de) {
+                        const u64 w = *(const u64 *)(de + 8);
+                        nat_slot = (u32)w;
+                        qos_slot = (u32)(w >> 32);
+                        dir_idx = (u32)((de - c.subdir.slots) >> 4);
+                    }
+                }
             }
         }
         __syncwarp();
@@ -202,7 +246,7 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
             sval[i] = oval;
         }
     }
-    if (AS) warp_stat_flush(bs, ST_AS_ALLOWED, n_allowed);
+    if (AS) ascnt_flush(bs, cn);
     warp_stat_flush(bs, ST_NAT_SNAT, n_snat);
     if (QOS) {
         warp_stat_flush(bs, ST_QOS_PASS_PKTS, n_qpass);
