@@ -382,28 +382,44 @@ __device__ __forceinline__ bool tbl_evict_near(const Tbl &t, u32 home, u64 *stat
 // tbl_find that also reports where an insert of k would go: *ins = index of the first tombstone on the probe path,
 // else of the EMPTY slot that ended it (0xFFFFFFFF: none seen).  A following tbl_claim_at() then costs one CAS
 // instead of a second walk.  SKIP_BUSY semantics (ordered phase: a key has one owner).
+// The state words of PROBE_W consecutive slots are requested together: in a table that lives in DRAM every probe
+// step is a full memory round trip, and the longest chain among a warp's 32 lanes (3-4 steps at load 0.25) used to
+// cost that many round trips per lookup; bandwidth, in the ordered phase, is plentiful.
+#define PROBE_W 4
 template <int KW>
 __device__ __forceinline__ u8 *tbl_find_ins(const Tbl &t, const u64 *k, u32 *ins) {
     *ins = 0xFFFFFFFFu;
     if (k[0] >= K_BUSY) return nullptr;
     u32 i = (u32)tbl_hash<KW>(k) & t.home_mask;
-    for (u32 probe = 0; probe <= t.mask; probe++) {
-        u8 *s = tbl_slot(t, i);
-        const u64 w0 = ld_vol64(s);
-        if (w0 == K_EMPTY) {
-            if (*ins == 0xFFFFFFFFu) *ins = i;
-            return nullptr;
-        }
-        if (w0 == K_TOMB && *ins == 0xFFFFFFFFu) *ins = i;
-        if (w0 == k[0]) {
-            bool eq = true;
+    for (u32 probe = 0; probe <= t.mask; probe += PROBE_W) {
+        u64 w[PROBE_W];
 #pragma unroll
-            for (int j = 1; j < KW; j++) eq = eq && (((const u64 *)s)[j] == k[j]);
-            if (eq) return s;
+        for (int j = 0; j < PROBE_W; j++) w[j] = ld_vol64(tbl_slot(t, (i + j) & t.mask));
+#pragma unroll
+        for (int j = 0; j < PROBE_W; j++) {
+            const u32 si = (i + j) & t.mask;
+            if (w[j] == K_EMPTY) {
+                if (*ins == 0xFFFFFFFFu) *ins = si;
+                return nullptr;
+            }
+            if (w[j] == K_TOMB && *ins == 0xFFFFFFFFu) *ins = si;
+            if (w[j] == k[0]) {
+                u8 *s = tbl_slot(t, si);
+                bool eq = true;
+#pragma unroll
+                for (int q = 1; q < KW; q++) eq = eq && (((volatile const u64 *)s)[q] == k[q]);
+                if (eq) return s;
+            }
         }
-        i = (i + 1) & t.mask;
+        i = (i + PROBE_W) & t.mask;
     }
     return nullptr;
+}
+// Existence test with the same windowed probing (allocate_port_from_block()'s collision check, bpf/nat44.c:450-455)
+template <int KW>
+__device__ __forceinline__ bool tbl_has(const Tbl &t, const u64 *k) {
+    u32 ins;
+    return tbl_find_ins<KW>(t, k, &ins) != nullptr;
 }
 // Claims slot `ins` (as reported by tbl_find_ins for a key that was absent) for k: EMPTY/TOMB -> BUSY with one
 // CAS, key words 1.. written; nullptr when somebody else took the slot meanwhile (the caller then walks again
@@ -418,6 +434,26 @@ __device__ __forceinline__ u8 *tbl_claim_at(const Tbl &t, u32 ins, const u64 *k)
     for (int j = 1; j < KW; j++) ((u64 *)s)[j] = k[j];
     return s;
 }
+// The first step of three claims at once (the three atomics are independent: one round trip, not three).  got[] =
+// what each CAS returned; a slot index of 0xFFFFFFFF is skipped (got = K_BUSY: "not claimed").
+__device__ __forceinline__ void tbl_cas3(const Tbl &a, u32 ia, const Tbl &b, u32 ib, const Tbl &c, u32 ic, u64 got[3]) {
+    got[0] = got[1] = got[2] = K_BUSY;
+    if (ia != 0xFFFFFFFFu) got[0] = atomicCAS((u64 *)tbl_slot(a, ia), K_EMPTY, K_BUSY);
+    if (ib != 0xFFFFFFFFu) got[1] = atomicCAS((u64 *)tbl_slot(b, ib), K_EMPTY, K_BUSY);
+    if (ic != 0xFFFFFFFFu) got[2] = atomicCAS((u64 *)tbl_slot(c, ic), K_EMPTY, K_BUSY);
+}
+// ... and the rest of one of them: the slot is ours when the CAS found it EMPTY, or when it was a tombstone and a
+// second CAS takes that; key words 1.. are then written.
+template <int KW>
+__device__ __forceinline__ u8 *tbl_claim_finish(const Tbl &t, u32 ins, u64 got, const u64 *k) {
+    if (ins == 0xFFFFFFFFu) return nullptr;
+    u8 *s = tbl_slot(t, ins);
+    if (got != K_EMPTY && !(got == K_TOMB && atomicCAS((u64 *)s, K_TOMB, K_BUSY) == K_TOMB)) return nullptr;
+#pragma unroll
+    for (int j = 1; j < KW; j++) ((u64 *)s)[j] = k[j];
+    return s;
+}
+
 // Reserves room for n new entries: true when they fit under max_entries (t.count then includes them; give back
 // what is not used with tbl_unreserve).  One atomic for a whole chunk of inserts, and exact: the count can never
 // overshoot max_entries, however many warps insert at once.
@@ -450,9 +486,13 @@ __device__ __forceinline__ u8 *tbl_find_or_claim(const Tbl &t, const u64 *k, boo
     const u32 home = (u32)tbl_hash<KW>(k) & t.home_mask;
     u32 i = home;
     int tomb = -1;
-    for (u32 probe = 0; probe <= t.mask;) {
+    for (u32 probe = 0; probe <= t.mask + 1;) {
+        // one step past the last slot: the table has no EMPTY slot left on this path (churn turned them all into
+        // tombstones); the key is not there, and the first tombstone seen takes it
+        const bool wrapped = probe == t.mask + 1;
+        if (wrapped && tomb < 0) return nullptr;
         u8 *s = tbl_slot(t, i);
-        u64 w0 = ld_vol64(s);
+        u64 w0 = wrapped ? K_EMPTY : ld_vol64(s);
         while (!SKIP_BUSY && w0 == K_BUSY) {
             __nanosleep(32);
             w0 = ld_vol64(s);
@@ -487,9 +527,9 @@ __device__ __forceinline__ u8 *tbl_find_or_claim(const Tbl &t, const u64 *k, boo
             }
             // lost the race for that slot: undo the reservation and look again
             if (!pending && !RESERVED) atomicSub(t.count, 1u);
-            if (tomb >= 0) {
+            if (tomb >= 0 || wrapped) {
                 tomb = -1;
-                i = (u32)tbl_hash<KW>(k) & t.home_mask;
+                i = home;
                 probe = 0;
             }
             continue; // re-examine the same slot (it may now hold our key)

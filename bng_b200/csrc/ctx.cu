@@ -85,6 +85,7 @@ struct bng_ctx {
     std::vector<Staged> staged;
     u64 staged_total = 0, staged_errors = 0, staged_flushes = 0;
     u64 rebuilds = 0; // flow-table rebuilds (tombstone compaction) so far
+    u64 evict_at_rebuild = 0; // ST_LRU_EVICT when the flow tables were last rebuilt
     bool small_dirty = false; // a map feeding the SmallTabs image changed since the image was built
     // grow-only scratch of map dumps (no cudaMalloc / cudaFree per call)
     u8 *dump_k = nullptr, *dump_v = nullptr;
@@ -539,9 +540,9 @@ bng_ctx *bng_open(const bng_open_opts *o) {
     u32 max_vlan = std::min<u32>(100000u, std::max<u32>(max_subs, 64));
     DevCtx &d = c->dev;
 
-    // subscriber_bindings: 32-byte slots, L2-resident; sparse (8 slots per subscriber) and probed a PAIR of slots at a
-    // time, so that a second, dependent probe — which stalls its whole warp — is needed by ~0.1 % of the lookups
-    OPEN_R(make_table(c, &d.bindings, 8, 24, 8, max_subs, 0, 0, 8));
+    // subscriber_bindings: 32-byte slots, L2-resident; k_antispoof probes the home PAIR of slots at once, so that a
+    // second, dependent probe — which stalls its whole warp — is rarely needed
+    OPEN_R(make_table(c, &d.bindings, 8, 24, 8, max_subs, 0, 0, 4));
     d.bindings.home_mask = d.bindings.mask & ~1u;
     OPEN_R(make_table(c, &d.qos_eg, 4, 32, 16, max_subs, VL_QOS));
     OPEN_R(make_table(c, &d.qos_in, 4, 32, 16, max_subs, VL_QOS));
@@ -997,6 +998,7 @@ static int dispatch(bng_ctx *c, int prog, const DevBatch &b) {
 // so PCIe reads, PCIe writes and compute of successive chunks overlap, and only the bytes a
 // program can touch ever cross the bus.
 #define ZC_CHUNK (c->zc_chunk)
+static int maybe_compact_locked(bng_ctx *c);
 static int run_host_zero_copy(bng_ctx *c, int prog, bng_batch *bb, u8 *arena_dev) {
     // Bytes of a frame a program can touch (hostio.cu): 96 for the TC programs (Ethernet + IPv4 with options + 20
     // bytes of L4), 448 for dhcp_fastpath_prog.  Frames that ARE a fixed slot no larger than that (64-byte
@@ -1091,7 +1093,7 @@ static int run_host_zero_copy(bng_ctx *c, int prog, bng_batch *bb, u8 *arena_dev
     CU(c, cudaStreamSynchronize(c->s_out));
     CU(c, cudaStreamSynchronize(sc));
     prof_collect(c->L);
-    return 0;
+    return maybe_compact_locked(c);
 }
 
 int bng_prog_run(bng_ctx *c, int prog, bng_batch *bb) {
@@ -1183,7 +1185,7 @@ int bng_prog_run(bng_ctx *c, int prog, bng_batch *bb) {
     if (bb->priority) CU(c, cudaMemcpyAsync(bb->priority, c->hb_prio, (size_t)bb->n * 4, cudaMemcpyDeviceToHost, st));
     CU(c, cudaStreamSynchronize(st));
     prof_collect(c->L);
-    return 0;
+    return maybe_compact_locked(c);
 }
 
 int bng_sync(bng_ctx *c) {
@@ -1193,6 +1195,7 @@ int bng_sync(bng_ctx *c) {
     int r = flush_staged_locked(c, -1);
     CU(c, cudaStreamSynchronize(c->L.stream));
     prof_collect(c->L);
+    if (!r) r = maybe_compact_locked(c);
     return r;
 }
 
@@ -1307,6 +1310,22 @@ static int table_rebuild_locked(bng_ctx *c, Tbl *t) {
     t->slots = nw.slots;
     c->rebuilds++;
     return 0;
+}
+
+// Tombstone compaction between batches: every eviction from a full LRU table leaves a tombstone, and a table that
+// churns at capacity runs out of EMPTY slots (every lookup of an absent key then walks the whole table).  Called
+// where the stream is synchronised anyway; rebuilds the three flow tables once the evictions since the last rebuild
+// exceed a quarter of nat_sessions' slots.
+static int maybe_compact_locked(bng_ctx *c) {
+    u64 ev = 0;
+    CU(c, cudaMemcpyAsync(&ev, c->dev.stats + ST_LRU_EVICT, 8, cudaMemcpyDeviceToHost, c->L.stream));
+    CU(c, cudaStreamSynchronize(c->L.stream));
+    if (ev - c->evict_at_rebuild <= (c->dev.sessions.mask + 1) / 4) return 0;
+    c->evict_at_rebuild = ev;
+    int r;
+    if ((r = table_rebuild_locked(c, &c->dev.sessions)) != 0) return r;
+    if ((r = table_rebuild_locked(c, &c->dev.reverse)) != 0) return r;
+    return table_rebuild_locked(c, &c->dev.eim);
 }
 
 // Session expiry sweep (sweep.cu): removes every nat_sessions entry idle for longer than the timeout of its

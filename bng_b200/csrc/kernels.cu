@@ -37,6 +37,14 @@
 // device-side counters (Scratch::counters)
 enum { CNT_M = 0, CNT_NSEG = 1, CNT_DEFERRED = 2, CNT_MAXKEY = 3, CNT_WORK = 4 };
 
+// The group-by's device counters and per-pass digit totals start every batch at zero: the classify kernel that feeds
+// it clears them (block 0) instead of two memset launches ahead of it — nothing reads them before the kernel ends.
+__device__ __forceinline__ void scratch_reset(u32 *cnt, u32 *T) {
+    if (blockIdx.x == 0) {
+        for (u32 i = threadIdx.x; i < 16 + 4 * 256; i += blockDim.x) (i < 16 ? cnt[i] : T[i - 16]) = 0;
+    }
+}
+
 // The grouped (key, value) arrays live in one of two ping-pong buffers depending on how many radix
 // passes actually ran: passes whose digit is zero for every key of the batch (largest key < 2^(8p))
 // are skipped on the device, so the consumers pick the buffer from the device-side maximum.
@@ -138,8 +146,9 @@ __global__ void __launch_bounds__(BLOCK) k_antispoof(const __grid_constant__ Dev
 // qos_egress_prog / qos_ingress_prog: classify
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(BLOCK)
-    k_qos_classify(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b, int egress, u32 *skey, u32 *sval) {
+    k_qos_classify(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b, int egress, u32 *skey, u32 *sval, u32 *cnt, u32 *T) {
     __shared__ BlockStats bs;
+    scratch_reset(cnt, T);
     bstats_init(bs);
     const Tbl &t = egress ? c.qos_eg : c.qos_in;
     for (u32 i = blockIdx.x * BLOCK + threadIdx.x; i < b.n; i += gridDim.x * BLOCK) {
@@ -821,6 +830,8 @@ static int bits_for(u64 max_key_exclusive) {
     return b;
 }
 
+static inline u32 *sort_T(Launcher &L) { return (u32 *)L.s.cub_tmp + 256 * 1024; } // per-pass digit totals (group_by_key)
+
 size_t sort_temp_bytes(u32 n) { // histogram matrix: 256 digits x blocks
     (void)n;
     return (size_t)(256 * 1024 + 4 * 256 + 1024) * sizeof(u32); // H, per-pass digit totals, per-block "any key" flags
@@ -880,9 +891,7 @@ static cudaError_t group_by_key(Launcher &L, u32 n, u64 key_space, Grouped *out)
     int rsb = L.num_sms * RS_BLOCKS_PER_SM;
     if (rsb > 1024) rsb = 1024;
     u32 *H = (u32 *)s.cub_tmp, *T = H + 256 * 1024, *ANYV = T + 4 * 256;
-    cudaError_t e = cudaMemsetAsync(s.counters, 0, 64, L.stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(T, 0, 4 * 256 * sizeof(u32), L.stream);
-    if (e != cudaSuccess) return e;
+    cudaError_t e = cudaSuccess; // (counters and T were cleared by the classify kernel: scratch_reset)
     u32 *ik = s.key_a, *iv = s.val_a, *ok = s.key_b, *ov = s.val_b;
     prof_begin(L, "group_by_key");
     for (int p = 0; p < passes; p++) {
@@ -934,7 +943,7 @@ cudaError_t run_antispoof(Launcher &L, const DevCtx &c, const DevBatch &b) {
 }
 
 cudaError_t run_qos(Launcher &L, const DevCtx &c, const DevBatch &b, bool egress) {
-    LAUNCH(k_qos_classify, b.n, 8, c, b, egress ? 1 : 0, L.s.key_a, L.s.val_a);
+    LAUNCH(k_qos_classify, b.n, 8, c, b, egress ? 1 : 0, L.s.key_a, L.s.val_a, L.s.counters, sort_T(L));
     const Tbl &t = egress ? c.qos_eg : c.qos_in;
     Grouped g;
     cudaError_t e = group_by_key(L, b.n, (u64)t.mask + 1, &g);
@@ -947,7 +956,7 @@ cudaError_t run_qos(Launcher &L, const DevCtx &c, const DevBatch &b, bool egress
 }
 
 cudaError_t run_nat_egress(Launcher &L, const DevCtx &c, const DevBatch &b) {
-    LAUNCH((k_pipe_classify<false, false>), b.n, CLASSIFY_BPS(false), c, b, L.s.key_a, L.s.val_a);
+    LAUNCH((k_pipe_classify<false, false>), b.n, CLASSIFY_BPS(false), c, b, L.s.key_a, L.s.val_a, L.s.counters, sort_T(L));
     Grouped g;
     cudaError_t e = group_by_key(L, b.n, (u64)c.subdir.mask + 1, &g);
     if (e != cudaSuccess) return e;
@@ -966,7 +975,7 @@ cudaError_t run_nat_hairpin_xdp(Launcher &L, const DevCtx &c, const DevBatch &b)
 }
 
 cudaError_t run_pipeline_up(Launcher &L, const DevCtx &c, const DevBatch &b) {
-    LAUNCH((k_pipe_classify<true, true>), b.n, CLASSIFY_BPS(true), c, b, L.s.key_a, L.s.val_a);
+    LAUNCH((k_pipe_classify<true, true>), b.n, CLASSIFY_BPS(true), c, b, L.s.key_a, L.s.val_a, L.s.counters, sort_T(L));
     Grouped g;
     cudaError_t e = group_by_key(L, b.n, (u64)c.subdir.mask + 1, &g);
     if (e != cudaSuccess) return e;
@@ -975,7 +984,7 @@ cudaError_t run_pipeline_up(Launcher &L, const DevCtx &c, const DevBatch &b) {
 }
 
 cudaError_t run_pipeline_tc(Launcher &L, const DevCtx &c, const DevBatch &b) {
-    LAUNCH((k_pipe_classify<true, true, true>), b.n, CLASSIFY_BPS(true), c, b, L.s.key_a, L.s.val_a);
+    LAUNCH((k_pipe_classify<true, true, true>), b.n, CLASSIFY_BPS(true), c, b, L.s.key_a, L.s.val_a, L.s.counters, sort_T(L));
     Grouped g;
     cudaError_t e = group_by_key(L, b.n, (u64)c.subdir.mask + 1, &g);
     if (e != cudaSuccess) return e;

@@ -22,7 +22,7 @@
 #define CLASSIFY_BPS(AS) ((AS) ? CLASSIFY_BLOCKS : 5)
 // CLASSIFY_PAIR: fetch the home PAIR of slots of the bindings table / subscriber directory with the first probe
 #ifndef CLASSIFY_PAIR
-#define CLASSIFY_PAIR 1
+#define CLASSIFY_PAIR 0 // measured (profiles/r02_notes.md): the 16 extra registers spill, 0.373 -> 0.425 ms
 #endif
 
 // AS: run antispoof_ingress first; QOS: honour the qos_ingress bucket.  <false,false> is the
@@ -34,8 +34,9 @@
 // phase with DEFER_FLAG and nat44_egress runs there, after token_bucket_check().
 template <bool AS, bool QOS, bool TC = false>
 __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
-    k_pipe_classify(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b, u32 *skey, u32 *sval) {
+    k_pipe_classify(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b, u32 *skey, u32 *sval, u32 *cnt, u32 *T) {
     __shared__ SmallTabs st;
+    scratch_reset(cnt, T);
     __shared__ BlockStats bs;
     __shared__ u64 bar;
     smem_stage_begin(&st, c.small, (u32)sizeof(SmallTabs), &bar);

@@ -609,7 +609,7 @@ __device__ __forceinline__ u32 nat_chunk_coop(const DevCtx &c, BlockStats &bs, c
     // second round of probes, in flight together: is the proposed port taken (:450-459)?  does the reverse key exist
     // already (:740 is BPF_ANY: then it is overwritten in place)?
     const u64 ck = (u64)f.saddr | ((u64)port << 32) | ((u64)f.proto << 48);
-    if (alloc && !clash && !all_clash && tbl_find<1, true, true>(c.eim, &ck)) clash = true;
+    if (alloc && !clash && !all_clash && tbl_has<1>(c.eim, &ck)) clash = true;
     if (create && !clash && !all_clash) rev = tbl_find_ins<2>(c.reverse, rk, &rev_ins);
     if (nalloc && eim_on) { // ... or about to be taken: an endpoint an earlier lane creates whose network-order port reads as my candidate
         for (u32 j = 0; j < 32; j++) {
@@ -676,11 +676,14 @@ __device__ __forceinline__ u32 nat_chunk_coop(const DevCtx &c, BlockStats &bs, c
             // the three claims first, so that their atomics are in flight together
             bool created;
             u8 *nm = nullptr, *ns, *rs = rev;
-            if (!m && eim_on) nm = tbl_claim_at<1>(c.eim, eim_ins, &ek);
-            ns = tbl_claim_at<2>(c.sessions, ses_ins, key);
+            u64 got[3];
+            const u32 e_i = (!m && eim_on) ? eim_ins : 0xFFFFFFFFu, r_i = rs ? 0xFFFFFFFFu : rev_ins;
+            tbl_cas3(c.eim, e_i, c.sessions, ses_ins, c.reverse, r_i, got);
+            nm = tbl_claim_finish<1>(c.eim, e_i, got[0], &ek);
+            ns = tbl_claim_finish<2>(c.sessions, ses_ins, got[1], key);
             bool rs_new = false;
             if (!rs) {
-                rs = tbl_claim_at<2>(c.reverse, rev_ins, rk);
+                rs = tbl_claim_finish<2>(c.reverse, r_i, got[2], rk);
                 rs_new = rs != nullptr;
             }
             // (a slot another subscriber's worker took in the meantime: walk again)
