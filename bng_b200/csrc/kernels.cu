@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(BLOCK) k_antispoof(const __grid_constant__ Dev
     __shared__ BlockStats bs;
     bstats_init(bs);
     u32 cfg = *(const u16 *)c.as_config;
-    AsCnt cn = {0, 0, 0, 0};
+    AsCnt cn = {0, 0};
     const u32 lane = threadIdx.x & 31;
     // warp-uniform trip count: the warp decides together whether its frames allow 256-bit loads
     for (u32 base = (blockIdx.x * BLOCK + (threadIdx.x & ~31u)) * AS_UNROLL; base < b.n; base += gridDim.x * BLOCK * AS_UNROLL) {
@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(BLOCK) k_antispoof(const __grid_constant__ Dev
             }
             if (act[u]) b.verdict[idx[u]] = (u8)antispoof_eval(c, h[u], len[u], idx[u] + b.base, frame_now(b, idx[u]), bv[u], cfg, cn);
         }
+        ascnt_spill(bs, cn);
     }
     ascnt_flush(bs, cn);
     bstats_flush(bs, c.stats);

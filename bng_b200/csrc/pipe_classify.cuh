@@ -42,19 +42,18 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
     smem_stage_begin(&st, c.small, (u32)sizeof(SmallTabs), &bar);
     bstats_init(bs);
     smem_stage_wait(&bar);
-    const u32 as_cfg = st.as_cfg, nflags = st.nat_flags;
     const u32 lane = threadIdx.x & 31;
-    const u32 epoch = c.epoch;
-    AsCnt cn = {0, 0, 0, 0};
-    u32 n_snat = 0, n_qpass = 0;
-    u64 n_qbytes = 0;
+#define as_cfg (st.as_cfg) /* read from shared memory / the constant bank where used: no live registers */
+#define nflags (st.nat_flags)
+#define epoch (c.epoch)
+    AsCnt cn = {0, 0};
+    u32 n_snat = 0, n_qpass = 0, n_qbytes = 0; // (bytes in 32 bits: flushed per trip well before they could wrap)
     // warp-uniform trip count: every lane stays in the loop, inactive lanes are predicated off
     for (u32 base = blockIdx.x * BLOCK + (threadIdx.x & ~31u); base < b.n; base += gridDim.x * BLOCK) {
         const u32 i = base + lane;
         const bool act = i < b.n;
         const u32 len = act ? b.len[i] : 0;      // skb->len: byte counters, token bucket
         const u32 dlen = frame_dlen(b, len);     // data_end - data: every bounds check
-        const u64 now = act ? frame_now(b, i) : 0; // bpf_ktime_get_ns() while this frame runs
         u8 *p = act ? frame_ptr(b, i) : b.pkts;
         const bool wide = __all_sync(0xffffffffu, !act || FRAME_WIDE_OK(b, p));
         Hdr64 h;
@@ -129,7 +128,7 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
             }
             __syncwarp();
             bv.has = bind != nullptr;
-            v = antispoof_eval(c, h, dlen, i + b.base, now, bv, as_cfg, cn);
+            v = antispoof_eval(c, h, dlen, i + b.base, frame_now(b, i), bv, as_cfg, cn); // (the clock is read where it is used: no live register)
             __syncwarp();
         }
         const bool alive = act && v != TC_SHOT && ip4;
@@ -167,7 +166,7 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
             if (ax >= 0) { // ALG traffic goes to userspace untranslated (:615-642)
                 bstats_add(bs, ST_NAT_ALG, 1);
                 const u8 *sub = tbl_slot(c.sub_nat, nat_slot);
-                nat_log(c, i + b.base, now, 7, *(const u32 *)(sub + 32), saddr, 0, sport, 0, daddr, dport, (u8)proto, st.alg_type[ax]);
+                nat_log(c, i + b.base, frame_now(b, i), 7, *(const u32 *)(sub + 32), saddr, 0, sport, 0, daddr, dport, (u8)proto, st.alg_type[ax]);
                 go = false;
             }
         }
@@ -185,7 +184,7 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
             if (ses != sslot0) tr = *(const uint2 *)(ses + SES_NAT_IP); // found on a later probe
             const u32 nat_ip = tr.x;
             const u16 nat_port = (u16)tr.y;
-            ses_touch(ses, now, tr.y >> 16, epoch, b.nowv != nullptr);
+            ses_touch(ses, frame_now(b, i), tr.y >> 16, epoch, b.nowv != nullptr);
             ses_count(ses, SES_OUT_LO, len);
             h.s32(26, nat_ip);
             h.s16(24, csum_upd32(h.b16(24), saddr, nat_ip));
@@ -223,7 +222,7 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
 
         // ---- IPv4 options: fields are not at fixed offsets, take the generic path (rare) ----
         if (has_sub && !ihl5) {
-            NatOut o = nat_egress_one<false>(c, bs, p, tbl_slot(c.sub_nat, nat_slot), len, dlen, i + b.base, now, nullptr, true, b.nowv != nullptr);
+            NatOut o = nat_egress_one<false>(c, bs, p, tbl_slot(c.sub_nat, nat_slot), len, dlen, i + b.base, frame_now(b, i), nullptr, true, b.nowv != nullptr);
             v = o.verdict;
             miss = o.miss;
         }
@@ -246,12 +245,20 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
             skey[i] = okey;
             sval[i] = oval;
         }
+        if (AS) ascnt_spill(bs, cn);
+        if (QOS && __any_sync(0xffffffffu, n_qbytes >= 0x04000000u)) {
+            warp_stat_flush(bs, ST_QOS_PASS_BYTES, n_qbytes);
+            n_qbytes = 0;
+        }
     }
+#undef as_cfg
+#undef nflags
+#undef epoch
     if (AS) ascnt_flush(bs, cn);
     warp_stat_flush(bs, ST_NAT_SNAT, n_snat);
     if (QOS) {
         warp_stat_flush(bs, ST_QOS_PASS_PKTS, n_qpass);
-        warp_stat_flush64(bs, ST_QOS_PASS_BYTES, n_qbytes);
+        warp_stat_flush(bs, ST_QOS_PASS_BYTES, n_qbytes);
     }
     bstats_flush(bs, c.stats);
 }

@@ -28,14 +28,32 @@
 // antispoof_stats of one thread, in registers: flushed once per thread at the end of the kernel (a 64-bit shared
 // atomic per dropped frame was 17 % of k_antispoof's stall samples: it compiles to a CAS loop with lane election)
 struct AsCnt {
-    u32 allowed, logged, v4, v6; // packets_dropped = v4 + v6
+    u32 allowed;
+    u32 rare; // logged | v4 violations << 10 | v6 violations << 20: a thread sees at most a few hundred frames per launch
 };
+#define ASC_LOGGED 1u
+#define ASC_V4 (1u << 10)
+#define ASC_V6 (1u << 20)
 __device__ __forceinline__ void ascnt_flush(BlockStats &bs, const AsCnt &n) { // all 32 lanes
+    const u32 lg = n.rare & 1023u, v4 = (n.rare >> 10) & 1023u, v6 = n.rare >> 20;
     warp_stat_flush(bs, ST_AS_ALLOWED, n.allowed);
-    warp_stat_flush(bs, ST_AS_LOGGED, n.logged);
-    warp_stat_flush(bs, ST_AS_V4_VIOL, n.v4);
-    warp_stat_flush(bs, ST_AS_V6_VIOL, n.v6);
-    warp_stat_flush(bs, ST_AS_DROPPED, n.v4 + n.v6);
+    warp_stat_flush(bs, ST_AS_LOGGED, lg);
+    warp_stat_flush(bs, ST_AS_V4_VIOL, v4);
+    warp_stat_flush(bs, ST_AS_V6_VIOL, v6);
+    warp_stat_flush(bs, ST_AS_DROPPED, v4 + v6);
+}
+// ... which bounds the batch: 1023 trips of the persistent grid (148 x 4 x 256 threads) = 155 M frames
+__device__ __forceinline__ void ascnt_spill(BlockStats &bs, AsCnt &n) { // called once per trip; keeps the 10-bit fields from wrapping
+    if (__any_sync(0xffffffffu, ((n.rare & 1023u) | ((n.rare >> 10) & 1023u) | (n.rare >> 20)) >= 1000u)) {
+        AsCnt t = n;
+        t.allowed = 0;
+        const u32 lg = t.rare & 1023u, v4 = (t.rare >> 10) & 1023u, v6 = t.rare >> 20;
+        warp_stat_flush(bs, ST_AS_LOGGED, lg);
+        warp_stat_flush(bs, ST_AS_V4_VIOL, v4);
+        warp_stat_flush(bs, ST_AS_V6_VIOL, v6);
+        warp_stat_flush(bs, ST_AS_DROPPED, v4 + v6);
+        n.rare = 0;
+    }
 }
 
 __device__ __forceinline__ void spoof_log(const DevCtx &c, AsCnt &cn, u32 idx, u64 now, const Hdr64 &h,
@@ -52,7 +70,7 @@ __device__ __forceinline__ void spoof_log(const DevCtx &c, AsCnt &cn, u32 idx, u
         ((uint4 *)r)[2] = z;
         ((uint2 *)r)[6] = make_uint2(0, 0);
     }
-    cn.logged++;
+    cn.rare += ASC_LOGGED;
 }
 
 // `bind` is the subscriber_bindings slot of the frame's source MAC (or null),
@@ -101,7 +119,7 @@ __device__ __forceinline__ int antispoof_eval(const DevCtx &c, const Hdr64 &h, u
                 n_allowed++;
                 return TC_OK;
             }
-            cn.v4++;
+            cn.rare += ASC_V4;
             return TC_SHOT;
         }
         n_allowed++;
@@ -120,7 +138,7 @@ __device__ __forceinline__ int antispoof_eval(const DevCtx &c, const Hdr64 &h, u
         }
         if (!allowed && mode != 3) {
             if (log_viol) spoof_log(c, cn, idx, now, h, 0, 0, true);
-            cn.v6++;
+            cn.rare += ASC_V6;
             return TC_SHOT;
         }
         n_allowed++;
