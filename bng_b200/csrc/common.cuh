@@ -468,6 +468,39 @@ __device__ __forceinline__ void tbl_unreserve(const Tbl &t, u32 n) {
     if (n) atomicSub(t.count, n);
 }
 
+// tbl_find for code that goes on for hundreds of instructions after the lookup: the lanes that entered together
+// leave together (lanes whose probe ended wait for the longest chain), so what follows runs once for the warp, not
+// once per distinct chain length — without it the compiler's tail duplication made dhcp_fastpath execute its body
+// 2.4 times per warp with 13 lanes active (ncu source view, profiles/r02_notes.md).  Read-only tables.
+template <int KW>
+__device__ __forceinline__ const u8 *tbl_find_conv(const Tbl &t, const u64 *k) {
+    const unsigned m = __activemask();
+    const u8 *res = nullptr;
+    bool done = k[0] >= K_BUSY;
+    u32 i = (u32)tbl_hash<KW>(k) & t.home_mask, left = t.mask + 1;
+    while (__any_sync(m, !done)) {
+        if (!done) {
+            const u8 *s = tbl_slot(t, i);
+            const u64 w0 = *(const u64 *)s;
+            if (w0 == K_EMPTY) {
+                done = true;
+            } else {
+                bool eq = w0 == k[0];
+#pragma unroll
+                for (int j = 1; j < KW; j++) eq = eq && (((const u64 *)s)[j] == k[j]);
+                if (eq) {
+                    res = s;
+                    done = true;
+                } else {
+                    i = (i + 1) & t.mask;
+                    done = --left == 0;
+                }
+            }
+        }
+    }
+    return res;
+}
+
 // Find-or-claim.  Returns the slot; *created says whether this call claimed
 // it.  A claimed slot is left in the K_BUSY state with key words 1.. written:
 // the caller fills the value and then calls tbl_publish().  Returns nullptr

@@ -416,6 +416,14 @@ void *bng_host_alloc(size_t bytes) {
             madvise(p, size, MADV_HUGEPAGE);
 #endif
             for (size_t o = 0; o < size; o += 4096) p[o] = 0; // first touch on the caller's (NUMA-bound) thread
+            // Whether the fault path found free 2 MB pages is luck (the same process was seen with one arena in huge
+            // pages and the next in 4 KB pages: 320 vs 65 Mpps end to end).  MADV_COLLAPSE (Linux 6.1+) collapses
+            // the range synchronously, compacting memory if it has to; best effort, errors ignored.
+#ifndef MADV_COLLAPSE
+#define MADV_COLLAPSE 25
+#endif
+            for (size_t o = 0; o < size; o += (size_t)64 << 20)
+                madvise(p + o, std::min<size_t>((size_t)64 << 20, size - o), MADV_COLLAPSE);
             if (cudaHostRegister(p, size, cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess) {
                 std::lock_guard<std::mutex> g(g_arena_mu);
                 g_arenas.push_back({p, HostArena{base, size + huge, size}});

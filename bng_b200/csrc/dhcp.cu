@@ -102,7 +102,7 @@ __device__ __forceinline__ int dhcp_one(const DevCtx &c, BlockStats &bs, u8 *p, 
     const u8 *a = nullptr; // -> pool_assignment
     if (tagged) {
         u64 vk = (u64)(vlan_id | (inner_id << 16));
-        const u8 *s = tbl_find<1, false>(c.vlan_pools, &vk);
+        const u8 *s = tbl_find_conv<1>(c.vlan_pools, &vk);
         if (s) a = s + c.vlan_pools.voff;
     }
     if (!a && opts + 64 <= dlen) { // extract_circuit_id_fixed(), :267-323
@@ -137,7 +137,7 @@ __device__ __forceinline__ int dhcp_one(const DevCtx &c, BlockStats &bs, u8 *p, 
         if (cid_at >= 0) {
             u64 ck[4] = {0, 0, 0, 0};
             for (u32 k = 0; k < cid_len; k++) ck[k >> 3] |= (u64)o[cid_at + k] << ((k & 7) * 8);
-            const u8 *s = tbl_find<4, false>(c.cid_subs, ck);
+            const u8 *s = tbl_find_conv<4>(c.cid_subs, ck);
             if (s) {
                 a = s + c.cid_subs.voff;
                 bstats_add(bs, ST_DHCP_O82_PRESENT, 1);
@@ -148,7 +148,7 @@ __device__ __forceinline__ int dhcp_one(const DevCtx &c, BlockStats &bs, u8 *p, 
         u64 mk = 0;
 #pragma unroll
         for (int k = 0; k < 6; k++) mk = (mk << 8) | p[dh + 28 + k]; // chaddr
-        const u8 *s = tbl_find<1, false>(c.sub_pools, &mk);
+        const u8 *s = tbl_find_conv<1>(c.sub_pools, &mk);
         if (s) a = s + c.sub_pools.voff;
     }
     if (!a) {
@@ -163,7 +163,7 @@ __device__ __forceinline__ int dhcp_one(const DevCtx &c, BlockStats &bs, u8 *p, 
         return XDP_PASS_;
     }
     u64 pk = *(const u32 *)a;
-    const u8 *pool = tbl_find<1, false>(c.ip_pools, &pk);
+    const u8 *pool = tbl_find_conv<1>(c.ip_pools, &pk);
     if (!pool) {
         bstats_add(bs, ST_DHCP_ERROR, 1);
         return XDP_PASS_;
