@@ -356,8 +356,11 @@ NcclApi *nccl_api() {
     static NcclApi api;
     static std::once_flag once;
     std::call_once(once, [] {
+        // the copy the host process already has (a Python process with torch loaded brings its own, newer than the
+        // system's; loading another libnccl.so.2 first would shadow it for everything loaded later), else by name
         const char *path = getenv("BNG_NCCL_LIB");
-        api.handle = dlopen(path ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        api.handle = path ? nullptr : dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!api.handle) api.handle = dlopen(path ? path : "libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
         if (!api.handle) {
             api.err = std::string("dlopen libnccl.so.2: ") + (dlerror() ? dlerror() : "?");
             return;

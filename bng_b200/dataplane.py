@@ -343,6 +343,10 @@ class Dataplane:
     @staticmethod
     def comm_unique_id() -> bytes:
         """128-byte NCCL unique id (rank 0 makes it, the host plumbing distributes it)."""
+        try:  # a process that will use torch must have torch's libnccl resident before the library resolves the name
+            import torch  # noqa: F401
+        except Exception:
+            pass
         buf = C.create_string_buffer(128)
         r = load_library().bng_comm_unique_id(buf, 128)
         if r < 0:
