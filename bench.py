@@ -256,6 +256,7 @@ class G:
     local = 0
     dev = None
     dist = None
+    as_shard = None
 
 
 def _traffic(name, kernel, world, reference_capacities):
@@ -281,9 +282,10 @@ def measure(a, name, frames, steps, warmup, *, wl=None, reference_capacities=Fal
     from bng_b200.layouts import as_bytes
     dev, dist, world, rank = G.dev, G.dist, G.world, G.rank
     if wl is None:
-        wl = W.build(name, frames, rank, world, subs_scale)
+        wl = W.build(name, frames, *(G.as_shard or (rank, world)), subs_scale)
     n = wl.n
-    dp = Dataplane(device=G.local, max_batch=max(n, 1 << 20), rank=rank, world=world,
+    sr, sw = G.as_shard or (rank, world)
+    dp = Dataplane(device=G.local, max_batch=max(n, 1 << 20), rank=sr, world=sw,
                    **({} if reference_capacities else W.sizing(wl)))
     for m, k, v in wl.maps:
         r = dp.update_batch(m, as_bytes(k), as_bytes(v))
@@ -496,6 +498,58 @@ def e2e_leg(a, live):
 EXTRA_WORKLOADS = ("antispoof_64", "nat_steady_64", "nat_cold_64", "dhcp")
 
 
+def control_plane_leg(dp, wl):
+    """What the Go side does between batches, timed on the live context of the headline run (host clock around the
+    C-ABI calls, which are synchronous): one Map.Put (bng_map_update), staged upserts applied at the next batch
+    boundary (bng_map_update_staged + bng_sync), a batch upsert, and the expiry sweep over the live nat_sessions
+    table (one streaming pass: 64 of every slot's 128 bytes).  Not part of the headline metric."""
+    from bng_b200.layouts import as_bytes
+    out = {}
+    qm = [(m, k, v) for m, k, v in wl.maps if m == "qos_ingress"]
+    if qm:
+        _, k, v = qm[0]
+        kb, vb = as_bytes(k), as_bytes(v)
+        m = min(len(kb), 20000)
+        t = []
+        for i in range(min(m, 300)):
+            t0 = time.perf_counter()
+            dp.update("qos_ingress", kb[i], vb[i])
+            t.append(time.perf_counter() - t0)
+        out["put_single_us"] = {"median": round(float(np.median(t)) * 1e6, 1), "p99": round(float(np.percentile(t, 99)) * 1e6, 1),
+                                "n": len(t), "what": "bng_map_update(qos_ingress), synchronous, through ctypes"}
+        t0 = time.perf_counter()
+        for i in range(m):
+            dp.update_staged("qos_ingress", kb[i], vb[i])
+        t1 = time.perf_counter()
+        dp.sync()
+        t2 = time.perf_counter()
+        out["put_staged"] = {"n": m, "stage_us_each": round((t1 - t0) / m * 1e6, 2), "apply_ms": round((t2 - t1) * 1e3, 3),
+                             "puts_per_s": round(m / (t2 - t0)), "what": "bng_map_update_staged x n, applied by one bng_sync"}
+        t0 = time.perf_counter()
+        dp.update_batch("qos_ingress", kb[:m], vb[:m])
+        dt = time.perf_counter() - t0
+        out["put_batch"] = {"n": m, "ms": round(dt * 1e3, 3), "puts_per_s": round(m / dt)}
+    info = dp.map_info("nat_sessions")
+    live = info["count"]
+    if live:
+        slots = 1
+        while slots < 2 * info["max_entries"]:
+            slots *= 2
+        dp.sync()
+        t0 = time.perf_counter()
+        expired = dp.sweep(wl.now0 + 300 * 10**9)
+        dt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        dp.sweep(wl.now0 + 300 * 10**9)  # second pass: nothing left to expire = the pure scan
+        dt2 = time.perf_counter() - t0
+        out["sweep"] = {"live_sessions": int(live), "slots": slots, "expired": int(expired), "ms": round(dt * 1e3, 3),
+                        "scan_only_ms": round(dt2 * 1e3, 3), "scan_GBps": round(slots * 64 / dt2 / 1e9, 1),
+                        "table_rebuilds": int(dp.table_rebuilds),
+                        "what": "bng_sweep at now + 300 s (UDP, ICMP and non-established TCP flows expire); host clock, "
+                                "includes the launch + sync; scan bytes = 64 per 128-byte slot"}
+    return out
+
+
 def run_gpu(a):
     import torch
     import torch.distributed as dist
@@ -510,6 +564,12 @@ def run_gpu(a):
     json_fd = os.dup(1)
     os.dup2(2, 1)
     numa = bind_to_gpu_numa_node(local)  # pinned host buffers must live next to the GPU's PCIe root
+    # The untimed host-side refills of the frame arena are torch copies that fan out over every CPU the process can
+    # see (64+); under a cgroup CPU quota (16 on the 1-GPU boxes) such a burst spends the whole period's allowance and
+    # the kernel then freezes the cgroup for the rest of the period — right when the timed bng_prog_run call runs
+    # (tools/e2e_diag.py: one 50 ms step among 2.4 ms ones).  Stay well inside the quota.
+    hc = host_cpus()
+    torch.set_num_threads(max(1, min(8, hc["usable"] // 2)))
     torch.cuda.set_device(local)
     G.dev = dev = torch.device("cuda", local)
     G.dist = dist
@@ -520,7 +580,7 @@ def run_gpu(a):
     # ---- headline: the workload at BASELINE's population, tables sized for it ----
     head, live = measure(a, a.workload, a.frames, a.steps, a.warmup, reference_capacities=a.reference_capacities, keep=True)
     wl, dp = live["wl"], live["dp"]
-    e2e, e2e_extra = e2e_leg(a, live)
+    e2e, e2e_extra = e2e_leg(a, live) if a.e2e_steps > 0 else (None, None)  # 0: kernel-only runs under a profiler
 
     # ---- counter reconciliation: NCCL all-reduce of the packed counter vector INSIDE the library (bng_sync_reduce)
     #      over a communicator of the library's own; the unique id travels through the host plumbing ----
@@ -541,6 +601,7 @@ def run_gpu(a):
         dist.all_reduce(check, op=dist.ReduceOp.SUM)  # the same reduction by torch: must agree
     reduce_ok = bool((check.cpu().numpy().view(np.uint64) == stats_global).all())
     coop = (int(mine[37].item()), int(mine[38].item()))
+    ctl = control_plane_leg(dp, wl) if rank == 0 and not a.no_extra else None
     dp.close()
     del live
     torch.cuda.empty_cache()
@@ -588,7 +649,7 @@ def run_gpu(a):
             "config": {"workload": wl.name, "program": wl.prog, "frames_per_gpu_per_step": head["frames_per_gpu_per_step"],
                        "subscribers_this_gpu": wl.n_subs_local, "subscribers_total": "10 000 (BASELINE config #4), split over the GPUs"
                        if wl.name.startswith("pipeline") else "see workloads.py",
-                       "sharding": f"splitmix64(mac) % {world}", "tables": head["tables"],
+                       "sharding": f"splitmix64(mac) % {world}" if not G.as_shard else f"diagnostic: shard {G.as_shard[0]} of {G.as_shard[1]} alone", "tables": head["tables"],
                        "avg_frame_bytes": round(float(wl.lens.mean()), 1), "frame_align": a.align if wl.imix else live_stride(wl),
                        "step_ms_min_med_max": [round(float(x), 4) for x in
                                                (min(head["step_ms"]), float(np.median(head["step_ms"])), max(head["step_ms"]))],
@@ -606,6 +667,7 @@ def run_gpu(a):
                                 "antispoof_allowed": int(stats_global[0]), "nat_snat": int(stats_global[10]),
                                 "qos_dropped": int(stats_global[7])},
             "lru_overflow": head["lru_overflow"], "events_lost": head["events_lost"],
+            "control_plane": ctl,
             "nat_ordered_frames": {"cooperative": coop[0], "sequential": coop[1]},
             "wall_s": round(time.time() - t_start, 1),
         }
@@ -667,10 +729,14 @@ def main():
     ap.add_argument("--reference-capacities", action="store_true",
                     help="size every table for the reference's compile-time max_entries instead of the workload")
     ap.add_argument("--align", type=int, default=64, help="frame placement granularity in the IMIX arena (16 or 64)")
+    ap.add_argument("--as-shard", default=None, metavar="R/N",
+                    help="diagnostic: run ONE GPU as shard R of an N-GPU job (its subscribers, its frames) without the other ranks")
     ap.add_argument("--no-extra", action="store_true",
                     help="only the headline: skip the reference-capacities variant, the per-GPU-constant variant and the other configs")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    if a.as_shard:
+        G.as_shard = tuple(int(x) for x in a.as_shard.split("/"))
     if a.workload == "dhcp_slow":
         run_dhcp_slow(a)
     elif a.impl == "reference":

@@ -267,7 +267,19 @@ struct DevBatch {
     u32 cap;
     u64 arena_len; // bytes addressable from pkts (0 = unknown: no access may run past a frame's 16-byte chunks)
     const u64 *nowv; // per-frame bpf_ktime_get_ns() (monotonic), or nullptr: `now` for every frame
+    // Ordering keys carry the frame length above bit `kshift` (0: they do not), so that the ordered phase reads a
+    // subscriber's (key, frame, length) with two coalesced loads instead of gathering len[frame] afterwards.
+    u32 kshift;
 };
+// key | min(len, KEY_LEN_SAT) << KEY_BITS: 21 key bits hold the largest directory / bucket table of the reference's
+// capacities (2 x 1 M slots); 11 bits hold the length of every frame but a jumbo (KEY_LEN_SAT: "look it up";
+// 0x7FF is never written, so a packed key cannot read as NO_KEY).  Tables beyond 2^21 slots: no packing.
+#define KEY_BITS 21
+#define KEY_LEN_SAT 0x7FEu
+__host__ __device__ __forceinline__ u32 key_mask_of(u32 kshift) { return kshift ? (1u << kshift) - 1 : 0xFFFFFFFFu; }
+__device__ __forceinline__ u32 key_pack(u32 key, u32 len, u32 kshift) {
+    return kshift ? key | ((len < KEY_LEN_SAT ? len : KEY_LEN_SAT) << kshift) : key;
+}
 // may the 64 bytes at p be read with 32-byte accesses?
 #define FRAME_WIDE_OK(b, p) ((((uintptr_t)(p)) & 31) == 0 && (u64)((p) - (b).pkts) + 64 <= (b).arena_len)
 
@@ -383,9 +395,13 @@ __device__ __forceinline__ bool tbl_evict_near(const Tbl &t, u32 home, u64 *stat
 // else of the EMPTY slot that ended it (0xFFFFFFFF: none seen).  A following tbl_claim_at() then costs one CAS
 // instead of a second walk.  SKIP_BUSY semantics (ordered phase: a key has one owner).
 // The state words of PROBE_W consecutive slots are requested together: in a table that lives in DRAM every probe
-// step is a full memory round trip, and the longest chain among a warp's 32 lanes (3-4 steps at load 0.25) used to
-// cost that many round trips per lookup; bandwidth, in the ordered phase, is plentiful.
-#define PROBE_W 4
+// step is a full memory round trip, and the longest chain among a warp's 32 lanes (3-4 steps at load 0.25) costs
+// that many round trips per lookup.  Every speculative slot is a 64-byte DRAM burst, though, and the cold-start
+// kernel moves 46 G bursts/s — the part's scattered-access limit: 4 slots per step measured 0.637 ms per 2^20 new
+// flows, 2 slots 0.567, 1 slot 0.574 (profiles/r02_notes.md).
+#ifndef PROBE_W
+#define PROBE_W 2
+#endif
 template <int KW>
 __device__ __forceinline__ u8 *tbl_find_ins(const Tbl &t, const u64 *k, u32 *ins) {
     *ins = 0xFFFFFFFFu;

@@ -165,8 +165,6 @@ int ensure_scratch(bng_ctx *c, u32 n) {
         if (*pp) cudaFree(*pp);
         CU(c, cudaMalloc(pp, (size_t)cap * 4));
     }
-    if (s.pflag) cudaFree(s.pflag);
-    CU(c, cudaMalloc((void **)&s.pflag, cap));
     if (s.cub_tmp) cudaFree(s.cub_tmp);
     s.cub_tmp_bytes = sort_temp_bytes(cap);
     CU(c, cudaMalloc(&s.cub_tmp, s.cub_tmp_bytes ? s.cub_tmp_bytes : 16));
@@ -478,7 +476,7 @@ int bng_close(bng_ctx *c) {
         }
         for (void *p : c->allocs) cudaFree(p);
         Scratch &s = c->L.s;
-        void *sp[] = {s.key_a, s.key_b, s.val_a, s.val_b, s.qslot, s.pflag, s.cub_tmp, s.counters,
+        void *sp[] = {s.key_a, s.key_b, s.val_a, s.val_b, s.qslot, s.cub_tmp, s.counters,
                       c->io_dev, c->hb_pkts, c->hb_off, c->hb_len, c->hb_prio, c->hb_verdict, c->hb_now, c->dump_k, c->dump_v, c->dump_c};
         for (void *p : sp)
             if (p) cudaFree(p);

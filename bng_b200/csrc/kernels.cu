@@ -35,6 +35,7 @@
 #define DEFER_FLAG 0x20000000u // pipeline_tc: nat44_egress runs in the ordered phase, after the token bucket passed the frame
 
 // device-side counters (Scratch::counters)
+#define IDX_MASK 0x1FFFFFFFu // frame index bits of a grouped value (flags above)
 enum { CNT_M = 0, CNT_NSEG = 1, CNT_DEFERRED = 2, CNT_MAXKEY = 3, CNT_WORK = 4 };
 
 // The group-by's device counters and per-pass digit totals start every batch at zero: the classify kernel that feeds
@@ -51,6 +52,7 @@ __device__ __forceinline__ void scratch_reset(u32 *cnt, u32 *T) {
 struct Grouped {
     const u32 *ka, *va, *kb, *vb; // pass 0 writes a -> b, pass 1 b -> a, ...
     int passes;
+    u32 kshift; // the keys carry the frame length above this bit (0: they do not), DevBatch.kshift
 };
 __device__ __forceinline__ bool rs_pass_needed(const u32 *cnt, int shift) { return shift == 0 || (cnt[CNT_MAXKEY] >> shift) != 0; }
 __device__ __forceinline__ void grouped_select(const Grouped &g, const u32 *cnt, const u32 *&k, const u32 *&v) {
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(BLOCK)
         u32 key = qos_classify_one(c, bs, t, h, len, dlen, egress != 0, &prio, &prio_set);
         if (prio_set && b.priority) b.priority[i] = prio;
         b.verdict[i] = TC_OK;
-        skey[i] = key;
+        skey[i] = key == NO_KEY ? NO_KEY : key_pack(key, len, b.kshift);
         sval[i] = i;
     }
     bstats_flush(bs, c.stats);
@@ -357,7 +359,7 @@ __device__ __forceinline__ void rs_range(u32 total, u32 &lo, u32 &hi) {
 }
 
 __global__ void __launch_bounds__(BLOCK) k_rs_hist(const u32 *keys, u32 n_host, u32 *cnt, int first, int shift, u32 *H, u32 *T,
-                                                   u32 *anyv) {
+                                                   u32 *anyv, u32 kmask) {
     __shared__ u32 h[256];
     __shared__ u32 smax;
     if (!rs_pass_needed(cnt, shift)) return; // every key has a zero digit here: the pass would be the identity
@@ -371,6 +373,7 @@ __global__ void __launch_bounds__(BLOCK) k_rs_hist(const u32 *keys, u32 n_host, 
     for (u32 i = lo + threadIdx.x; i < hi; i += BLOCK) {
         u32 k = keys[i];
         if (k != NO_KEY) {
+            k &= kmask; // (the bits above the key carry the frame length: DevBatch.kshift)
             atomicAdd(&h[(k >> shift) & 0xff], 1u);
             mymax = k > mymax ? k : mymax;
         }
@@ -441,7 +444,7 @@ __global__ void __launch_bounds__(1024) k_rs_scan(u32 *H, const u32 *T, u32 nblo
 #define RS_TILE (RS_ROWS * BLOCK)
 #define RS_WARPS (BLOCK / 32)
 __global__ void __launch_bounds__(BLOCK) k_rs_scatter(const u32 *keys, const u32 *vals, u32 *okeys, u32 *ovals, u32 n_host,
-                                                      const u32 *cnt, int first, int shift, const u32 *H, const u32 *anyv) {
+                                                      const u32 *cnt, int first, int shift, const u32 *H, const u32 *anyv, u32 kmask) {
     __shared__ u16 wh[RS_WARPS][256]; // per-warp digit counts, then the warp's offset inside the digit's run
     __shared__ u32 stage_k[RS_TILE], stage_v[RS_TILE];
     __shared__ u32 tstart[256]; // tile-local start of digit d
@@ -487,7 +490,7 @@ __global__ void __launch_bounds__(BLOCK) k_rs_scatter(const u32 *keys, const u32
 #pragma unroll
         for (int r = 0; r < RS_ROWS; r++) {
             const bool ok = k[r] != NO_KEY;
-            u32 d = ok ? ((k[r] >> shift) & 0xff) : (256 + lane); // invalid lanes match nobody
+            u32 d = ok ? (((k[r] & kmask) >> shift) & 0xff) : (256 + lane); // invalid lanes match nobody
             u32 peers = __match_any_sync(0xffffffffu, d);
             u32 before = ok ? wh[w][d] : 0; // elements of digit d in the earlier rows of this warp
             u32 rk = __popc(peers & ((1u << lane) - 1));
@@ -527,7 +530,7 @@ __global__ void __launch_bounds__(BLOCK) k_rs_scatter(const u32 *keys, const u32
 #pragma unroll
         for (int r = 0; r < RS_ROWS; r++) {
             if (k[r] != NO_KEY) {
-                u32 d = (k[r] >> shift) & 0xff;
+                u32 d = ((k[r] & kmask) >> shift) & 0xff;
                 u32 lp = tstart[d] + wh[w][d] + rank[r];
                 stage_k[lp] = k[r];
                 stage_v[lp] = v[r];
@@ -537,7 +540,7 @@ __global__ void __launch_bounds__(BLOCK) k_rs_scatter(const u32 *keys, const u32
         const u32 tn = tile_n;
         for (u32 j = threadIdx.x; j < tn; j += BLOCK) {
             u32 kk = stage_k[j];
-            u32 g = gdelta[(kk >> shift) & 0xff] + j;
+            u32 g = gdelta[((kk & kmask) >> shift) & 0xff] + j;
             okeys[g] = kk;
             ovals[g] = stage_v[j];
         }
@@ -550,8 +553,9 @@ __global__ void __launch_bounds__(BLOCK) k_heads(const __grid_constant__ Grouped
     const u32 *skey, *sval_unused;
     grouped_select(g, cnt, skey, sval_unused);
     u32 m = cnt[CNT_M];
+    const u32 kmask = key_mask_of(g.kshift);
     for (u32 j = 4 * (blockIdx.x * BLOCK + threadIdx.x); j < m; j += 4 * gridDim.x * BLOCK) { // 4 keys per thread
-        u32 k[4], prev = j ? skey[j - 1] : ~skey[0];
+        u32 k[4], prev = j ? skey[j - 1] & kmask : ~(skey[0] & kmask);
         if (j + 3 < m) {
             const uint4 v = *(const uint4 *)(skey + j);
             k[0] = v.x, k[1] = v.y, k[2] = v.z, k[3] = v.w;
@@ -561,6 +565,7 @@ __global__ void __launch_bounds__(BLOCK) k_heads(const __grid_constant__ Grouped
         }
 #pragma unroll
         for (int t = 0; t < 4; t++) {
+            k[t] &= kmask;
             if (j + t < m && k[t] != prev) seg[atomicAdd(&cnt[CNT_NSEG], 1u)] = j + t;
             prev = k[t];
         }
@@ -582,9 +587,11 @@ __global__ void __launch_bounds__(BLOCK) k_heads(const __grid_constant__ Grouped
 // The group key is the subscriber-directory slot (programs with a NAT stage) or the bucket's own slot.
 // ---------------------------------------------------------------------------
 #define DROP_FLAG 0x40000000u // staged value: nat44_egress dropped the frame (port exhaustion): no QoS stage
-#define IDX_MASK 0x1FFFFFFFu
 #ifndef RS_PER_THREAD
 #define RS_PER_THREAD 8
+#endif
+#ifndef RS_PREFETCH
+#define RS_PREFETCH 1
 #endif
 
 // The NAT stage of one 32-frame chunk that holds new flows (mm: their lanes), kept out of line: the steady state
@@ -644,7 +651,7 @@ __device__ __forceinline__ bool resolve_nat_chunk(const DevCtx &c, const DevBatc
 // new flows alike — for the frames it passed (DEFER_FLAG), with the parse-stage counters still to be counted.
 template <bool NAT, bool QOS, bool EGRESS, int TEAM, bool TC = false>
 #ifndef RESOLVE_MINB
-#define RESOLVE_MINB 20
+#define RESOLVE_MINB 16
 #endif
 __global__ void __launch_bounds__(TEAM, (TEAM == 128 ? 6 : RESOLVE_MINB)) k_resolve(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b,
                                                   const __grid_constant__ Grouped g, const u32 *seg, u32 *cnt) {
@@ -658,6 +665,7 @@ __global__ void __launch_bounds__(TEAM, (TEAM == 128 ? 6 : RESOLVE_MINB)) k_reso
     const Tbl &qt = EGRESS ? c.qos_eg : c.qos_in;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 m = cnt[CNT_M], nseg = cnt[CNT_NSEG];
+    const u32 kmask = key_mask_of(g.kshift);
     u32 pp = 0, dp = 0; // per-thread partial QoS counters
     u64 pb = 0, db = 0;
     // groups are handed out dynamically (fat and thin groups mix: a static stride leaves blocks idle at the end)
@@ -667,7 +675,7 @@ __global__ void __launch_bounds__(TEAM, (TEAM == 128 ? 6 : RESOLVE_MINB)) k_reso
         const u32 s = s_next;
         if (s >= nseg) break;
         const u32 start = seg[s];
-        const u32 key = skey[start];
+        const u32 key = skey[start] & kmask;
         u8 *sub = nullptr, *slot = nullptr;
         if (NAT) {
             const u64 w = *(const u64 *)(c.subdir.slots + (size_t)key * 16 + 8);
@@ -684,21 +692,26 @@ __global__ void __launch_bounds__(TEAM, (TEAM == 128 ? 6 : RESOLVE_MINB)) k_reso
             if (tid == 0) s_cnt = STAGE;
             __syncthreads();
             {
-                u32 sv[RS_PER_THREAD];
+                u32 kk[RS_PER_THREAD], sv[RS_PER_THREAD];
                 bool ok[RS_PER_THREAD];
 #pragma unroll
                 for (int t = 0; t < RS_PER_THREAD; t++) {
                     const u32 q = pos + t * TEAM + tid;
-                    ok[t] = q < m && skey[q] == key;
-                    sv[t] = ok[t] ? sval[q] : 0;
+                    kk[t] = q < m ? skey[q] : 0;
+                    sv[t] = q < m ? sval[q] : 0;
+                    ok[t] = q < m && (kk[t] & kmask) == key;
                 }
                 u32 first_bad = STAGE;
 #pragma unroll
                 for (int t = 0; t < RS_PER_THREAD; t++) {
                     const u32 j = t * TEAM + tid;
                     if (ok[t]) {
+                        // the length came with the key (DevBatch.kshift); a jumbo frame's, or any when the key space
+                        // leaves no room, is looked up
+                        u32 l = g.kshift ? kk[t] >> g.kshift : KEY_LEN_SAT;
+                        if (l == KEY_LEN_SAT) l = b.len[sv[t] & IDX_MASK];
                         s_sv[j] = sv[t];
-                        s_len[j] = b.len[sv[t] & IDX_MASK];
+                        s_len[j] = l;
                     } else if (j < first_bad) {
                         first_bad = j;
                     }
@@ -708,6 +721,15 @@ __global__ void __launch_bounds__(TEAM, (TEAM == 128 ? 6 : RESOLVE_MINB)) k_reso
             __syncthreads();
             const u32 n_here = s_cnt;
             const u32 nchunk = (n_here + 31) / 32;
+#if RS_PREFETCH
+            // a fat group: the next sweep's two cache-line runs are requested now (into L1, no registers held) and
+            // arrive while this sweep is walked
+            if (n_here == (u32)STAGE && tid < 2 * (STAGE * 4 / 128)) {
+                const u32 *base = tid < STAGE / 32 ? skey : sval;
+                const u32 q = pos + STAGE + (tid % (STAGE / 32)) * 32;
+                if (q < m) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + q));
+            }
+#endif
             // ---- NAT stage of this subscriber's frames, strictly in index order: new flows (MISS_FLAG) and, in TC
             //      order, every frame that waited for the token bucket (DEFER_FLAG) and was not dropped by it ----
             auto nat_phase = [&]() {
@@ -886,7 +908,7 @@ void prof_collect(Launcher &L) {
 // Groups the (key, value) pairs in (key_a, val_a)[0..n) by key, stably, skipping NO_KEY.
 // On return *sk / *sv name the buffers holding the grouped pairs; counters[CNT_M] holds their
 // number and seg[0..counters[CNT_NSEG]) the group heads.
-static cudaError_t group_by_key(Launcher &L, u32 n, u64 key_space, Grouped *out) {
+static cudaError_t group_by_key(Launcher &L, u32 n, u64 key_space, u32 kshift, Grouped *out) {
     Scratch &s = L.s;
     int passes = (bits_for(key_space) + 7) / 8;
     int rsb = L.num_sms * RS_BLOCKS_PER_SM;
@@ -897,9 +919,9 @@ static cudaError_t group_by_key(Launcher &L, u32 n, u64 key_space, Grouped *out)
     prof_begin(L, "group_by_key");
     for (int p = 0; p < passes; p++) {
         int first = p == 0;
-        k_rs_hist<<<rsb, BLOCK, 0, L.stream>>>(ik, n, s.counters, first, 8 * p, H, T + 256 * p, ANYV);
+        k_rs_hist<<<rsb, BLOCK, 0, L.stream>>>(ik, n, s.counters, first, 8 * p, H, T + 256 * p, ANYV, key_mask_of(kshift));
         k_rs_scan<<<256, 1024, 0, L.stream>>>(H, T + 256 * p, (u32)rsb, s.counters, first, 8 * p);
-        k_rs_scatter<<<rsb, BLOCK, 0, L.stream>>>(ik, iv, ok, ov, n, s.counters, first, 8 * p, H, ANYV);
+        k_rs_scatter<<<rsb, BLOCK, 0, L.stream>>>(ik, iv, ok, ov, n, s.counters, first, 8 * p, H, ANYV, key_mask_of(kshift));
         L.launches += 3;
         u32 *t = ik;
         ik = ok;
@@ -914,12 +936,16 @@ static cudaError_t group_by_key(Launcher &L, u32 n, u64 key_space, Grouped *out)
     g.kb = s.key_b;
     g.vb = s.val_b;
     g.passes = passes;
+    g.kshift = kshift;
     *out = g;
     k_heads<<<grid_for(L, n, 8), BLOCK, 0, L.stream>>>(g, s.qslot, s.counters);
     L.launches++;
     prof_end(L);
     return cudaGetLastError();
 }
+
+// Room for the frame length above the ordering key?  (KEY_BITS covers the reference's capacities.)
+static inline u32 kshift_for(u64 key_space) { return bits_for(key_space) <= KEY_BITS ? KEY_BITS : 0; }
 
 // k_resolve walks one group per block and a batch of n frames can hold n groups: the grid is sized for n blocks,
 // capped at what the GPU holds at once (the blocks loop over the groups).
@@ -943,11 +969,13 @@ cudaError_t run_antispoof(Launcher &L, const DevCtx &c, const DevBatch &b) {
     return cudaGetLastError();
 }
 
-cudaError_t run_qos(Launcher &L, const DevCtx &c, const DevBatch &b, bool egress) {
-    LAUNCH(k_qos_classify, b.n, 8, c, b, egress ? 1 : 0, L.s.key_a, L.s.val_a, L.s.counters, sort_T(L));
+cudaError_t run_qos(Launcher &L, const DevCtx &c, const DevBatch &b0, bool egress) {
     const Tbl &t = egress ? c.qos_eg : c.qos_in;
+    DevBatch b = b0;
+    b.kshift = kshift_for((u64)t.mask + 1);
+    LAUNCH(k_qos_classify, b.n, 8, c, b, egress ? 1 : 0, L.s.key_a, L.s.val_a, L.s.counters, sort_T(L));
     Grouped g;
-    cudaError_t e = group_by_key(L, b.n, (u64)t.mask + 1, &g);
+    cudaError_t e = group_by_key(L, b.n, (u64)t.mask + 1, b.kshift, &g);
     if (e != cudaSuccess) return e;
     if (egress)
         launch_resolve<false, true, true, 32>(L, c, b, g, "(k_resolve<false, true, true>)");
@@ -956,10 +984,12 @@ cudaError_t run_qos(Launcher &L, const DevCtx &c, const DevBatch &b, bool egress
     return cudaGetLastError();
 }
 
-cudaError_t run_nat_egress(Launcher &L, const DevCtx &c, const DevBatch &b) {
+cudaError_t run_nat_egress(Launcher &L, const DevCtx &c, const DevBatch &b0) {
+    DevBatch b = b0;
+    b.kshift = kshift_for((u64)c.subdir.mask + 1);
     LAUNCH((k_pipe_classify<false, false>), b.n, CLASSIFY_BPS(false), c, b, L.s.key_a, L.s.val_a, L.s.counters, sort_T(L));
     Grouped g;
-    cudaError_t e = group_by_key(L, b.n, (u64)c.subdir.mask + 1, &g);
+    cudaError_t e = group_by_key(L, b.n, (u64)c.subdir.mask + 1, b.kshift, &g);
     if (e != cudaSuccess) return e;
     launch_resolve<true, false, false, 32>(L, c, b, g, "(k_resolve<true, false, false>)");
     return cudaGetLastError();
@@ -975,19 +1005,23 @@ cudaError_t run_nat_hairpin_xdp(Launcher &L, const DevCtx &c, const DevBatch &b)
     return cudaGetLastError();
 }
 
-cudaError_t run_pipeline_up(Launcher &L, const DevCtx &c, const DevBatch &b) {
+cudaError_t run_pipeline_up(Launcher &L, const DevCtx &c, const DevBatch &b0) {
+    DevBatch b = b0;
+    b.kshift = kshift_for((u64)c.subdir.mask + 1);
     LAUNCH((k_pipe_classify<true, true>), b.n, CLASSIFY_BPS(true), c, b, L.s.key_a, L.s.val_a, L.s.counters, sort_T(L));
     Grouped g;
-    cudaError_t e = group_by_key(L, b.n, (u64)c.subdir.mask + 1, &g);
+    cudaError_t e = group_by_key(L, b.n, (u64)c.subdir.mask + 1, b.kshift, &g);
     if (e != cudaSuccess) return e;
     launch_resolve<true, true, false, 32>(L, c, b, g, "(k_resolve<true, true, false>)");
     return cudaGetLastError();
 }
 
-cudaError_t run_pipeline_tc(Launcher &L, const DevCtx &c, const DevBatch &b) {
+cudaError_t run_pipeline_tc(Launcher &L, const DevCtx &c, const DevBatch &b0) {
+    DevBatch b = b0;
+    b.kshift = kshift_for((u64)c.subdir.mask + 1);
     LAUNCH((k_pipe_classify<true, true, true>), b.n, CLASSIFY_BPS(true), c, b, L.s.key_a, L.s.val_a, L.s.counters, sort_T(L));
     Grouped g;
-    cudaError_t e = group_by_key(L, b.n, (u64)c.subdir.mask + 1, &g);
+    cudaError_t e = group_by_key(L, b.n, (u64)c.subdir.mask + 1, b.kshift, &g);
     if (e != cudaSuccess) return e;
     launch_resolve<true, true, false, 32, true>(L, c, b, g, "(k_resolve<true, true, false, tc>)");
     return cudaGetLastError();

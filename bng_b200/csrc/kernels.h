@@ -5,8 +5,7 @@
 
 struct Scratch {
     u32 *key_a, *key_b, *val_a, *val_b; // ordering keys / frame indices, unsorted and grouped
-    u32 *qslot;                         // pipeline: qos bucket slot per frame
-    u8 *pflag;                          // pipeline: per-frame flags
+    u32 *qslot;                         // group heads (positions in the grouped arrays)
     void *cub_tmp;
     size_t cub_tmp_bytes;
     u32 *counters; // 16 x u32 of per-run device counters

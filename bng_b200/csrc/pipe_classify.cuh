@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
                 n_qpass++; // unlimited bucket and nothing left to order (bpf/qos_ratelimit.c:77-78)
                 n_qbytes += len;
             } else if (qos_slot != DIR_NONE || miss) {
-                okey = dir_idx;
+                okey = key_pack(dir_idx, len, b.kshift);
             }
             if (miss) oval |= MISS_FLAG;
             if (defer) oval |= DEFER_FLAG;

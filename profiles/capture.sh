@@ -9,8 +9,8 @@ mkdir -p $O
 B="--steps 3 --warmup 3 --no-cpu --no-extra --e2e-steps 1"
 # 1. launch list: every kernel of a short headline run with its device time (cold-cache, serialised:
 #    compare SHARES, not absolutes)
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_" -s 60 -c 120 --csv \
-    --log-file $O/launches.csv python bench.py $B > $O/launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_" -c 400 --csv \
+    --log-file $O/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-extra --e2e-steps 0 > $O/launches.log 2>&1
 # 2. full-set captures (one instance each) of the kernels of the headline step ...
 ncu --set full --clock-control none --import-source on -k regex:"k_pipe_classify" -s 5 -c 1 -o $O/classify -f \
     python bench.py $B > $O/classify.log 2>&1

@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 
 from bng_b200 import layouts as L
+from bng_b200 import synth as S
 from bng_b200 import workloads as W
 from bng_b200.layouts import as_bytes
 
@@ -151,6 +152,48 @@ def test_million_frames_against_reference(name):
     ref = _oracle_run(wl, arena, off16, stride, steps)
     gpu = _gpu_run(wl, arena, off16, stride, steps, "device")
     _same(ref, gpu, f"{name}: reference oracle vs gpu (device-resident)")
+
+
+@pytest.mark.parametrize("case", ["pipeline_up", "pipeline_tc", "qos", "qos_egress", "nat_cold", "nat_cold_exhaust", "pipeline_up_miss"])
+def test_fat_subscribers_against_reference(case):
+    """A handful of subscribers with thousands of frames each: every subscriber's run spans many tiles of the ordered
+    phase, so its token bucket, port counter and flow creation travel along the chain of warps (kernels.cu: ChainRec)
+    — what one GPU of an 8-GPU job sees, pushed further.  Bit for bit against the reference oracle."""
+    n = 1 << 17
+    if case in ("pipeline_up", "pipeline_tc", "pipeline_up_miss"):
+        wl = W.pipeline(n, 0, 1, n_subs=12, flows_per_sub=64 if case != "pipeline_up_miss" else 700)
+        if case == "pipeline_tc":
+            wl.prog = "pipeline_tc"
+        if case == "pipeline_up_miss":
+            wl.prewarm = []  # nothing pre-created: the first batch creates 700 flows per subscriber along the chain
+    elif case in ("qos", "qos_egress"):
+        wl = W.qos(n, 0, 1, n_subs=7, egress=case == "qos_egress")
+    else:
+        # 1024-port blocks (AllocateNAT): 900 flows fit, 1500 exhaust the block in mid-run (drops + sequential code)
+        wl = W.nat(n, 0, 1, n_subs=9, flows_per_sub=900 if case == "nat_cold" else 1500, cold=True)
+    arena, off16, stride = _arena(wl)
+    steps = 1 if case.startswith("nat_cold") else 3
+    ref = _oracle_run(wl, arena, off16, stride, steps)
+    gpu = _gpu_run(wl, arena, off16, stride, steps, "device")
+    _same(ref, gpu, f"fat subscribers / {case}: reference oracle vs gpu")
+
+
+@pytest.mark.parametrize("case", ["pipeline_up", "pipeline_tc", "qos"])
+def test_jumbo_lengths_against_reference(case):
+    """The ordered phase carries a frame's length in the spare bits of its ordering key (DevBatch.kshift); lengths
+    of 2046 bytes and more do not fit and are looked up instead.  A header ring (64-byte slots) whose len[] runs from
+    64 to 9000 bytes, around the 2046 boundary in particular, against the reference oracle."""
+    n = 1 << 16
+    wl = W.qos(n, 0, 1, n_subs=300) if case == "qos" else W.pipeline(n, 0, 1, n_subs=300, imix=False)
+    if case == "pipeline_tc":
+        wl.prog = "pipeline_tc"
+    pick = np.array([64, 128, 1518, 2044, 2045, 2046, 2047, 2048, 4000, 9000], np.uint32)
+    wl.lens = pick[(S.splitmix64_array(0x7B0, n) % np.uint64(len(pick))).astype(np.int64)]
+    arena, off16, stride = _arena(wl)
+    assert off16 is None and stride == 64
+    ref = _oracle_run(wl, arena, off16, stride, 2)
+    gpu = _gpu_run(wl, arena, off16, stride, 2, "device")
+    _same(ref, gpu, f"jumbo lengths / {case}: reference oracle vs gpu")
 
 
 @pytest.mark.parametrize("mode", ["device", "pinned"])

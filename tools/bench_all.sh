@@ -11,7 +11,7 @@ import json,sys
 try:
     d=json.load(open(sys.argv[1]))
     r=d["roofline"]
-    print(f"coop {d.get('nat_ordered_chunks')}", end=" "); print(f'{d["config"]["workload"]:16s} {d["value"]:9.1f} Mpps  {d["ms_per_step"]:.4f} ms/step  top {r["kernel"]} {r["kernel_ms"]} ms frac {r["frac"]}  e2e {d["e2e"]["value"]}  kernels {r["kernels_ms"]}')
+    print(f"coop {d.get('nat_ordered_chunks')}", end=" "); print(f'{d["config"]["workload"]:16s} {d["value"]:9.1f} Mpps  {d["ms_per_step"]:.4f} ms/step  top {r["kernel"]} {r["kernel_ms"]} ms frac {r["frac"]}  e2e {(d.get("e2e") or {}).get("value")}  kernels {r["kernels_ms"]}')
 except Exception as e:
     print("no result", sys.argv[1], e)
 PY
