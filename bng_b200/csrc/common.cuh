@@ -271,6 +271,10 @@ struct DevBatch {
     // subscriber's (key, frame, length) with two coalesced loads instead of gathering len[frame] afterwards.
     u32 kshift;
 };
+// First statement (before any global access) of a kernel launched with programmatic stream serialisation
+// (kernels.cu: launch_dep): returns when the preceding grid of the stream has completed and its writes are visible.
+// A no-op in a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // key | min(len, KEY_LEN_SAT) << KEY_BITS: 21 key bits hold the largest directory / bucket table of the reference's
 // capacities (2 x 1 M slots); 11 bits hold the length of every frame but a jumbo (KEY_LEN_SAT: "look it up";
 // 0x7FF is never written, so a packed key cannot read as NO_KEY).  Tables beyond 2^21 slots: no packing.

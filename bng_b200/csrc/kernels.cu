@@ -362,6 +362,7 @@ __global__ void __launch_bounds__(BLOCK) k_rs_hist(const u32 *keys, u32 n_host, 
                                                    u32 *anyv, u32 kmask) {
     __shared__ u32 h[256];
     __shared__ u32 smax;
+    pdl_wait();
     if (!rs_pass_needed(cnt, shift)) return; // every key has a zero digit here: the pass would be the identity
     h[threadIdx.x] = 0;
     if (threadIdx.x == 0) smax = 0;
@@ -397,6 +398,7 @@ __global__ void __launch_bounds__(BLOCK) k_rs_hist(const u32 *keys, u32 n_host, 
 __global__ void __launch_bounds__(1024) k_rs_scan(u32 *H, const u32 *T, u32 nblocks, u32 *cnt, int first, int shift) {
     __shared__ u32 wsum[32];
     __shared__ u32 s_base;
+    pdl_wait();
     if (!rs_pass_needed(cnt, shift)) return;
     const u32 d = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     u32 t = (threadIdx.x < 256 && threadIdx.x < d) ? T[threadIdx.x] : 0; // digits below d
@@ -451,6 +453,7 @@ __global__ void __launch_bounds__(BLOCK) k_rs_scatter(const u32 *keys, const u32
     __shared__ u32 gdelta[256]; // global position of a staged element = gdelta[digit] + its tile-local position
     __shared__ u32 wsum[RS_WARPS];
     __shared__ u32 tile_n;
+    pdl_wait();
     if (!rs_pass_needed(cnt, shift)) return;
     if (first && !anyv[blockIdx.x]) return; // nothing but NO_KEY in this block's range
     u32 goff = H[threadIdx.x * gridDim.x + blockIdx.x]; // thread d owns the running global offset of digit d
@@ -551,6 +554,7 @@ __global__ void __launch_bounds__(BLOCK) k_rs_scatter(const u32 *keys, const u32
 // group heads: positions where the sorted key changes (any order; groups are independent)
 __global__ void __launch_bounds__(BLOCK) k_heads(const __grid_constant__ Grouped g, u32 *seg, u32 *cnt) {
     const u32 *skey, *sval_unused;
+    pdl_wait();
     grouped_select(g, cnt, skey, sval_unused);
     u32 m = cnt[CNT_M];
     const u32 kmask = key_mask_of(g.kshift);
@@ -660,6 +664,7 @@ __global__ void __launch_bounds__(TEAM, (TEAM == 128 ? 6 : RESOLVE_MINB)) k_reso
     __shared__ u32 s_sv[STAGE], s_len[STAGE];
     __shared__ u32 s_cnt, s_next;
     bstats_init(bs);
+    pdl_wait();
     const u32 *skey, *sval;
     grouped_select(g, cnt, skey, sval);
     const Tbl &qt = EGRESS ? c.qos_eg : c.qos_in;
@@ -897,6 +902,33 @@ void prof_collect(Launcher &L) {
     L.npend = 0;
 }
 
+// Programmatic dependent launch for the kernels that FOLLOW the classify kernel of a batch (radix passes, group
+// heads, resolve): the launch may be processed while its predecessor in the stream is still running — its blocks are
+// set up early and wait in pdl_wait() (griddepcontrol.wait: returns once the preceding grid has completed and its
+// memory operations are visible), which takes the launch latency out of the chain of eight dependent kernels that
+// a small batch consists of.  Every kernel launched this way calls pdl_wait() before its first global access.
+#ifndef BNG_PDL
+#define BNG_PDL 1
+#endif
+template <typename... KArgs, typename... Args>
+static inline void launch_dep(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args &&...args) {
+#if BNG_PDL
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+#else
+    kern<<<grid, block, 0, st>>>(KArgs(args)...);
+#endif
+}
+
 #define LAUNCH(kern, n, bps, ...)                                      \
     do {                                                               \
         prof_begin(L, #kern);                                          \
@@ -919,9 +951,9 @@ static cudaError_t group_by_key(Launcher &L, u32 n, u64 key_space, u32 kshift, G
     prof_begin(L, "group_by_key");
     for (int p = 0; p < passes; p++) {
         int first = p == 0;
-        k_rs_hist<<<rsb, BLOCK, 0, L.stream>>>(ik, n, s.counters, first, 8 * p, H, T + 256 * p, ANYV, key_mask_of(kshift));
-        k_rs_scan<<<256, 1024, 0, L.stream>>>(H, T + 256 * p, (u32)rsb, s.counters, first, 8 * p);
-        k_rs_scatter<<<rsb, BLOCK, 0, L.stream>>>(ik, iv, ok, ov, n, s.counters, first, 8 * p, H, ANYV, key_mask_of(kshift));
+        launch_dep(k_rs_hist, rsb, BLOCK, L.stream, ik, n, s.counters, first, 8 * p, H, T + 256 * p, ANYV, key_mask_of(kshift));
+        launch_dep(k_rs_scan, 256, 1024, L.stream, H, T + 256 * p, (u32)rsb, s.counters, first, 8 * p);
+        launch_dep(k_rs_scatter, rsb, BLOCK, L.stream, ik, iv, ok, ov, n, s.counters, first, 8 * p, H, ANYV, key_mask_of(kshift));
         L.launches += 3;
         u32 *t = ik;
         ik = ok;
@@ -938,7 +970,7 @@ static cudaError_t group_by_key(Launcher &L, u32 n, u64 key_space, u32 kshift, G
     g.passes = passes;
     g.kshift = kshift;
     *out = g;
-    k_heads<<<grid_for(L, n, 8), BLOCK, 0, L.stream>>>(g, s.qslot, s.counters);
+    launch_dep(k_heads, grid_for(L, n, 8), BLOCK, L.stream, g, s.qslot, s.counters);
     L.launches++;
     prof_end(L);
     return cudaGetLastError();
@@ -959,7 +991,7 @@ static void launch_resolve(Launcher &L, const DevCtx &c, const DevBatch &b, cons
     long cap = (long)L.num_sms * per_sm, want = b.n ? b.n : 1;
     int grid = (int)(want < cap ? want : cap);
     prof_begin(L, name);
-    k_resolve<NAT, QOS, EGRESS, TEAM, TC><<<grid, TEAM, 0, L.stream>>>(c, b, g, L.s.qslot, L.s.counters);
+    launch_dep(k_resolve<NAT, QOS, EGRESS, TEAM, TC>, grid, TEAM, L.stream, c, b, g, L.s.qslot, L.s.counters);
     prof_end(L);
     L.launches++;
 }
