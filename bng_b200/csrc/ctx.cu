@@ -48,6 +48,11 @@ thread_local std::string g_open_err;
 
 } // namespace
 
+// buffers of the zero-copy pipeline: three stages (in, compute, out) in flight need three
+#ifndef ZC_BUFS
+#define ZC_BUFS 3
+#endif
+
 struct bng_ctx {
     std::mutex mu;
     int device = 0;
@@ -64,19 +69,19 @@ struct bng_ctx {
     u8 *hb_pkts = nullptr;
     u32 *hb_off = nullptr, *hb_len = nullptr, *hb_prio = nullptr;
     u64 *hb_now = nullptr;
-    u64 *zc_now[2] = {nullptr, nullptr};
+    u64 *zc_now[ZC_BUFS] = {};
     u8 *hb_verdict = nullptr;
     size_t hb_arena = 0;
     u32 hb_n = 0;
     u64 lost_base[2] = {0, 0};
     // zero-copy pipeline for BNG_MEM_HOST batches in pinned memory: two chunk buffers, three streams
     cudaStream_t s_in = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-    u8 *zc_hdr[2] = {nullptr, nullptr}, *zc_verdict[2] = {nullptr, nullptr};
-    u32 *zc_off[2] = {nullptr, nullptr}, *zc_len[2] = {nullptr, nullptr}, *zc_len0[2] = {nullptr, nullptr},
-        *zc_prio[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in[ZC_BUFS] = {}, ev_comp[ZC_BUFS] = {}, ev_out[ZC_BUFS] = {};
+    u8 *zc_hdr[ZC_BUFS] = {}, *zc_verdict[ZC_BUFS] = {};
+    u32 *zc_off[ZC_BUFS] = {}, *zc_len[ZC_BUFS] = {}, *zc_len0[ZC_BUFS] = {}, *zc_prio[ZC_BUFS] = {};
     u32 zc_hb = 0;
-    u32 zc_chunk = 1u << 19; // frames per chunk of the zero-copy pipeline
+    u32 zc_chunk = 1u << 18; // frames per chunk of the zero-copy pipeline
+    u32 zc_bps = 1;          // blocks per SM of the header gather / scatter kernels (PCIe-bound: hostio.cu)
     // staged upserts (bng_map_update_staged): per map, keys/values in arrival order, applied at the next batch boundary
     struct Staged {
         std::vector<u8> keys, vals;
@@ -120,7 +125,7 @@ int fail(bng_ctx *c, int code, const char *fmt, ...) {
 
 u32 zc_chunk_frames() { // frames per chunk of the zero-copy pipeline; BNG_ZC_CHUNK_LOG2 overrides for tuning (read at bng_open)
     const char *e = getenv("BNG_ZC_CHUNK_LOG2");
-    int lg = e ? atoi(e) : 19;
+    int lg = e ? atoi(e) : 18; // (tools/e2e_chunk_sweep.sh: 2^18 is the best or equal-best for both host layouts)
     if (lg < 10) lg = 10;
     if (lg > 22) lg = 22;
     return 1u << lg;
@@ -481,7 +486,7 @@ int bng_close(bng_ctx *c) {
         for (void *p : sp)
             if (p) cudaFree(p);
         if (c->io_host) cudaFreeHost(c->io_host);
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < ZC_BUFS; i++) {
             void *zp[] = {c->zc_hdr[i], c->zc_verdict[i], c->zc_off[i], c->zc_len[i], c->zc_len0[i], c->zc_prio[i], c->zc_now[i]};
             for (void *p : zp)
                 if (p) cudaFree(p);
@@ -540,6 +545,7 @@ bng_ctx *bng_open(const bng_open_opts *o) {
     }
     c->L.num_sms = prop.multiProcessorCount;
     c->zc_chunk = zc_chunk_frames();
+    if (const char *e = getenv("BNG_ZC_BLOCKS_PER_SM")) c->zc_bps = (u32)std::min(16, std::max(1, atoi(e))); // tuning knob
     OPEN_CU(cudaStreamCreateWithFlags(&c->L.stream, cudaStreamNonBlocking));
 
     u32 max_subs = opts.max_subscribers ? opts.max_subscribers : 1000000u;
@@ -1020,7 +1026,7 @@ static int run_host_zero_copy(bng_ctx *c, int prog, bng_batch *bb, u8 *arena_dev
     if (!c->s_in) {
         CU(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
         CU(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < ZC_BUFS; i++) {
             CU(c, cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
             CU(c, cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming));
             CU(c, cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
@@ -1033,21 +1039,33 @@ static int run_host_zero_copy(bng_ctx *c, int prog, bng_batch *bb, u8 *arena_dev
         }
     }
     if (c->zc_hb < hb) {
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < ZC_BUFS; i++) {
             if (c->zc_hdr[i]) cudaFree(c->zc_hdr[i]);
             c->zc_hdr[i] = nullptr;
         }
         c->zc_hb = 0;
-        for (int i = 0; i < 2; i++) CU(c, cudaMalloc((void **)&c->zc_hdr[i], (size_t)ZC_CHUNK * hb + 64));
+        for (int i = 0; i < ZC_BUFS; i++) CU(c, cudaMalloc((void **)&c->zc_hdr[i], (size_t)ZC_CHUNK * hb + 64));
         c->zc_hb = hb;
     }
     cudaStream_t sc = c->L.stream;
     const u32 nchunks = (bb->n + ZC_CHUNK - 1) / ZC_CHUNK;
+    // BNG_ZC_TRACE=1: a timeline of the three stages of every chunk on stderr (timing events on the three streams)
+    static const bool trace = getenv("BNG_ZC_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tev.push_back(e);
+    };
+    mark(c->s_in); // t0
     for (u32 k = 0; k < nchunks; k++) {
-        const int buf = k & 1;
+        const int buf = k % ZC_BUFS;
         const u32 base = k * ZC_CHUNK, cn = std::min<u32>(ZC_CHUNK, bb->n - base);
         // ---- in ----
-        if (k >= 2) CU(c, cudaStreamWaitEvent(c->s_in, c->ev_out[buf], 0));
+        if (k >= ZC_BUFS) CU(c, cudaStreamWaitEvent(c->s_in, c->ev_out[buf], 0));
+        mark(c->s_in);
         if (bb->off16) CU(c, cudaMemcpyAsync(c->zc_off[buf], bb->off16 + base, (size_t)cn * 4, cudaMemcpyHostToDevice, c->s_in));
         CU(c, cudaMemcpyAsync(c->zc_len[buf], bb->len + base, (size_t)cn * 4, cudaMemcpyHostToDevice, c->s_in));
         if (bb->priority)
@@ -1059,13 +1077,15 @@ static int run_host_zero_copy(bng_ctx *c, int prog, bng_batch *bb, u8 *arena_dev
             CU(c, cudaMemcpyAsync(c->zc_hdr[buf], (u8 *)bb->pkts + (size_t)base * hb, (size_t)cn * hb, cudaMemcpyHostToDevice,
                                   c->s_in));
         } else {
-            CU(c, run_gather_frames(c->s_in, c->L.num_sms, chunk_arena, bb->off16 ? c->zc_off[buf] : nullptr, c->zc_len[buf],
+            CU(c, run_gather_frames(c->s_in, c->L.num_sms * (int)c->zc_bps, chunk_arena, bb->off16 ? c->zc_off[buf] : nullptr, c->zc_len[buf],
                                     bb->stride, cn, hb, tc, c->zc_hdr[buf], c->zc_len0[buf]));
             c->L.launches++;
         }
         CU(c, cudaEventRecord(c->ev_in[buf], c->s_in));
+        mark(c->s_in);
         // ---- compute ----
         CU(c, cudaStreamWaitEvent(sc, c->ev_in[buf], 0));
+        mark(sc);
         DevBatch b{};
         b.pkts = c->zc_hdr[buf];
         b.off16 = nullptr;
@@ -1082,13 +1102,15 @@ static int run_host_zero_copy(bng_ctx *c, int prog, bng_batch *bb, u8 *arena_dev
         int r = dispatch(c, prog, b);
         if (r) return r;
         CU(c, cudaEventRecord(c->ev_comp[buf], sc));
+        mark(sc);
         // ---- out ----
         CU(c, cudaStreamWaitEvent(c->s_out, c->ev_comp[buf], 0));
+        mark(c->s_out);
         if (contiguous) {
             CU(c, cudaMemcpyAsync((u8 *)bb->pkts + (size_t)base * hb, c->zc_hdr[buf], (size_t)cn * hb, cudaMemcpyDeviceToHost,
                                   c->s_out));
         } else {
-            CU(c, run_scatter_frames(c->s_out, c->L.num_sms, chunk_arena, bb->off16 ? c->zc_off[buf] : nullptr,
+            CU(c, run_scatter_frames(c->s_out, c->L.num_sms * (int)c->zc_bps, chunk_arena, bb->off16 ? c->zc_off[buf] : nullptr,
                                      c->zc_len0[buf], bb->stride, cn, hb, c->zc_hdr[buf], first_chunk));
             c->L.launches++;
         }
@@ -1098,9 +1120,18 @@ static int run_host_zero_copy(bng_ctx *c, int prog, bng_batch *bb, u8 *arena_dev
         if (bb->priority)
             CU(c, cudaMemcpyAsync(bb->priority + base, c->zc_prio[buf], (size_t)cn * 4, cudaMemcpyDeviceToHost, c->s_out));
         CU(c, cudaEventRecord(c->ev_out[buf], c->s_out));
+        mark(c->s_out);
     }
     CU(c, cudaStreamSynchronize(c->s_out));
     CU(c, cudaStreamSynchronize(sc));
+    if (trace) {
+        for (u32 k = 0; k < nchunks; k++) {
+            float t[6];
+            for (int j = 0; j < 6; j++) cudaEventElapsedTime(&t[j], tev[0], tev[1 + 6 * k + j]);
+            fprintf(stderr, "zc chunk %u: in %.3f-%.3f  compute %.3f-%.3f  out %.3f-%.3f ms\n", k, t[0], t[1], t[2], t[3], t[4], t[5]);
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    }
     prof_collect(c->L);
     return maybe_compact_locked(c);
 }

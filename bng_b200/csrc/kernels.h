@@ -52,9 +52,9 @@ cudaError_t run_pipeline_tc(Launcher &L, const DevCtx &c, const DevBatch &b);
 cudaError_t run_dhcp_fastpath(Launcher &L, const DevCtx &c, const DevBatch &b);
 
 // header gather / scatter between a pinned host arena and a compact device copy (hostio.cu)
-cudaError_t run_gather_frames(cudaStream_t st, int num_sms, const u8 *arena, const u32 *off16, const u32 *len, u32 stride,
+cudaError_t run_gather_frames(cudaStream_t st, int blocks, const u8 *arena, const u32 *off16, const u32 *len, u32 stride,
                               u32 n, u32 slot, bool tc, u8 *dst, u32 *need);
-cudaError_t run_scatter_frames(cudaStream_t st, int num_sms, u8 *arena, const u32 *off16, const u32 *need, u32 stride, u32 n,
+cudaError_t run_scatter_frames(cudaStream_t st, int blocks, u8 *arena, const u32 *off16, const u32 *need, u32 stride, u32 n,
                                u32 slot, const u8 *src, u32 first_chunk);
 
 // table maintenance (tableops.cu); keys/values/results are device pointers

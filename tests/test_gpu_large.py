@@ -5,7 +5,7 @@
   a million frames in about a second.
 * 2^22-frame batches through size-independent properties: the three ways of
   feeding a batch (device-resident, pageable host staging, pinned zero-copy
-  pipeline in 2^19-frame chunks) must produce identical bytes, verdicts and
+  pipeline in 2^18-frame chunks) must produce identical bytes, verdicts and
   counters; conservation laws tie the counters to the verdicts.
 """
 import numpy as np
@@ -211,7 +211,7 @@ def test_full_size_feed_paths_agree_and_conserve():
     wl = W.pipeline(n, 0, 1, imix=True)
     arena, off16, stride = _arena(wl)
     dev = _gpu_run(wl, arena, off16, stride, 2, "device")
-    pin = _gpu_run(wl, arena, off16, stride, 2, "pinned")  # 8 chunks of 2^19 frames through the 3-stage pipeline
+    pin = _gpu_run(wl, arena, off16, stride, 2, "pinned")  # 16 chunks of 2^18 frames through the 3-stage pipeline
     _same(dev, pin, "pipeline 2^22: device-resident vs pinned zero-copy")
     outs, stats, events, tables = dev
     v = np.concatenate([o[0] for o in outs])
