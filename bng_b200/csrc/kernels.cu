@@ -73,14 +73,22 @@ __device__ __forceinline__ void grouped_select(const Grouped &g, const u32 *cnt,
 #ifndef AS_FULL_HEADER
 #define AS_FULL_HEADER 0
 #endif
-__global__ void __launch_bounds__(BLOCK) k_antispoof(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b) {
+#ifndef AS_MINB
+#define AS_MINB 5
+#endif
+__global__ void __launch_bounds__(BLOCK, AS_MINB) k_antispoof(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b) {
     __shared__ BlockStats bs;
+    __shared__ SpoofQ sqs[BLOCK / 32];
+    static_assert(32 * AS_UNROLL + 32 <= SPOOFQ_CAP, "a trip must fit in what a flush leaves free");
     bstats_init(bs);
+    spoofq_init(sqs);
+    SpoofQ &sq = sqs[threadIdx.x >> 5];
     u32 cfg = *(const u16 *)c.as_config;
     AsCnt cn = {0, 0};
     const u32 lane = threadIdx.x & 31;
     // warp-uniform trip count: the warp decides together whether its frames allow 256-bit loads
     for (u32 base = (blockIdx.x * BLOCK + (threadIdx.x & ~31u)) * AS_UNROLL; base < b.n; base += gridDim.x * BLOCK * AS_UNROLL) {
+        if (*(volatile u32 *)&sq.n >= 32) spoof_flush(c, sq); // (warp-uniform: the queue is the warp's own)
         Hdr64 h[AS_UNROLL];
         u32 len[AS_UNROLL], idx[AS_UNROLL];
         bool act[AS_UNROLL];
@@ -137,10 +145,11 @@ __global__ void __launch_bounds__(BLOCK) k_antispoof(const __grid_constant__ Dev
                     bv[u] = bind_load(tbl_finish<1>(c.bindings, &mk[u], hi[u] + 1, w1, true));
                 }
             }
-            if (act[u]) b.verdict[idx[u]] = (u8)antispoof_eval(c, h[u], len[u], idx[u] + b.base, frame_now(b, idx[u]), bv[u], cfg, cn);
+            if (act[u]) b.verdict[idx[u]] = (u8)antispoof_eval(c, &sq, h[u], len[u], idx[u] + b.base, frame_now(b, idx[u]), bv[u], cfg, cn);
         }
         ascnt_spill(bs, cn);
     }
+    spoof_flush(c, sq);
     ascnt_flush(bs, cn);
     bstats_flush(bs, c.stats);
 }

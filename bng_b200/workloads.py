@@ -72,7 +72,7 @@ def antispoof(n: int, rank=0, world=1, n_subs=10_000, seed=0xB2000002) -> Worklo
     keys, v = S.bindings(n_subs)
     w = Workload("antispoof_64", "antispoof_ingress")
     cfg = np.zeros(1, L.antispoof_config)
-    cfg["default_mode"], cfg["log_violations"] = L.ANTISPOOF_STRICT, 1
+    cfg["default_mode"], cfg["log_violations"] = L.ANTISPOOF_STRICT, 0 if os.environ.get("BNG_EXP_AS_NOLOG") else 1  # (experiment knob)
     w.maps = [("subscriber_bindings", keys[subs], v[subs]), ("antispoof_config", np.zeros(1, "<u4"), cfg)]
     sub = subs[_pick(seed + rank, n, len(subs))]
     r = (S.splitmix64_array(seed ^ 0x77 + rank, n) % np.uint64(1000)).astype(np.int64)
