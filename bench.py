@@ -185,6 +185,19 @@ def host_cpus() -> dict:
     return out
 
 
+PROGRAM_OF = {"pipeline_imix": "pipeline_up", "pipeline_64": "pipeline_up", "antispoof_64": "antispoof_ingress",
+              "nat_steady_64": "nat44_egress", "nat_cold_64": "nat44_egress", "nat_ingress_64": "nat44_ingress",
+              "qos_64": "qos_ingress_prog", "qos_egress_64": "qos_egress_prog", "dhcp": "dhcp_fastpath_prog"}
+
+
+def workload_config(name: str, frames: int, world: int) -> dict:
+    """What the two arms of the bench are run ON — the same dict in the GPU line and in the --impl reference line
+    of the same N (everything that describes HOW an arm ran goes under its own "details" key)."""
+    return {"workload": name, "program": PROGRAM_OF.get(name, name), "frames_per_gpu_per_step": frames, "gpus": world,
+            "subscribers_total": "10 000 (BASELINE config #4), split over the GPUs" if name.startswith("pipeline") else "see bng_b200/workloads.py",
+            "sharding": f"splitmix64(mac) % {world}"}
+
+
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -198,8 +211,10 @@ def run_reference_arm(a):
         "impl": "reference", "metric": METRIC, "value": round(mpps, 3), "unit": "Mpps", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": round(tmax / a.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/u32/u64 integer", "data": "synthetic",
-        "config": {"workload": a.workload, "frames_per_step": n * procs, "host_procs": procs, "host_cpus": cpus,
-                   "sharding": "subscriber MAC hash, one private map set per core"},
+        "config": workload_config(a.workload, a.frames, a.gpus),
+        "details": {"frames_per_step_timed": n * procs, "host_procs": procs, "host_cpus": cpus,
+                    "state": "subscribers split over the processes by MAC hash, one private map set per process",
+                    "note": "a bounded sample of the workload per step (cpu_baseline.sample); under torchrun rank 0 alone runs"},
         "cpu_baseline": {"value": round(mpps, 3), "unit": "Mpps", "cores": procs,
                          "kind": "reference" if kind == "reference" else "port",
                          "sample": f"{procs} processes (sched_getaffinity {cpus['sched_affinity']}, cgroup quota "
@@ -646,16 +661,16 @@ def run_gpu(a):
             "metric": METRIC, "value": head["value"], "unit": "Mpps", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/u32/u64 integer", "data": "synthetic",
-            "config": {"workload": wl.name, "program": wl.prog, "frames_per_gpu_per_step": head["frames_per_gpu_per_step"],
-                       "subscribers_this_gpu": wl.n_subs_local, "subscribers_total": "10 000 (BASELINE config #4), split over the GPUs"
-                       if wl.name.startswith("pipeline") else "see workloads.py",
-                       "sharding": f"splitmix64(mac) % {world}" if not G.as_shard else f"diagnostic: shard {G.as_shard[0]} of {G.as_shard[1]} alone", "tables": head["tables"],
-                       "avg_frame_bytes": round(float(wl.lens.mean()), 1), "frame_align": a.align if wl.imix else live_stride(wl),
-                       "step_ms_min_med_max": [round(float(x), 4) for x in
-                                               (min(head["step_ms"]), float(np.median(head["step_ms"])), max(head["step_ms"]))],
-                       "step_ms_all": head["step_ms"],
-                       "l2_policy": "inputs larger than L2 (frame arena + tables) and rewritten between steps",
-                       **wl.info},
+            "config": workload_config(wl.name, head["frames_per_gpu_per_step"], world),
+            "details": {"frames_this_gpu": head["frames_per_gpu_per_step"], "subscribers_this_gpu": wl.n_subs_local,
+                        "sharding": f"splitmix64(mac) % {world}" if not G.as_shard else f"diagnostic: shard {G.as_shard[0]} of {G.as_shard[1]} alone",
+                        "tables": head["tables"], "avg_frame_bytes": round(float(wl.lens.mean()), 1),
+                        "frame_align": a.align if wl.imix else live_stride(wl),
+                        "step_ms_min_med_max": [round(float(x), 4) for x in
+                                                (min(head["step_ms"]), float(np.median(head["step_ms"])), max(head["step_ms"]))],
+                        "step_ms_all": head["step_ms"],
+                        "l2_policy": "inputs larger than L2 (frame arena + tables) and rewritten between steps",
+                        **wl.info},
             "wire_gbps": round(head["value"] * 1e6 * float(wl.lens.mean()) * 8 / 1e9, 1),
             "roofline": head["roofline"], "cpu_baseline": cpu,
             "e2e": e2e, "e2e_header_split": e2e_extra, "host_affinity": numa,

@@ -560,27 +560,53 @@ __global__ void __launch_bounds__(BLOCK) k_rs_scatter(const u32 *keys, const u32
     }
 }
 
-// group heads: positions where the sorted key changes (any order; groups are independent)
+// group heads: positions where the sorted key changes (any order; groups are independent).
+// 16 keys per thread and trip (four 128-bit loads in flight), one atomic per warp for the heads its lanes found.
 __global__ void __launch_bounds__(BLOCK) k_heads(const __grid_constant__ Grouped g, u32 *seg, u32 *cnt) {
     const u32 *skey, *sval_unused;
     pdl_wait();
     grouped_select(g, cnt, skey, sval_unused);
-    u32 m = cnt[CNT_M];
+    const u32 m = cnt[CNT_M];
     const u32 kmask = key_mask_of(g.kshift);
-    for (u32 j = 4 * (blockIdx.x * BLOCK + threadIdx.x); j < m; j += 4 * gridDim.x * BLOCK) { // 4 keys per thread
-        u32 k[4], prev = j ? skey[j - 1] & kmask : ~(skey[0] & kmask);
-        if (j + 3 < m) {
-            const uint4 v = *(const uint4 *)(skey + j);
-            k[0] = v.x, k[1] = v.y, k[2] = v.z, k[3] = v.w;
+    const u32 lane = threadIdx.x & 31;
+    for (u32 wbase = 16 * (blockIdx.x * BLOCK + (threadIdx.x & ~31u)); wbase < m; wbase += 16 * gridDim.x * BLOCK) { // warp-uniform
+        const u32 j = wbase + 16 * lane;
+        u32 k[16];
+        u32 prev = 0;
+        if (j < m) prev = j ? skey[j - 1] & kmask : ~(skey[0] & kmask);
+        if (j + 15 < m) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint4 v = *(const uint4 *)(skey + j + 4 * q);
+                k[4 * q] = v.x, k[4 * q + 1] = v.y, k[4 * q + 2] = v.z, k[4 * q + 3] = v.w;
+            }
         } else {
 #pragma unroll
-            for (int t = 0; t < 4; t++) k[t] = j + t < m ? skey[j + t] : 0;
+            for (int t = 0; t < 16; t++) k[t] = j + t < m ? skey[j + t] : 0;
         }
+        u32 hm = 0;
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-            k[t] &= kmask;
-            if (j + t < m && k[t] != prev) seg[atomicAdd(&cnt[CNT_NSEG], 1u)] = j + t;
-            prev = k[t];
+        for (int t = 0; t < 16; t++) {
+            const u32 kk = k[t] & kmask;
+            if (j + t < m && kk != prev) hm |= 1u << t;
+            prev = kk;
+        }
+        const u32 mine = __popc(hm);
+        u32 inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 x = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (u32)o) inc += x;
+        }
+        const u32 total = __shfl_sync(0xffffffffu, inc, 31);
+        if (!total) continue;
+        u32 basepos = 0;
+        if (lane == 31) basepos = atomicAdd(&cnt[CNT_NSEG], total);
+        basepos = __shfl_sync(0xffffffffu, basepos, 31) + inc - mine;
+        while (hm) {
+            const u32 t = __ffs(hm) - 1;
+            hm &= hm - 1;
+            seg[basepos++] = j + t;
         }
     }
 }
@@ -979,7 +1005,7 @@ static cudaError_t group_by_key(Launcher &L, u32 n, u64 key_space, u32 kshift, G
     g.passes = passes;
     g.kshift = kshift;
     *out = g;
-    launch_dep(k_heads, grid_for(L, n, 8), BLOCK, L.stream, g, s.qslot, s.counters);
+    launch_dep(k_heads, grid_for(L, (n + 15) / 16, 4), BLOCK, L.stream, g, s.qslot, s.counters);
     L.launches++;
     prof_end(L);
     return cudaGetLastError();

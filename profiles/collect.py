@@ -112,7 +112,19 @@ def main():
         rc = j.get("reference_capacities")
         if rc:
             L += ["| same, every table at the reference's compile-time capacity | %.0f Mpps, %.4f ms/step, `%s` |" % (
-                rc["value"], rc["ms_per_step"], json.dumps(rc.get("kernels_ms")))]
+                rc["value"], rc["ms_per_step"], json.dumps((rc.get("roofline") or {}).get("kernels_ms")))]
+        cp = j.get("control_plane") or {}
+        if cp:
+            L += ["| one `Map.Put` (`bng_map_update`, synchronous) | median %s us, p99 %s us |" % (
+                      cp.get("put_single_us", {}).get("median"), cp.get("put_single_us", {}).get("p99")),
+                  "| staged upserts (`bng_map_update_staged` x %s + one `bng_sync`) | %s puts/s (staging %s us each through ctypes, apply %s ms) |" % (
+                      cp.get("put_staged", {}).get("n"), cp.get("put_staged", {}).get("puts_per_s"),
+                      cp.get("put_staged", {}).get("stage_us_each"), cp.get("put_staged", {}).get("apply_ms")),
+                  "| batch upsert (`bng_map_update_batch`, %s entries) | %s puts/s |" % (
+                      cp.get("put_batch", {}).get("n"), cp.get("put_batch", {}).get("puts_per_s")),
+                  "| expiry sweep (`bng_sweep`, %s slots, %s live) | %s ms expiring %s sessions; scan only %s ms = %s GB/s |" % (
+                      cp.get("sweep", {}).get("slots"), cp.get("sweep", {}).get("live_sessions"), cp.get("sweep", {}).get("ms"),
+                      cp.get("sweep", {}).get("expired"), cp.get("sweep", {}).get("scan_only_ms"), cp.get("sweep", {}).get("scan_GBps"))]
         L += ["", "### The other BASELINE configs, from the same line (`workloads`)", "",
               "| workload | Mpps | ms/step | dominant kernel | its ms | frac of HBM peak | DRAM bytes/launch (ncu) |", "|---|---|---|---|---|---|---|"]
         for w, e in (j.get("workloads") or {}).items():
@@ -135,6 +147,19 @@ def main():
         j = json.loads(open(p).readline())
         L += ["", "Reference arm (`bench.py --impl reference`, `oracle/_ref` = the reference's eBPF C): **%.1f Mpps** on %s "
               "host threads (%s)." % (j["value"], j["cpu_baseline"]["cores"], j["cpu_baseline"].get("sample", ""))]
+    rows = []
+    for tag, f in (("1", f"{R}_bench.json"), ("2", f"{R}_bench_2gpu.json"), ("4", f"{R}_bench_4gpu.json"), ("8", f"{R}_bench_8gpu.json")):
+        pp = os.path.join(DST, f)
+        if os.path.exists(pp) and open(pp).readline().strip():
+            jj = json.loads(open(pp).readline())
+            pg = jj.get("per_gpu_constant") or {}
+            rows.append("| %s | %.0f | %.4f | %s | %.0f | %s | %s |" % (
+                jj["n_gpus"], jj["value"], jj["ms_per_step"], (jj.get("details") or jj["config"]).get("subscribers_this_gpu"), jj["e2e"]["value"],
+                pg.get("value"), (jj.get("stats_allreduce") or {}).get("matches_torch_allreduce")))
+    if len(rows) > 1:
+        L += ["", "## GPUs (torchrun, one rank per GPU, shard = splitmix64(mac) % N; each line measured on its own box)", "",
+              "| N | Mpps (all GPUs) | ms/step (max over ranks) | subscribers on rank 0 | e2e Mpps | 10 k subscribers PER GPU: Mpps | `bng_sync_reduce` == torch all-reduce |",
+              "|---|---|---|---|---|---|---|"] + rows
     p = os.path.join(DST, f"{R}_batch_sweep.jsonl")
     if os.path.exists(p):
         L += ["", "## Batch size (default workload, `tools/batch_sweep.sh`)", "",
