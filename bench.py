@@ -490,7 +490,7 @@ def e2e_leg(a, live):
     val = run(arena_h, off_h, stride, restore_host, total16_e * 16)
     per_frame_in = float(np.minimum(lens_e, hb).mean())
     h2d = int(n_e * per_frame_in) + n_e * 4 + (n_e * 4 if off16 is not None else 0)
-    d2h = int(n_e * (per_frame_in - (16 if tc_prog else 0))) + n_e + (n_e * 4 if not tc_prog else 0)
+    d2h = int(n_e * per_frame_in) + n_e + (n_e * 4 if not tc_prog else 0)  # (whole 64-byte header slots go back: one write per frame)
     out = {"value": round(val, 2), "unit": "Mpps", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "steps": e2e_steps, "frames_per_step": n_e, "arena": "bng_host_alloc(): 2 MB huge pages registered with CUDA",
            "layout": "pinned host arena, full frames; only the bytes a program can touch cross PCIe"}

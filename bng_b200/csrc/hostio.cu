@@ -8,7 +8,8 @@
 // How many bytes can a program touch?  The TC programs (antispoof, QoS, NAT44, the pipeline) read at most
 // the Ethernet + IPv4 header and 20 bytes of L4 header at 14 + ihl*4: 54 bytes when ihl = 5 — one 64-byte
 // slot covers it — and up to 14 + 60 + 20 = 94 bytes when the header carries options (bpf/nat44.c:606-653,
-// 752-798).  Compact slots are therefore 96 bytes apart; the first 64 bytes are always moved, the two
+// 752-798).  Compact slots are therefore 96 bytes apart; the first 64 bytes are always moved (both ways: a single
+// 64-byte PCIe write per frame costs less than the 48 bytes that can change sent as two), the two
 // further 16-byte chunks only for frames whose ihl says the L4 header reaches them.  The TC programs never
 // write below byte 16 — except nat44_egress on a frame with ihl = 0, whose "TCP source port" is bytes
 // 14-15 (the L4 header then overlaps the IP header); such frames are flagged so the scatter writes their
