@@ -7,6 +7,7 @@ R=${1:-r02}
 O=gpurun_out/$R/cap
 mkdir -p $O
 B="--steps 3 --warmup 3 --no-cpu --no-extra --e2e-steps 1"
+if [ -z "${SKIP_NCU:-}" ]; then   # SKIP_NCU=1: only the plain bench lines (parts 3 and 4)
 # 1. launch list: every kernel of a short headline run with its device time (cold-cache, serialised:
 #    compare SHARES, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_" -c 400 --csv \
@@ -22,6 +23,7 @@ for spec in "dhcp k_dhcp_fastpath 4" "antispoof_64 k_antispoof 4" "nat_cold_64 k
     ncu --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c 1 -o $O/$1 -f \
         python bench.py --workload $1 $B > $O/$1.log 2>&1
 done
+fi
 # 3. clocks during a plain (unprofiled) run, next to the number itself
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap \
     --format=csv -lms 200 > $O/clocks.csv &
