@@ -385,94 +385,8 @@ __global__ void __launch_bounds__(DH_TILE) k_dhcp_fastpath(const __grid_constant
     bstats_flush(bs, c.stats);
 }
 
-// Double-buffered variant (A/B knob DHCP_DB): two staging slots per thread; the bulk load of tile i+1 is issued
-// before the program runs on tile i, the bulk store of tile i drains while tile i+1 is processed.  Tiles stay
-// block-synchronous (one mbarrier per buffer), so a tile's frames are still moved as one contiguous run.
-#ifndef DHCP_DB
-#define DHCP_DB 0
-#endif
-#define DH_TILE2 64
-__global__ void __launch_bounds__(DH_TILE2) k_dhcp_fastpath_db(const __grid_constant__ DevCtx c, const __grid_constant__ DevBatch b) {
-    extern __shared__ __align__(128) u8 stage[]; // 2 x DH_TILE2 * DH_SLOT
-    __shared__ BlockStats bs;
-    __shared__ u64 bar[2];
-    bstats_init(bs);
-    const u32 bar_a[2] = {(u32)__cvta_generic_to_shared(&bar[0]), (u32)__cvta_generic_to_shared(&bar[1])};
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a[0]), "r"(DH_TILE2));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a[1]), "r"(DH_TILE2));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    u8 *slot[2] = {stage + (size_t)threadIdx.x * DH_SLOT, stage + (size_t)(DH_TILE2 + threadIdx.x) * DH_SLOT};
-    const u32 slot_a[2] = {(u32)__cvta_generic_to_shared(slot[0]), (u32)__cvta_generic_to_shared(slot[1])};
-    u32 phase[2] = {0, 0};
-    const u32 step = gridDim.x * DH_TILE2;
-    auto issue = [&](u32 base, int x, u32 &len, u8 *&g, u32 &nbytes, u32 &present, bool &act) {
-        const u32 i = base + threadIdx.x;
-        act = base < b.n && i < b.n;
-        len = act ? b.len[i] : 0;
-        g = act ? frame_ptr(b, i) : b.pkts;
-        present = frame_dlen(b, len);
-        nbytes = ((present < DH_SLOT ? present : DH_SLOT) + 15u) & ~15u;
-        if (nbytes > DH_SLOT) nbytes = DH_SLOT;
-        if (nbytes) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a[x]), "r"(nbytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(slot_a[x]),
-                         "l"(g), "r"(nbytes), "r"(bar_a[x])
-                         : "memory");
-        } else {
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a[x]) : "memory");
-        }
-    };
-    u32 len[2], nbytes[2], present[2];
-    u8 *g[2];
-    bool act[2];
-    u32 base = blockIdx.x * DH_TILE2;
-    if (base < b.n) issue(base, 0, len[0], g[0], nbytes[0], present[0], act[0]);
-    for (int it = 0; base < b.n; it++, base += step) {
-        const int x = it & 1, y = x ^ 1;
-        // my store out of slot y (tile it-1) has read the slot: it may be overwritten
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        if (base + step < b.n) issue(base + step, y, len[y], g[y], nbytes[y], present[y], act[y]);
-        u32 done = 0;
-        while (!done) {
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                "selp.u32 %0, 1, 0, p;\n\t}"
-                : "=r"(done)
-                : "r"(bar_a[x]), "r"(phase[x])
-                : "memory");
-        }
-        phase[x] ^= 1;
-        u8 *mine = slot[x];
-        const u32 i = base + threadIdx.x;
-        bool direct = false;
-        if (act[x] && present[x] > DH_SLOT) {
-            u32 et = rd16(mine, 12), l3 = 14;
-            if (et == 0x0081u || et == 0xA888u) {
-                l3 = 18;
-                if (rd16(mine, 16) == 0x0081u) l3 = 22;
-            }
-            direct = l3 + (u32)(mine[l3] & 0x0f) * 4 + 8 + 240 + 64 > DH_SLOT;
-        }
-        if (act[x]) {
-            u32 l = len[x];
-            const u32 l0 = l;
-            int v = dhcp_one(c, bs, direct ? g[x] : mine, l, frame_dlen(b, l0), frame_now(b, i));
-            b.verdict[i] = (u8)v;
-            if (l != l0) b.len[i] = l;
-        }
-        if (nbytes[x] && !direct) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g[x]), "r"(slot_a[x]), "r"(nbytes[x]) : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-    }
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    bstats_flush(bs, c.stats);
-}
+// (A double-buffered variant — two staging slots per thread, the load of tile i+1 issued before the program runs on
+// tile i — was measured in round 2 and dropped: 0.97 -> 1.43 ms per 2^22 requests, profiles/r02_notes.md.)
 
 cudaError_t run_dhcp_fastpath(Launcher &L, const DevCtx &c, const DevBatch &b) {
     const int smem = DH_TILE * DH_SLOT;
@@ -481,22 +395,6 @@ cudaError_t run_dhcp_fastpath(Launcher &L, const DevCtx &c, const DevBatch &b) {
         if (e != cudaSuccess) return e;
         L.dhcp_smem_set = 1;
     }
-#if DHCP_DB
-    const int smem2 = 2 * DH_TILE2 * DH_SLOT;
-    if (L.dhcp_smem_set < 2) {
-        cudaError_t e = cudaFuncSetAttribute(k_dhcp_fastpath_db, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-        if (e != cudaSuccess) return e;
-        L.dhcp_smem_set = 2;
-    }
-    long want2 = ((long)b.n + DH_TILE2 - 1) / DH_TILE2;
-    long cap2 = (long)L.num_sms * 4;
-    int grid2 = (int)(want2 < cap2 ? (want2 < 1 ? 1 : want2) : cap2);
-    prof_begin(L, "k_dhcp_fastpath");
-    k_dhcp_fastpath_db<<<grid2, DH_TILE2, smem2, L.stream>>>(c, b);
-    prof_end(L);
-    L.launches++;
-    return cudaGetLastError();
-#endif
     long want = ((long)b.n + DH_TILE - 1) / DH_TILE;
     long cap = (long)L.num_sms * 4; // 4 x 50 KB of staging per SM
     int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);

@@ -19,12 +19,16 @@
 //             without a key never enter the sort, and every later kernel reads
 //             its element count from device memory, so an all-hit batch costs
 //             a few empty launches and no host round trip.
-//   RESOLVE   one warp per subscriber walks its group 32 frames at a time
-//             (two chunks' loads in flight): lanes gather the frames' lengths
-//             in parallel, new flows are created in index order, and the
-//             token bucket is applied with warp-uniform fast paths (whole
-//             chunk passes / whole chunk drops) before falling back to a
-//             lane-by-lane scan.
+//   RESOLVE   one warp per subscriber walks its group: 256 (key + length, frame)
+//             pairs per sweep are staged in shared memory with coalesced
+//             loads (the frame length rides in the spare bits of the ordering
+//             key), new flows are created warp-cooperatively in index order,
+//             and the token bucket is applied with warp-uniform fast paths
+//             (whole chunk passes / whole chunk drops) before falling back to
+//             a lane-by-lane scan.
+// The kernels after CLASSIFY are launched with programmatic stream
+// serialisation (launch_dep / pdl_wait): their launch overlaps the tail of the
+// kernel before them.
 #include <string.h>
 
 #include "kernels.h"
@@ -615,9 +619,9 @@ __global__ void __launch_bounds__(BLOCK) k_heads(const __grid_constant__ Grouped
 // RESOLVE: one TEAM (a single warp in every program as built: concurrency across groups hides more latency
 // than parallelism inside one; the code is written for any multiple of 32) per group, frames in index order.
 //   stage   all threads copy the group's (value, length) pairs into shared memory, RS_STAGE frames per
-//           sweep: the dependent gather sval -> len[idx] runs on every lane at once instead of 32 frames
-//           per round trip of a single warp (a fat group — 3 000 frames per subscriber when 10 k subscribers
-//           are sharded over 8 GPUs — used to be ~50 serial round trips of one warp).
+//           sweep, with coalesced loads: the length comes out of the key word (DevBatch.kshift), so nothing
+//           depends on the frame index just loaded (a fat group — 3 000 frames per subscriber when 10 k
+//           subscribers are sharded over 8 GPUs — used to be ~50 serial round trips of one warp).
 //   NAT     warp 0 creates the new flows (MISS_FLAG) chunk by chunk, warp-cooperatively when the chunk's
 //           flows provably do not interact (nat_chunk_coop), else one lane at a time in index order.
 //   QOS     warp 0 applies token_bucket_check() to the staged lengths with warp-uniform fast paths
