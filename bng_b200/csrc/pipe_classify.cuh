@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(BLOCK, CLASSIFY_BPS(AS))
             }
             __syncwarp();
             bv.has = bind != nullptr;
-            v = antispoof_eval(c, nullptr, h, dlen, i + b.base, frame_now(b, i), bv, as_cfg, cn); // (the clock is read where it is used: no live register)
+            v = antispoof_eval(c, nullptr, h, dlen, i + b.base, act ? frame_now(b, i) : 0, bv, as_cfg, cn); // (the clock is read where it is used: no live register)
             __syncwarp();
         }
         const bool alive = act && v != TC_SHOT && ip4;
