@@ -653,9 +653,9 @@ def run_gpu(a):
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
         c_n = 1 << 20
-        mpps, kind, tt = cpu_run(a.workload, c_n, 1, 4, 1)
+        mpps, kind, tt = cpu_run(a.workload, c_n, 1, 20, 1)  # ~10 s of one core
         cpu = {"value": round(mpps, 3), "unit": "Mpps", "cores": 1, "kind": kind,
-               "sample": f"1 core x {c_n} frames x 4 passes of {a.workload} ({tt:.1f} s), reference eBPF C run natively"}
+               "sample": f"1 core x {c_n} frames x 20 passes of {a.workload} ({tt:.1f} s), reference eBPF C run natively"}
     if rank == 0:
         out = {
             "metric": METRIC, "value": head["value"], "unit": "Mpps", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
