@@ -62,10 +62,10 @@ def _oracle_run(wl, arena, off16, stride, steps):
     return outs, stats, events, tables
 
 
-def _gpu_run(wl, arena, off16, stride, steps, mode):
+def _gpu_run(wl, arena, off16, stride, steps, mode, sizing=None):
     import torch
     from bng_b200 import MEM_DEVICE, MEM_HOST, Dataplane
-    dp = Dataplane(max_batch=wl.n, **W.sizing(wl))
+    dp = Dataplane(max_batch=wl.n, **(sizing or W.sizing(wl)))
     try:
         _load(dp, wl)
         for prog, h, l in wl.prewarm:
@@ -194,6 +194,19 @@ def test_jumbo_lengths_against_reference(case):
     ref = _oracle_run(wl, arena, off16, stride, 2)
     gpu = _gpu_run(wl, arena, off16, stride, 2, "device")
     _same(ref, gpu, f"jumbo lengths / {case}: reference oracle vs gpu")
+
+
+@pytest.mark.parametrize("case", ["pipeline_up", "qos"])
+def test_tables_too_large_for_packed_keys(case):
+    """Subscriber tables beyond 2^21 slots: the ordering key needs more than KEY_BITS bits, the frame length no longer
+    rides in it (DevBatch.kshift = 0, three radix passes) and the ordered phase looks lengths up.  Same results."""
+    n = 1 << 16
+    wl = W.qos(n, 0, 1, n_subs=500) if case == "qos" else W.pipeline(n, 0, 1, n_subs=500)
+    arena, off16, stride = _arena(wl)
+    ref = _oracle_run(wl, arena, off16, stride, 2)
+    big = dict(W.sizing(wl), max_subscribers=(1 << 21) + 4096)  # capacity = 2 x that, rounded up: 2^23 slots
+    gpu = _gpu_run(wl, arena, off16, stride, 2, "device", sizing=big)
+    _same(ref, gpu, f"unpacked keys / {case}: reference oracle vs gpu")
 
 
 @pytest.mark.parametrize("mode", ["device", "pinned"])
