@@ -5,6 +5,8 @@ import pytest
 
 from bng_b200 import layouts as L
 from bng_b200 import synth as S
+from bng_b200 import workloads as W
+from bng_b200.layouts import as_bytes
 
 pytestmark = pytest.mark.gpu
 
@@ -182,3 +184,43 @@ def test_update_batch_with_repeated_keys_applies_in_order():
             assert bytes(dp.lookup("subscriber_bindings", keys[i])) == bytes(L.as_bytes(v[i:i + 1])[0])
     finally:
         dp.close()
+
+
+@pytest.mark.parametrize("name,ring", [("antispoof_64", "spoof_events"), ("pipeline_64", "spoof_events"), ("nat_cold_64", "nat_log_rb")])
+def test_event_staging_ring_overflow_is_counted_not_fatal(name, ring):
+    """A staging ring smaller than what one batch logs: the records that found a slot come out, the rest are counted
+    in bng_events_lost, and nothing else about the batch changes (verdicts, counters — packets_logged counts a
+    violation whether or not its record could be written, bpf/antispoof.c:171-174)."""
+    from bng_b200 import Dataplane
+    n = 1 << 13 if name == "nat_cold_64" else 1 << 15  # (nat_log_rb also has the reference's 1 MiB ring rule: stay under it)
+    wl = W.build(name, n)
+
+    def run(cap):
+        dp = Dataplane(max_batch=n, event_capacity=cap, **W.sizing(wl))
+        try:
+            for m, k, val in wl.maps:
+                assert dp.update_batch(m, as_bytes(k), as_bytes(val)) == 0, m
+            for prog, h, l in wl.prewarm:
+                dp.run(prog, h.reshape(-1).copy(), l.copy(), wl.now0 - 1, stride=64)
+                dp.drain("nat_log_rb")
+            lost0 = dp.events_lost
+            a = np.ascontiguousarray(wl.headers).reshape(-1).copy()
+            v = dp.run(wl.prog, a, wl.lens.copy(), wl.now0, stride=wl.headers.shape[1])
+            ev = dp.drain(ring)
+            stats = {m: dp.stats(m).copy() for m in ("antispoof_stats", "nat_stats_map", "qos_stats_map")}
+            return np.asarray(v).copy(), a, ev, dp.events_lost - lost0, stats
+        finally:
+            dp.close()
+
+    v_big, a_big, ev_big, lost_big, st_big = run(1 << 18)
+    assert lost_big == 0 and ev_big.shape[0] > 200, ev_big.shape
+    cap = 96
+    v_small, a_small, ev_small, lost_small, st_small = run(cap)
+    assert ev_small.shape[0] == cap
+    assert lost_small == ev_big.shape[0] - cap
+    assert np.array_equal(v_big, v_small) and np.array_equal(a_big, a_small)
+    for m in st_big:
+        assert np.array_equal(st_big[m], st_small[m]), m
+    # every record that did come out is one of the records of the unconstrained run
+    big = {bytes(r) for r in ev_big}
+    assert all(bytes(r) in big for r in ev_small)
