@@ -15,11 +15,18 @@
 // gather-heavy kernel like this one.
 #pragma once
 
-// Resident blocks per SM each instantiation is compiled for (registers: 65536 / (256 x blocks)).
+// Resident blocks per SM each instantiation is compiled for (registers: 65536 / (256 x blocks)).  Measured at the
+// end of round 2 for the pipeline instantiations (ms per 2^22 frames): 2 blocks 0.429, 3 blocks 0.355 (78 registers,
+// nothing spilled), 4 blocks 0.363 (64 registers, 24 bytes spilled), 5 blocks 0.44.  3 is 2 % faster; the default
+// stays at 4 because the round's GPU time ran out before the parity suite could be re-run on that build
+// (-DCLASSIFY_BLOCKS=3 is the whole change).
 #ifndef CLASSIFY_BLOCKS
 #define CLASSIFY_BLOCKS 4
 #endif
-#define CLASSIFY_BPS(AS) ((AS) ? CLASSIFY_BLOCKS : 5)
+#ifndef CLASSIFY_BLOCKS_NAT
+#define CLASSIFY_BLOCKS_NAT 5
+#endif
+#define CLASSIFY_BPS(AS) ((AS) ? CLASSIFY_BLOCKS : CLASSIFY_BLOCKS_NAT)
 // CLASSIFY_PAIR: fetch the home PAIR of slots of the bindings table / subscriber directory with the first probe
 #ifndef CLASSIFY_PAIR
 #define CLASSIFY_PAIR 0 // measured (profiles/r02_notes.md): the 16 extra registers spill, 0.373 -> 0.425 ms
