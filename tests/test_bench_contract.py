@@ -30,6 +30,10 @@ def test_reference_arm_line(workload):
         assert k in j, k
     assert j["impl"] == "reference" and j["value"] > 0 and j["unit"] == "Mpps"
     assert j["config"]["workload"] == workload
+    # both arms describe WHAT they ran with the same dict (the driver compares them); how an arm ran is under "details"
+    sys.path.insert(0, ROOT)
+    import bench
+    assert j["config"] == bench.workload_config(workload, 1 << 22, 1) and "host_procs" in j["details"]
     assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"]["value"] == j["value"] and j["e2e"]["h2d_bytes_per_step"] == 0 and j["gpu_launches"] == 0
 
